@@ -1,0 +1,166 @@
+/*
+ * liblkg -- C ABI of the B200-native LiteralKG message-passing + scoring path.
+ *
+ * The reference (NSLab-CUK/LiteralKG) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md 8(b)); the drop-in surface is the Python class API of model.py / gate.py /
+ * dataloader.py.  This header is the boundary underneath that surface: every entry point below
+ * replaces the body of one reference function (cited as file:line next to it) and is what a
+ * maintainer binds with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no C++ / torch types;
+ *   - every function returns an lkg_status (0 = ok, < 0 = error); lkg_last_error() gives the
+ *     thread-local message of the last failure;
+ *   - all pointers are DEVICE pointers unless a parameter is documented as "host";
+ *   - buffers are borrowed for the duration of the call: the library never allocates, frees or
+ *     retains device memory (callers size scratch with the *_workspace_bytes queries);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host unless
+ *     documented otherwise, re-entrant, and keep no global mutable state;
+ *   - row-major matrices; `ld*` arguments are leading dimensions in ELEMENTS;
+ *   - sm_100 only: there is no CPU or other-architecture fallback by design.
+ */
+#ifndef LKG_H_
+#define LKG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LKG_ABI_VERSION 1
+
+typedef enum {
+    LKG_OK = 0,
+    LKG_ERR_INVALID = -1,      /* bad argument / shape / alignment */
+    LKG_ERR_UNSUPPORTED = -2,  /* shape outside the compiled kernel envelope */
+    LKG_ERR_CUDA = -3,         /* CUDA runtime / launch failure (message has the cudaError) */
+    LKG_ERR_ARCH = -4,         /* device is not sm_100 */
+    LKG_ERR_WORKSPACE = -5     /* workspace too small */
+} lkg_status;
+
+/* CSR plan of the knowledge graph, all arrays int32, built once per edge list by lkg_plan_build.
+ *   "att" order: the E kept triples sorted by (head, relation, tail); used by the attention update,
+ *                where tanh(e_h + e_r) is shared by a whole (head, relation) run;
+ *   "agg" order: the nnz UNIQUE (head, tail) pairs sorted by (head, tail) == the coalesced A_in of
+ *                the reference (model.py:466-471); att_seg maps every triple to its pair. */
+typedef struct {
+    int64_t n_entities;
+    int64_t n_edges;            /* E   : triples kept (relation filter applied)            */
+    int64_t nnz;                /* E'  : unique (h,t) pairs                                  */
+    int32_t n_relations;
+    const int32_t* att_rowptr;  /* [N+1] */
+    const int32_t* att_tail;    /* [E]   */
+    const int32_t* att_rel;     /* [E]   */
+    const int32_t* att_seg;     /* [E]   index into the agg arrays                          */
+    const int32_t* rowptr;      /* [N+1] */
+    const int32_t* col;         /* [nnz] */
+} lkg_graph;
+
+/* K-concatenated row-major operand: logical A[m, :] = [ src0[row(m), 0:k0] | src1[row(m), 0:k1] | ... ]
+ * where row(m) = rows ? rows[m] : m.  Used for the virtual torch.cat of gate.py:23 / model.py:309. */
+#define LKG_MAX_SEGMENTS 4
+typedef struct {
+    int32_t n_segments;
+    const float* ptr[LKG_MAX_SEGMENTS];
+    int64_t ld[LKG_MAX_SEGMENTS];
+    int32_t k[LKG_MAX_SEGMENTS];
+    const int64_t* rows;        /* optional gather indices [M] (nullable) */
+} lkg_operand;
+
+typedef enum { LKG_ACT_NONE = 0, LKG_ACT_LEAKY_RELU = 1 } lkg_activation;
+typedef enum { LKG_AGG_GCN = 0, LKG_AGG_GRAPHSAGE = 1, LKG_AGG_BI_INTERACTION = 2 } lkg_aggregator;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int lkg_abi_version(void);
+const char* lkg_last_error(void);
+/* LKG_OK iff `device` is an sm_100 GPU (B200).  Host call. */
+int lkg_device_check(int device);
+
+/* ---- graph plan: replaces DataLoader.construct_data's tensor products + the coalesce/sort that
+ *      torch.sparse.softmax performs inside update_attention (dataloader.py:369-424,
+ *      model.py:462-470) ------------------------------------------------------------------------ */
+int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, size_t* bytes /*host out*/);
+/* h,t,r: int64 [n_edges] in file order.  rel_keep: optional uint8 [n_relations]; triples whose
+ * relation has rel_keep == 0 are dropped (a `relations` list that omits ids, model.py:451).
+ * Outputs are caller-allocated: att_* and col sized for n_edges, rowptrs for n_entities+1,
+ * coo_rows/coo_cols (nullable) int64 [n_edges] receive the coalesced COO indices, file_seg
+ * (nullable) int32 [n_edges] receives for every INPUT triple the index of its (h,t) pair (-1 if
+ * dropped), counts_dev int64[3] receives {E kept, nnz, number of out-of-range ids (must be 0)}. */
+int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
+                   int64_t n_entities, int32_t n_relations, const uint8_t* rel_keep,
+                   int32_t* att_rowptr, int32_t* att_tail, int32_t* att_rel, int32_t* att_seg,
+                   int32_t* rowptr, int32_t* col, int64_t* coo_rows, int64_t* coo_cols,
+                   int32_t* file_seg, int64_t* counts_dev, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* values_out[file_seg[i]] += values_in[i]: imports an un-coalesced COO value list (e.g. an A_in taken
+ * from a checkpoint, model.py:257-261) into plan order, summing duplicates like coalesce(). */
+int lkg_segment_scatter_add(const float* values_in, const int32_t* file_seg, int64_t n_edges,
+                            float* values_out, int64_t nnz, void* stream);
+
+/* Initial A_in = sum_r D_r^-1 A_r (random-walk) or D_r^-1/2 A_r D_r^-1/2 (symmetric, row sums on
+ * both sides), float64 accumulation then fp32 cast (dataloader.py:449-495).  values: [nnz];
+ * scratch: float64 [nnz] accumulator. */
+int lkg_laplacian_init(const lkg_graph* g, int symmetric, float* values, double* scratch, void* stream);
+
+/* ---- attention update (model.py:430-471): per triple v = sum_d e_t[d]*tanh(e_h[d]+e_r[d]) on the
+ *      raw tables, duplicate (h,t) logits summed, max-subtracted softmax per head row.
+ *      values: [nnz] in agg order. ------------------------------------------------------------ */
+int lkg_attn_workspace_bytes(size_t* bytes /*host out*/);
+int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t ld_entity,
+                    const float* relation, int64_t ld_relation, int32_t dim,
+                    float* values, void* workspace, void* stream);
+
+/* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) (torch Linear layout: B is [out, in]) ------- */
+/* out = act(A @ B^T + bias)  (linear_gat model.py:309-310; h0 residual pre-projection) */
+int lkg_linear_fwd(const lkg_operand* a, int64_t m, const float* b, int64_t ldb, int32_t n,
+                   const float* bias /*nullable [n]*/, int32_t activation,
+                   float* out, int64_t ldo, void* stream);
+/* Literal gate (gate.py:22-28 / :45-51).  `x` is the K-concatenation (entity | literals...);
+ * w_pair is [2*dim, K] with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of
+ * output j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]).  x_ent is the entity table used
+ * by the mix  out = (1 - z) * x_ent + z * tanh(g). */
+int lkg_gate_fwd(const lkg_operand* x, int64_t m, const float* w_pair, int64_t ldw,
+                 const float* bias_pair, int32_t dim, const float* x_ent, int64_t ld_ent,
+                 float* out, int64_t ldo, void* stream);
+
+/* ---- one aggregator layer, forward (model.py:101-164 + F.normalize of model.py:305) ----------
+ * side = A_in @ ego fused with the combine, LeakyReLU, LayerNorm, optional dropout mask and the
+ * L2-normalised copy for the concat buffer.  The residual connection (model.py:90-99) and the
+ * Linear layers are passed FOLDED:
+ *     o1 = ego @ Pa + side @ Pb + r1[row]          (Pa may be NULL: term folded into r1)
+ *     o2 = (ego * side) @ P2 + r2[row]             (bi-interaction only, P2 non-NULL)
+ *     emb = leaky(o1) (+ leaky(o2));  x = LayerNorm(emb) * mask;  xn = x / max(|x|_2, 1e-12)
+ * Pa, Pb, P2: [d_in, d_out] row-major.  r1/r2: per-row terms with leading dimension ld_r
+ * (ld_r == 0 broadcasts one [d_out] vector, i.e. a plain bias). */
+int lkg_aggregate_workspace_bytes(size_t* bytes /*host out*/);
+int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* ego, int64_t ld_ego,
+                      int32_t d_in, int32_t d_out, const float* pa, const float* pb, const float* p2,
+                      const float* r1, const float* r2, int64_t ld_r,
+                      const float* ln_weight, const float* ln_bias,
+                      const float* drop_mask /*nullable [N,d_out] multiplicative*/,
+                      float* x_out, int64_t ld_x, float* xn_out /*nullable*/, int64_t ld_xn,
+                      void* workspace, void* stream);
+
+/* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
+/* scores[B,Nt] = emb[heads] @ emb[tails]^T; minmax_dev (nullable) is an opaque uint32[2] running
+ * {min, max} state (order-preserving encoding) that must be reset with lkg_minmax_reset first. */
+int lkg_score(const float* emb, int64_t ld_emb, int32_t dim, const int64_t* heads, int64_t n_heads,
+              const int64_t* tails, int64_t n_tails, float* scores, int64_t ld_scores,
+              uint32_t* minmax_dev, void* stream);
+int lkg_minmax_reset(uint32_t* minmax_dev, void* stream);
+/* pred = ((s - min) / (max - min) > milestone) as int32 (model.py:490-491); NaN compares false. */
+int lkg_predict_threshold(const float* scores, int64_t ld_scores, int64_t n_heads, int64_t n_tails,
+                          const uint32_t* minmax_dev, float milestone, int32_t* pred, int64_t ld_pred,
+                          void* stream);
+/* Per-row top-k of a score matrix: larger score first, ties -> lower column.  k <= 1024.
+ * target_cols (nullable) int64 [n_rows]: ranks_out[i] = number of columns that beat target_cols[i]. */
+int lkg_topk_rows(const float* scores, int64_t ld_scores, int64_t n_rows, int64_t n_cols, int32_t k,
+                  float* top_values, int64_t* top_cols, const int64_t* target_cols,
+                  int64_t* ranks_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKG_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of liblkg.so (include/lkg.h).  There is no fallback: a missing library, a missing
+CUDA device or a non-sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblkg.so")
+
+LKG_MAX_SEGMENTS = 4
+ACT_NONE, ACT_LEAKY_RELU = 0, 1
+
+i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
+
+
+class LkgGraph(C.Structure):
+    _fields_ = [("n_entities", i64), ("n_edges", i64), ("nnz", i64), ("n_relations", i32),
+                ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
+                ("rowptr", vp), ("col", vp)]
+
+
+class LkgOperand(C.Structure):
+    _fields_ = [("n_segments", i32), ("ptr", vp * LKG_MAX_SEGMENTS), ("ld", i64 * LKG_MAX_SEGMENTS),
+                ("k", i32 * LKG_MAX_SEGMENTS), ("rows", vp)]
+
+
+# name -> (restype, argtypes); mirrors include/lkg.h one to one
+SIGNATURES = {
+    "lkg_abi_version": (C.c_int, []),
+    "lkg_last_error": (C.c_char_p, []),
+    "lkg_device_check": (C.c_int, [C.c_int]),
+    "lkg_plan_workspace_bytes": (C.c_int, [i64, i64, C.POINTER(C.c_size_t)]),
+    "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                 C.c_size_t, vp]),
+    "lkg_segment_scatter_add": (C.c_int, [vp, vp, i64, vp, i64, vp]),
+    "lkg_laplacian_init": (C.c_int, [C.POINTER(LkgGraph), C.c_int, vp, vp, vp]),
+    "lkg_attn_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
+    "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),
+    "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgOperand), i64, vp, i64, i32, vp, i32, vp, i64, vp]),
+    "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgOperand), i64, vp, i64, vp, i32, vp, i64, vp, i64, vp]),
+    "lkg_aggregate_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
+    "lkg_aggregate_fwd": (C.c_int, [C.POINTER(LkgGraph), vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp,
+                                    vp, vp, i64, vp, i64, vp, vp]),
+    "lkg_score": (C.c_int, [vp, i64, i32, vp, i64, vp, i64, vp, i64, vp, vp]),
+    "lkg_minmax_reset": (C.c_int, [vp, vp]),
+    "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),
+    "lkg_topk_rows": (C.c_int, [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+_checked_devices = set()
+
+
+def load() -> C.CDLL:
+    """Loads liblkg.so (built in-tree by ``python -m literalkg_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m literalkg_b200.build` "
+                "(literalkg_b200 has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.lkg_abi_version() != 1:
+            raise RuntimeError("liblkg.so ABI version mismatch; rebuild with `python -m literalkg_b200.build`")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().lkg_last_error().decode(errors="replace")
+        raise RuntimeError(f"liblkg error {rc}: {msg}")
+
+
+def require_cuda(t: torch.Tensor, what: str = "tensor") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"literalkg_b200: {what} is on {t.device}; the path runs on CUDA sm_100 only "
+                           "(no CPU fallback)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        check(load().lkg_device_check(idx))
+        _checked_devices.add(idx)
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def operand(segments, rows: Optional[torch.Tensor] = None) -> LkgOperand:
+    """segments: list of 2-D fp32 CUDA tensors with unit inner stride (row stride = leading dim)."""
+    op = LkgOperand()
+    op.n_segments = len(segments)
+    for i, s in enumerate(segments):
+        assert s.dim() == 2 and s.stride(1) == 1 and s.dtype == torch.float32
+        op.ptr[i] = s.data_ptr()
+        op.ld[i] = s.stride(0)
+        op.k[i] = s.shape[1]
+    op.rows = ptr(rows)
+    return op

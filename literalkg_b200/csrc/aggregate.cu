@@ -1,0 +1,348 @@
+// One aggregator layer, forward: CSR SpMM fused with the combine, LeakyReLU, LayerNorm, dropout mask
+// and the L2-normalised copy for the concat buffer.
+//
+// Replaces Aggregator.forward + residual_connection (model.py:90-164) and the F.normalize of
+// model.py:305.  The reference runs cuSPARSE SpMM, then 2-4 dense N x d x d GEMMs, ~10 elementwise
+// kernels and a LayerNorm, each a full pass over N x d.  Here one warp owns kRows head rows:
+//   phase 1  side = sum_j A[row, j] * ego[col_j]   128-bit streaming gathers, kUnroll neighbours in flight
+//   phase 2  u-vectors (side | ego+side | ego | ego*side) staged in shared memory, then the folded
+//            combine  o = u @ P + r[row]  with lane = output channel (P lives in shared memory)
+//   phase 3  leaky / add / LayerNorm / mask / L2 normalise, all in registers + warp shuffles
+// Folding (host side): linear(res(hi)) = hi @ P + h0 @ Q + c, P = (1-a) M W^T.
+// HBM bound: algorithmic bytes = nnz*(4 col + 4 val + 4 d_in) + N*(4 d_in + 8 + r terms + 2*4*d_out).
+#include "common.cuh"
+
+namespace lkg {
+namespace {
+
+constexpr int kRows = 2;  // head rows per warp per step (P is read from shared memory once per kRows rows)
+
+enum Mode { kOneTerm = 0, kTwoTerms = 1, kBi = 2 };
+
+struct AggParams {
+    lkg_graph g;
+    const float* a_val;
+    const float* ego;
+    int64_t ld_ego;
+    int d_in, d_out, nvec;
+    const float* p0;   // term 0 matrix [d_in, d_out]
+    const float* p1;   // term 1 matrix (kTwoTerms: side matrix; kBi: product matrix)
+    int sum_ego;       // term 0 vector: 1 -> ego + side, 0 -> side   (kOneTerm / kBi);  kTwoTerms: term0 = ego, term1 = side
+    const float* r1;
+    const float* r2;
+    int64_t ld_r;
+    const float* ln_w;
+    const float* ln_b;
+    const float* mask;
+    float* x_out;
+    int64_t ld_x;
+    float* xn_out;
+    int64_t ld_xn;
+    int* counter;
+    int p_stride;      // padded row stride (floats) of P in shared memory
+};
+
+template <int S, int NC, int MODE>
+__global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int UNROLL = S == 1 ? 8 : 4;   // narrow rows: more neighbours in flight
+    constexpr int NT = MODE == kOneTerm ? 1 : 2;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int d_in = p.d_in, d_out = p.d_out, nvec = p.nvec;
+    const int ps = p.p_stride;
+    float* sp0 = smem;
+    float* sp1 = smem + (size_t)d_in * ps;
+    float* stage = smem + (size_t)NT * d_in * ps + (size_t)warp * (kRows * NT * d_in);
+
+    // stage the folded matrices once per CTA
+    for (int i = threadIdx.x; i < d_in * d_out; i += blockDim.x) {
+        const int d = i / d_out, c = i - d * d_out;
+        sp0[d * ps + c] = p.p0[i];
+        if (NT == 2) sp1[d * ps + c] = p.p1[i];
+    }
+    __syncthreads();
+    (void)nwarps;
+
+    const int n = (int)p.g.n_entities;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, kRows);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+
+        // ---- phase 1: SpMM + u-vector staging ------------------------------------------------
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) {
+            const int row = base + rr;
+            if (row >= n) break;
+            float4 side[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) side[s] = make_float4(0, 0, 0, 0);
+            const int u0 = p.g.rowptr[row], u1 = p.g.rowptr[row + 1];
+            for (int u = u0; u < u1; u += UNROLL) {
+                int cl[UNROLL];
+                float av[UNROLL];
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j) {
+                    const bool live = u + j < u1;
+                    cl[j] = live ? __ldg(p.g.col + u + j) : -1;
+                    av[j] = live ? __ldg(p.a_val + u + j) : 0.f;
+                }
+                float4 x[UNROLL][S];
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j) {
+                    const float* src = p.ego + (int64_t)(cl[j] < 0 ? 0 : cl[j]) * p.ld_ego;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const int v = lane + 32 * s;
+                        x[j][s] = (cl[j] >= 0 && v < nvec) ? ldg_stream4(src + 4 * v) : make_float4(0, 0, 0, 0);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        side[s].x = fmaf(av[j], x[j][s].x, side[s].x);
+                        side[s].y = fmaf(av[j], x[j][s].y, side[s].y);
+                        side[s].z = fmaf(av[j], x[j][s].z, side[s].z);
+                        side[s].w = fmaf(av[j], x[j][s].w, side[s].w);
+                    }
+                }
+            }
+            const float* erow = p.ego + (int64_t)row * p.ld_ego;
+            float* st = stage + rr * NT * d_in;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int v = lane + 32 * s;
+                if (v < nvec) {
+                    const float4 sd = side[s];
+                    float4 eg = make_float4(0, 0, 0, 0);
+                    if (MODE != kOneTerm || p.sum_ego) eg = __ldg(reinterpret_cast<const float4*>(erow) + v);
+                    float4 t0, t1;
+                    if (MODE == kTwoTerms) {
+                        t0 = eg;
+                        t1 = sd;
+                    } else {
+                        t0 = p.sum_ego ? make_float4(eg.x + sd.x, eg.y + sd.y, eg.z + sd.z, eg.w + sd.w) : sd;
+                        t1 = make_float4(eg.x * sd.x, eg.y * sd.y, eg.z * sd.z, eg.w * sd.w);
+                    }
+                    reinterpret_cast<float4*>(st)[v] = t0;
+                    if (NT == 2) reinterpret_cast<float4*>(st + d_in)[v] = t1;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2: folded combine, lane = output channel ----------------------------------
+        float acc1[kRows][NC], acc2[kRows][NC];
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) {
+            const int row = min(base + rr, n - 1);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                acc1[rr][c] = (ch < d_out && p.r1) ? __ldg(p.r1 + (int64_t)row * p.ld_r + ch) : 0.f;
+                acc2[rr][c] = (MODE == kBi && ch < d_out && p.r2) ? __ldg(p.r2 + (int64_t)row * p.ld_r + ch) : 0.f;
+            }
+        }
+        for (int d4 = 0; d4 < nvec; ++d4) {
+            float4 u[kRows][NT];
+#pragma unroll
+            for (int rr = 0; rr < kRows; ++rr)
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    u[rr][t] = reinterpret_cast<const float4*>(stage + (rr * NT + t) * d_in)[d4];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                const int chc = ch < d_out ? ch : 0;
+                float w0[4], w1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w0[i] = sp0[(4 * d4 + i) * ps + chc];
+                    w1[i] = NT == 2 ? sp1[(4 * d4 + i) * ps + chc] : 0.f;
+                }
+#pragma unroll
+                for (int rr = 0; rr < kRows; ++rr) {
+                    float a = acc1[rr][c];
+                    a = fmaf(u[rr][0].x, w0[0], a);
+                    a = fmaf(u[rr][0].y, w0[1], a);
+                    a = fmaf(u[rr][0].z, w0[2], a);
+                    a = fmaf(u[rr][0].w, w0[3], a);
+                    if (MODE == kTwoTerms) {
+                        a = fmaf(u[rr][1].x, w1[0], a);
+                        a = fmaf(u[rr][1].y, w1[1], a);
+                        a = fmaf(u[rr][1].z, w1[2], a);
+                        a = fmaf(u[rr][1].w, w1[3], a);
+                    }
+                    acc1[rr][c] = a;
+                    if (MODE == kBi) {
+                        float b = acc2[rr][c];
+                        b = fmaf(u[rr][1].x, w1[0], b);
+                        b = fmaf(u[rr][1].y, w1[1], b);
+                        b = fmaf(u[rr][1].z, w1[2], b);
+                        b = fmaf(u[rr][1].w, w1[3], b);
+                        acc2[rr][c] = b;
+                    }
+                }
+            }
+        }
+        __syncwarp();   // staging buffer is reused by the next step
+
+        // ---- phase 3: activation, LayerNorm, mask, L2 normalise --------------------------------
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) {
+            const int row = base + rr;
+            if (row >= n) break;
+            float emb[NC];
+            float s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                float e = leaky(acc1[rr][c]);
+                if (MODE == kBi) e += leaky(acc2[rr][c]);
+                emb[c] = ch < d_out ? e : 0.f;
+                s1 += emb[c];
+            }
+            const float mean = warp_sum(s1) / (float)d_out;
+            float s2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                const float dlt = ch < d_out ? emb[c] - mean : 0.f;
+                s2 = fmaf(dlt, dlt, s2);
+            }
+            const float rstd = rsqrtf(warp_sum(s2) / (float)d_out + 1e-5f);
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                float x = 0.f;
+                if (ch < d_out) {
+                    x = (emb[c] - mean) * rstd * __ldg(p.ln_w + ch) + __ldg(p.ln_b + ch);
+                    if (p.mask) x *= __ldg(p.mask + (int64_t)row * d_out + ch);
+                    p.x_out[(int64_t)row * p.ld_x + ch] = x;
+                }
+                emb[c] = x;
+                sq = fmaf(x, x, sq);
+            }
+            if (p.xn_out) {
+                const float inv = 1.f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int ch = lane + 32 * c;
+                    if (ch < d_out) p.xn_out[(int64_t)row * p.ld_xn + ch] = emb[c] * inv;
+                }
+            }
+        }
+    }
+}
+
+template <int S, int NC, int MODE>
+int launch(const AggParams& p, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = aggregate_kernel<S, NC, MODE>;
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    LKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate kernel does not fit (smem %zu)", smem);
+    const int grid = sm_count() * per_sm;
+    kern<<<grid, threads, smem, stream>>>(p);
+    LKG_LAUNCH_CHECK("aggregate_kernel");
+    return LKG_OK;
+}
+
+template <int S, int NC>
+int dispatch_mode(int mode, const AggParams& p, int threads, size_t smem, cudaStream_t stream) {
+    switch (mode) {
+        case kOneTerm: return launch<S, NC, kOneTerm>(p, threads, smem, stream);
+        case kTwoTerms: return launch<S, NC, kTwoTerms>(p, threads, smem, stream);
+        default: return launch<S, NC, kBi>(p, threads, smem, stream);
+    }
+}
+
+}  // namespace
+}  // namespace lkg
+
+using namespace lkg;
+
+extern "C" int lkg_aggregate_workspace_bytes(size_t* bytes) {
+    LKG_REQUIRE(bytes != nullptr, "bytes is null");
+    *bytes = 256;
+    return LKG_OK;
+}
+
+extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* ego, int64_t ld_ego,
+                                 int32_t d_in, int32_t d_out, const float* pa, const float* pb, const float* p2,
+                                 const float* r1, const float* r2, int64_t ld_r, const float* ln_weight,
+                                 const float* ln_bias, const float* drop_mask, float* x_out, int64_t ld_x,
+                                 float* xn_out, int64_t ld_xn, void* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(g && ego && pb && ln_weight && ln_bias && x_out && workspace, "null argument");
+    LKG_REQUIRE(g->nnz == 0 || a_values != nullptr, "a_values is null");
+    LKG_REQUIRE(d_in > 0 && d_in % 4 == 0, "d_in must be a positive multiple of 4 (got %d)", d_in);
+    LKG_REQUIRE(ld_ego % 4 == 0 && aligned16(ego), "ego rows must be 16-byte aligned");
+    LKG_REQUIRE(d_out > 0, "d_out must be positive");
+    LKG_REQUIRE(!(p2 && pa && pa != pb), "bi-interaction takes one shared sum matrix (pa == pb or pa NULL)");
+    if (d_in > 512) LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate d_in %d > 512", d_in);
+    if (d_out > 64) LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate d_out %d > 64", d_out);
+
+    AggParams p{};
+    p.g = *g;
+    p.a_val = a_values;
+    p.ego = ego;
+    p.ld_ego = ld_ego;
+    p.d_in = d_in;
+    p.d_out = d_out;
+    p.nvec = d_in / 4;
+    int mode;
+    if (p2) {
+        mode = kBi;
+        p.p0 = pb;
+        p.p1 = p2;
+        p.sum_ego = pa != nullptr;
+    } else if (pa && pa != pb) {
+        mode = kTwoTerms;
+        p.p0 = pa;
+        p.p1 = pb;
+        p.sum_ego = 0;
+    } else {
+        mode = kOneTerm;
+        p.p0 = pb;
+        p.p1 = nullptr;
+        p.sum_ego = pa != nullptr;
+    }
+    p.r1 = r1;
+    p.r2 = r2;
+    p.ld_r = ld_r;
+    p.ln_w = ln_weight;
+    p.ln_b = ln_bias;
+    p.mask = drop_mask;
+    p.x_out = x_out;
+    p.ld_x = ld_x;
+    p.xn_out = xn_out;
+    p.ld_xn = ld_xn;
+    p.counter = static_cast<int*>(workspace);
+    // lane c reads sp[d * ps + c]: any stride is conflict free for 32 consecutive channels; pad to a
+    // multiple of 4 floats to keep rows 16-byte aligned
+    p.p_stride = (d_out + 3) / 4 * 4;
+    LKG_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(int), stream));
+
+    const int nt = mode == kOneTerm ? 1 : 2;
+    const size_t p_bytes = (size_t)nt * d_in * p.p_stride * sizeof(float);
+    const size_t stage_per_warp = (size_t)kRows * nt * d_in * sizeof(float);
+    int warps = 16;
+    while (warps > 4 && p_bytes + warps * stage_per_warp > 200 * 1024) warps /= 2;
+    const size_t smem = p_bytes + warps * stage_per_warp;
+    if (smem > 227 * 1024) LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate shapes need %zu bytes of shared memory", smem);
+    const int threads = warps * 32;
+    const int slots = (p.nvec + 31) / 32;
+    const int nc = (d_out + 31) / 32;
+#define LKG_AGG_CASE(SS, CC) \
+    if (slots == SS && nc == CC) return dispatch_mode<SS, CC>(mode, p, threads, smem, stream);
+    LKG_AGG_CASE(1, 1) LKG_AGG_CASE(2, 1) LKG_AGG_CASE(3, 1) LKG_AGG_CASE(4, 1)
+    LKG_AGG_CASE(1, 2) LKG_AGG_CASE(2, 2) LKG_AGG_CASE(3, 2) LKG_AGG_CASE(4, 2)
+#undef LKG_AGG_CASE
+    LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate: no kernel for d_in %d d_out %d", d_in, d_out);
+}

@@ -1,0 +1,92 @@
+// Shared helpers for liblkg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/lkg.h"
+
+namespace lkg {
+
+void set_error(const char* fmt, ...);
+
+#define LKG_FAIL(code, ...)              \
+    do {                                 \
+        ::lkg::set_error(__VA_ARGS__);   \
+        return (code);                   \
+    } while (0)
+
+#define LKG_REQUIRE(cond, ...)                               \
+    do {                                                     \
+        if (!(cond)) LKG_FAIL(LKG_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define LKG_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            LKG_FAIL(LKG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                     __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define LKG_LAUNCH_CHECK(name)                                                                \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            LKG_FAIL(LKG_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// streaming 128-bit load through the read-only path, no L1 allocation (gathered rows are used once)
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
+
+// tanh with ~2e-7 absolute error: odd polynomial near zero, (1-e)/(1+e) with e = exp(-2|x|) elsewhere
+__device__ __forceinline__ float tanh_acc(float x) {
+    const float ax = fabsf(x);
+    const float x2 = x * x;
+    float p = fmaf(x2, 2.1869488e-2f, -5.3968254e-2f);   // 62/2835, -17/315
+    p = fmaf(x2, p, 1.3333334e-1f);                       // 2/15
+    p = fmaf(x2, p, -3.3333334e-1f);                      // -1/3
+    p = fmaf(x2 * x, p, x);
+    const float e = exp2f(-2.8853900817779268f * ax);     // exp(-2|x|)
+    const float q = copysignf(__fdividef(1.f - e, 1.f + e), x);
+    return ax < 0.25f ? p : q;
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
+
+}  // namespace lkg

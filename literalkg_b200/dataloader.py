@@ -1,0 +1,131 @@
+"""Graph / literal tensors of the reference's ``DataLoader`` (dataloader.py:345-512), built on device.
+
+Only the tensor-producing part of the reference loader is on the accelerated path (SURVEY.md 8(a) rows
+a1-a3): ``h_list / t_list / r_list``, the ``relations`` order, ``n_entities / n_relations``, the initial
+``A_in`` (sum of per-relation normalised adjacencies) and the dense literal tables.  Samplers and label
+files stay with the reference (section 8(f)).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .graph import GraphPlan
+
+
+def read_triples(path: str) -> np.ndarray:
+    """``h r t`` per line, space separated; exact duplicate rows dropped keeping the first occurrence and
+    the file order (``load_graph`` dataloader.py:186-190).  Returns int64 [E, 3] in (h, r, t) columns."""
+    arr = np.loadtxt(path, dtype=np.int64, ndmin=2)
+    if arr.shape[1] != 3:
+        raise ValueError(f"{path}: expected 3 columns 'h r t'")
+    _, first = np.unique(arr, axis=0, return_index=True)
+    return arr[np.sort(first)]
+
+
+def relation_order(r: np.ndarray) -> List[int]:
+    """Order of first appearance == ``laplacian_dict.keys()`` (dataloader.py:403,491), which main.py:150
+    passes to ``update_att`` as ``relations``."""
+    _, first = np.unique(r, return_index=True)
+    return [int(x) for x in r[np.sort(first)]]
+
+
+def read_numeric_literals(paths: Sequence[str], n_entities: Optional[int], numeric_dim: int):
+    """``load_attributes`` + ``embed_num_literal`` (dataloader.py:111-137, 426-431): file i fills column i
+    with (v + 1) / max(v); lines without a tab (the leading count) are skipped; a later file resets the
+    whole row of an entity it mentions.  Returns (table float32 [n, numeric_dim], max entity id)."""
+    rows: Dict[int, np.ndarray] = {}
+    for col, path in enumerate(paths):
+        ids, vals = [], []
+        with open(path) as fh:
+            for line in fh:
+                parts = line.split("\t")
+                if len(parts) > 1:
+                    ids.append(int(parts[0]))
+                    vals.append(float(parts[1]))
+        vmax = max([0.0] + vals)
+        latest = dict(zip(ids, vals))                      # a repeated id keeps its last value (dict semantics)
+        for ent, v in latest.items():
+            row = np.zeros(numeric_dim)
+            if vmax != 0:
+                row[col] = (v + 1) / vmax
+            rows[ent] = row
+    max_id = max(rows) if rows else -1
+    n = max(n_entities or 0, max_id + 1)
+    table = np.zeros((n, numeric_dim), dtype=np.float32)
+    if rows:
+        idx = np.fromiter(rows.keys(), dtype=np.int64)
+        table[idx] = np.stack(list(rows.values())).astype(np.float32)
+    return table, max_id
+
+
+class KGTensors:
+    """Device tensors with the attribute names the reference's training loop reads from its DataLoader
+    (main.py:42-43,147-151): ``A_in``, ``h_list``, ``t_list``, ``r_list``, ``laplacian_dict`` (keys only),
+    ``num_embedding_table``, ``text_embedding_table``, ``n_entities``, ``n_relations``."""
+
+    def __init__(self, h, t, r, n_entities: Optional[int] = None, laplacian_type: str = "random-walk",
+                 device="cuda", num_table=None, text_table=None, min_entities: int = 0):
+        h = torch.as_tensor(h, dtype=torch.int64)
+        t = torch.as_tensor(t, dtype=torch.int64)
+        r = torch.as_tensor(r, dtype=torch.int64)
+        self.device = torch.device(device)
+        self.n_relations = len(torch.unique(r))            # dataloader.py:374 (ids must be 0..R-1)
+        n = int(max(h.max().item() + 1, t.max().item() + 1, min_entities))   # dataloader.py:405-418
+        for tab in (num_table, text_table):
+            if tab is not None:
+                n = max(n, tab.shape[0])
+        self.n_entities = n if n_entities is None else int(n_entities)
+        self.h_list, self.t_list, self.r_list = h.to(self.device), t.to(self.device), r.to(self.device)
+        self.relations = relation_order(r.cpu().numpy())
+        self.laplacian_dict = {rel: None for rel in self.relations}   # the training loop only uses .keys()
+        self.laplacian_type = laplacian_type
+        self.plan = GraphPlan(self.h_list, self.t_list, self.r_list, self.n_entities, self.n_relations)
+        self.A_in = self.plan.sparse(self.plan.laplacian(laplacian_type))    # dataloader.py:449-495
+        self.num_embedding_table = None if num_table is None else self._table(num_table)
+        self.text_embedding_table = None if text_table is None else self._table(text_table)
+
+    def _table(self, tab) -> torch.Tensor:
+        tab = torch.as_tensor(tab, dtype=torch.float32)
+        if tab.shape[0] < self.n_entities:
+            tab = torch.cat([tab, tab.new_zeros(self.n_entities - tab.shape[0], tab.shape[1])])
+        return tab.to(self.device).contiguous()
+
+    @classmethod
+    def from_dir(cls, data_dir: str, kg_file: str = "pre_training_train.txt", numeric_dim: int = 2,
+                 text_dim: int = 300, numeric_files=("age_dict.txt", "weight_dict.txt"),
+                 text_files=("cc_dict.pickle", "disease_dict.pickle", "memo_dict.pickle",
+                             "prescription_dict.pickle", "treatment_dict.pickle"),
+                 use_num_lit: bool = True, use_txt_lit: bool = True, **kw) -> "KGTensors":
+        """Reads a reference data directory (dataloader.py:24-32).  Missing literal files are skipped
+        (the Drive-hosted pickles are not bundled with the reference)."""
+        trip = read_triples(os.path.join(data_dir, kg_file))
+        num_paths = [os.path.join(data_dir, f) for f in numeric_files if os.path.exists(os.path.join(data_dir, f))]
+        n_kg = int(max(trip[:, 0].max(), trip[:, 2].max()) + 1)
+        num_table = text_table = None
+        text: Dict[int, np.ndarray] = {}
+        if use_txt_lit:
+            for f in text_files:
+                p = os.path.join(data_dir, f)
+                if os.path.exists(p):
+                    with open(p, "rb") as fh:
+                        text.update(pickle.load(fh))
+        if use_num_lit and num_paths:
+            table, _ = read_numeric_literals(num_paths, n_kg, numeric_dim)
+            if text:                                                  # dataloader.py:147-150
+                ids = np.fromiter((k for k in text if k < table.shape[0]), dtype=np.int64)
+                table[ids] = 0
+            num_table = table
+        if use_txt_lit:
+            n_txt = max([n_kg] + [k + 1 for k in text]) if text else n_kg
+            if num_table is not None:
+                n_txt = max(n_txt, num_table.shape[0])
+            tt = np.zeros((n_txt, text_dim), dtype=np.float32)
+            for k, v in text.items():
+                tt[k] = np.asarray(v, dtype=np.float32)
+            text_table = tt
+        return cls(trip[:, 0], trip[:, 2], trip[:, 1], num_table=num_table, text_table=text_table, **kw)

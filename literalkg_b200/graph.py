@@ -1,0 +1,112 @@
+"""Device-resident CSR plan of the knowledge graph (lkg_graph in include/lkg.h).
+
+Built once per edge list; the reference re-derives the same structure on every ``update_att`` call
+inside ``torch.sparse.softmax`` (coalesce = sort + duplicate merge, model.py:466-470) and inside the
+scipy Laplacian construction (dataloader.py:449-495).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import torch
+
+from . import _lib
+
+
+class GraphPlan:
+    """att order = kept triples sorted by (h, r, t); agg order = unique (h, t) pairs sorted by (h, t),
+    i.e. the coalesced ``A_in`` of the reference.  ``file_seg[i]`` = pair index of input triple i."""
+
+    def __init__(self, h: torch.Tensor, t: torch.Tensor, r: torch.Tensor, n_entities: int, n_relations: int,
+                 relations: Optional[Iterable[int]] = None):
+        _lib.require_cuda(h, "h_list")
+        lib = _lib.load()
+        dev = h.device
+        h = h.to(torch.int64).contiguous()
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        r = r.to(device=dev, dtype=torch.int64).contiguous()
+        e = h.numel()
+        if not (t.numel() == e and r.numel() == e):
+            raise ValueError("h_list, t_list and r_list must have the same length")
+        keep = None
+        if relations is not None:
+            rel = sorted({int(x) for x in relations})
+            if rel != list(range(n_relations)):       # a relation list that omits ids drops their triples
+                keep = torch.zeros(n_relations, dtype=torch.uint8)
+                keep[[x for x in rel if 0 <= x < n_relations]] = 1
+                keep = keep.to(dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.att_rowptr = torch.empty(n_entities + 1, **i32)
+        self.rowptr = torch.empty(n_entities + 1, **i32)
+        self.att_tail = torch.empty(max(e, 1), **i32)
+        self.att_rel = torch.empty(max(e, 1), **i32)
+        self.att_seg = torch.empty(max(e, 1), **i32)
+        self.col = torch.empty(max(e, 1), **i32)
+        coo = torch.empty((2, max(e, 1)), dtype=torch.int64, device=dev)
+        self.file_seg = torch.empty(max(e, 1), **i32)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.lkg_plan_workspace_bytes(e, n_entities, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lkg_plan_build(h.data_ptr(), t.data_ptr(), r.data_ptr(), e, n_entities, n_relations,
+                                          _lib.ptr(keep), self.att_rowptr.data_ptr(), self.att_tail.data_ptr(),
+                                          self.att_rel.data_ptr(), self.att_seg.data_ptr(), self.rowptr.data_ptr(),
+                                          self.col.data_ptr(), coo[0].data_ptr(), coo[1].data_ptr(),
+                                          self.file_seg.data_ptr(), counts.data_ptr(), ws.data_ptr(), nbytes.value,
+                                          _lib.stream()))
+        kept, nnz, bad = counts.tolist()          # one host sync per plan build
+        del ws
+        if bad:
+            raise ValueError(f"{bad} triples have entity / relation ids outside [0, n_entities) / [0, n_relations)")
+        self.device = dev
+        self.n_entities, self.n_relations = int(n_entities), int(n_relations)
+        self.n_input, self.n_edges, self.nnz = e, int(kept), int(nnz)
+        self.att_tail, self.att_rel, self.att_seg = (x[:self.n_edges] for x in (self.att_tail, self.att_rel, self.att_seg))
+        self.col = self.col[:self.nnz]
+        self.file_seg = self.file_seg[:e]
+        self.indices = coo[:, :self.nnz]          # int64 [2, nnz]: A_in.coalesce().indices()
+        self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations,
+                               self.att_rowptr.data_ptr(), self.att_tail.data_ptr(), self.att_rel.data_ptr(),
+                               self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr())
+        self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
+
+    # -- constructors ---------------------------------------------------------------------------
+    @classmethod
+    def from_coo(cls, indices: torch.Tensor, n_entities: int) -> "GraphPlan":
+        """Plan of an existing sparse matrix (e.g. ``A_in`` from the DataLoader or a checkpoint);
+        every entry is treated as a triple of relation 0."""
+        r = torch.zeros(indices.shape[1], dtype=torch.int64, device=indices.device)
+        return cls(indices[0], indices[1], r, n_entities, 1)
+
+    # -- helpers ------------------------------------------------------------------------------
+    def byref(self):
+        return C.byref(self.c)
+
+    def scratch(self) -> int:
+        return self._scratch.data_ptr()
+
+    def import_values(self, values: torch.Tensor) -> torch.Tensor:
+        """Values given per INPUT entry -> plan (coalesced) order, duplicates summed."""
+        values = _lib.f32c(values.to(self.device))
+        out = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.device)[:self.nnz]
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().lkg_segment_scatter_add(values.data_ptr(), self.file_seg.data_ptr(), self.n_input,
+                                                           out.data_ptr(), self.nnz, _lib.stream()))
+        return out
+
+    def laplacian(self, laplacian_type: str = "random-walk") -> torch.Tensor:
+        """Initial A_in values (dataloader.py:462-495), plan order, fp32."""
+        if laplacian_type not in ("random-walk", "symmetric"):
+            raise NotImplementedError(laplacian_type)
+        out = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.device)[:self.nnz]
+        acc = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().lkg_laplacian_init(self.byref(), int(laplacian_type == "symmetric"),
+                                                      out.data_ptr(), acc.data_ptr(), _lib.stream()))
+        return out
+
+    def sparse(self, values: torch.Tensor) -> torch.Tensor:
+        """Coalesced sparse COO view (shares ``values``) in the reference's A_in format."""
+        return torch.sparse_coo_tensor(self.indices, values, (self.n_entities, self.n_entities), is_coalesced=True)

@@ -1,0 +1,146 @@
+"""Thin functional wrappers over the C ABI (one per entry point of include/lkg.h).
+
+All tensors must live on one sm_100 CUDA device; nothing here falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .graph import GraphPlan
+
+
+def _dev_guard(t: torch.Tensor):
+    _lib.require_cuda(t)
+    return torch.cuda.device(t.device)
+
+
+def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A_in values after ``update_att`` (model.py:444-471), plan (coalesced) order."""
+    entity, relation = _lib.f32c(entity), _lib.f32c(relation)
+    if entity.shape[1] != relation.shape[1]:
+        raise ValueError("update_att needs embed_dim == relation_dim (model.py:441 adds the two tables)")
+    if out is None:
+        out = torch.empty(max(plan.nnz, 1), dtype=torch.float32, device=entity.device)[:plan.nnz]
+    with _dev_guard(entity):
+        _lib.check(_lib.load().lkg_attn_update(plan.byref(), entity.data_ptr(), entity.stride(0),
+                                               relation.data_ptr(), relation.stride(0), entity.shape[1],
+                                               out.data_ptr(), plan.scratch(), _lib.stream()))
+    return out
+
+
+def linear(segments: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor],
+           activation: int = _lib.ACT_NONE, out: Optional[torch.Tensor] = None,
+           rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act([seg0 | seg1 | ...] @ weight^T + bias); weight is [out_features, sum(k)] (nn.Linear layout)."""
+    segs = [s if (s.dtype == torch.float32 and s.stride(1) == 1) else _lib.f32c(s) for s in segments]
+    weight = _lib.f32c(weight)
+    m = segs[0].shape[0] if rows is None else rows.numel()
+    n = weight.shape[0]
+    if sum(s.shape[1] for s in segs) != weight.shape[1]:
+        raise ValueError("segment widths do not add up to weight.shape[1]")
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
+    op = _lib.operand(segs, rows)
+    with _dev_guard(weight):
+        _lib.check(_lib.load().lkg_linear_fwd(C.byref(op), m, weight.data_ptr(), weight.stride(0), n,
+                                              _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
+                                              out.data_ptr(), out.stride(0), _lib.stream()))
+    return out
+
+
+def gate(segments: Sequence[torch.Tensor], w_pair: torch.Tensor, bias_pair: torch.Tensor,
+         x_ent: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Literal gate (gate.py:22-28): out = (1 - z) * x_ent + z * tanh(g) with (g, z) interleaved in w_pair."""
+    segs = [s if (s.dtype == torch.float32 and s.stride(1) == 1) else _lib.f32c(s) for s in segments]
+    w_pair, bias_pair = _lib.f32c(w_pair), _lib.f32c(bias_pair)
+    x_ent = x_ent if (x_ent.dtype == torch.float32 and x_ent.stride(1) == 1) else _lib.f32c(x_ent)
+    m, dim = x_ent.shape
+    if out is None:
+        out = torch.empty((m, dim), dtype=torch.float32, device=x_ent.device)
+    op = _lib.operand(segs)
+    with _dev_guard(x_ent):
+        _lib.check(_lib.load().lkg_gate_fwd(C.byref(op), m, w_pair.data_ptr(), w_pair.stride(0),
+                                            bias_pair.data_ptr(), dim, x_ent.data_ptr(), x_ent.stride(0),
+                                            out.data_ptr(), out.stride(0), _lib.stream()))
+    return out
+
+
+def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out: int,
+              pa: Optional[torch.Tensor], pb: torch.Tensor, p2: Optional[torch.Tensor],
+              r1: Optional[torch.Tensor], r2: Optional[torch.Tensor],
+              ln_weight: torch.Tensor, ln_bias: torch.Tensor, drop_mask: Optional[torch.Tensor],
+              x_out: torch.Tensor, xn_out: Optional[torch.Tensor]) -> torch.Tensor:
+    """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases."""
+    assert ego.dtype == torch.float32 and ego.stride(1) == 1
+    d_in = ego.shape[1]
+    ld_r = 0
+    for r in (r1, r2):
+        if r is not None and r.dim() == 2:
+            assert r.stride(1) == 1
+            ld_r = r.stride(0)
+    if r1 is not None and r2 is not None:
+        assert (r1.dim() == r2.dim()) and (r1.dim() == 1 or r1.stride(0) == r2.stride(0))
+    same = pa is not None and pa is pb
+    pb_c = _lib.f32c(pb)
+    pa_c = pb_c if same else (None if pa is None else _lib.f32c(pa))
+    p2_c = None if p2 is None else _lib.f32c(p2)
+    with _dev_guard(ego):
+        _lib.check(_lib.load().lkg_aggregate_fwd(
+            plan.byref(), _lib.ptr(a_values), ego.data_ptr(), ego.stride(0), d_in, d_out,
+            _lib.ptr(pa_c), pb_c.data_ptr(), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
+            _lib.f32c(ln_weight).data_ptr(), _lib.f32c(ln_bias).data_ptr(), _lib.ptr(drop_mask),
+            x_out.data_ptr(), x_out.stride(0), _lib.ptr(xn_out), 0 if xn_out is None else xn_out.stride(0),
+            plan.scratch(), _lib.stream()))
+    return x_out
+
+
+def score(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor,
+          minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores = emb[heads] @ emb[tails]^T (model.py:473-486); ``minmax``: opaque uint32[2] state."""
+    assert emb.dtype == torch.float32 and emb.stride(1) == 1
+    heads = heads.to(device=emb.device, dtype=torch.int64).contiguous()
+    tails = tails.to(device=emb.device, dtype=torch.int64).contiguous()
+    out = torch.empty((heads.numel(), tails.numel()), dtype=torch.float32, device=emb.device)
+    with _dev_guard(emb):
+        lib = _lib.load()
+        if minmax is not None:
+            _lib.check(lib.lkg_minmax_reset(minmax.data_ptr(), _lib.stream()))
+        _lib.check(lib.lkg_score(emb.data_ptr(), emb.stride(0), emb.shape[1], heads.data_ptr(), heads.numel(),
+                                 tails.data_ptr(), tails.numel(), out.data_ptr(), out.stride(0) if out.numel() else max(tails.numel(), 1),
+                                 _lib.ptr(minmax), _lib.stream()))
+    return out
+
+
+def predict(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor, milestone: float) -> torch.Tensor:
+    """(minmax-normalised scores > milestone).int() (model.py:488-491)."""
+    mm = torch.empty(2, dtype=torch.int32, device=emb.device)
+    s = score(emb, heads, tails, mm)
+    pred = torch.empty(s.shape, dtype=torch.int32, device=emb.device)
+    if s.numel():
+        with _dev_guard(emb):
+            _lib.check(_lib.load().lkg_predict_threshold(s.data_ptr(), s.stride(0), s.shape[0], s.shape[1],
+                                                         mm.data_ptr(), float(milestone), pred.data_ptr(),
+                                                         pred.stride(0), _lib.stream()))
+    return pred
+
+
+def topk_rows(scores: torch.Tensor, k: int, target_cols: Optional[torch.Tensor] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Row-wise top-k (larger first, ties -> lower column) and optional rank of ``target_cols``."""
+    assert scores.dtype == torch.float32 and scores.stride(1) == 1
+    rows, cols = scores.shape
+    vals = torch.empty((rows, k), dtype=torch.float32, device=scores.device)
+    idx = torch.empty((rows, k), dtype=torch.int64, device=scores.device)
+    ranks = None
+    if target_cols is not None:
+        target_cols = target_cols.to(device=scores.device, dtype=torch.int64).contiguous()
+        ranks = torch.empty(rows, dtype=torch.int64, device=scores.device)
+    with _dev_guard(scores):
+        _lib.check(_lib.load().lkg_topk_rows(scores.data_ptr(), scores.stride(0), rows, cols, k, vals.data_ptr(),
+                                             idx.data_ptr(), _lib.ptr(target_cols), _lib.ptr(ranks), _lib.stream()))
+    return vals, idx, ranks
