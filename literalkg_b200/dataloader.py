@@ -85,7 +85,15 @@ class KGTensors:
         self.laplacian_dict = {rel: None for rel in self.relations}   # the training loop only uses .keys()
         self.laplacian_type = laplacian_type
         self.plan = GraphPlan(self.h_list, self.t_list, self.r_list, self.n_entities, self.n_relations)
-        self.A_in = self.plan.sparse(self.plan.laplacian(laplacian_type))    # dataloader.py:449-495
+        vals = self.plan.laplacian(laplacian_type)                          # dataloader.py:449-495
+        if laplacian_type == "symmetric":
+            # scipy's diags() drops zero diagonal entries structurally (dataloader.py:466-470), so a
+            # triple whose tail has no outgoing edge under that relation leaves no entry at all
+            live = vals != 0
+            self.A_in = torch.sparse_coo_tensor(self.plan.indices[:, live], vals[live],
+                                                (self.n_entities, self.n_entities), is_coalesced=True)
+        else:
+            self.A_in = self.plan.sparse(vals)
         self.num_embedding_table = None if num_table is None else self._table(num_table)
         self.text_embedding_table = None if text_table is None else self._table(text_table)
 
