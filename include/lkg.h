@@ -50,6 +50,8 @@ typedef struct {
     int64_t n_edges;            /* E   : triples kept (relation filter applied)            */
     int64_t nnz;                /* E'  : unique (h,t) pairs                                  */
     int32_t n_relations;
+    int64_t row_begin;          /* kernels process head rows [row_begin, row_end): the row partition */
+    int64_t row_end;            /* owned by this rank (0, N on a single GPU)                          */
     const int32_t* att_rowptr;  /* [N+1] */
     const int32_t* att_tail;    /* [E]   */
     const int32_t* att_rel;     /* [E]   */
@@ -98,6 +100,11 @@ int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t
  * from a checkpoint, model.py:257-261) into plan order, summing duplicates like coalesce(). */
 int lkg_segment_scatter_add(const float* values_in, const int32_t* file_seg, int64_t n_edges,
                             float* values_out, int64_t nnz, void* stream);
+
+/* Order-independent 128-bit fingerprint of an edge list (fp_dev: uint64[2], zeroed by the call); used by
+ * the host side to recognise an unchanged (h, t, r) list and reuse its plan across update_att calls. */
+int lkg_edge_fingerprint(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
+                         uint64_t* fp_dev, void* stream);
 
 /* Initial A_in = sum_r D_r^-1 A_r (random-walk) or D_r^-1/2 A_r D_r^-1/2 (symmetric, row sums on
  * both sides), float64 accumulation then fp32 cast (dataloader.py:449-495).  values: [nnz];

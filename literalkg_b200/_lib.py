@@ -19,7 +19,7 @@ i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 
 class LkgGraph(C.Structure):
     _fields_ = [("n_entities", i64), ("n_edges", i64), ("nnz", i64), ("n_relations", i32),
-                ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
+                ("row_begin", i64), ("row_end", i64), ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
                 ("rowptr", vp), ("col", vp)]
 
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  C.c_size_t, vp]),
     "lkg_segment_scatter_add": (C.c_int, [vp, vp, i64, vp, i64, vp]),
+    "lkg_edge_fingerprint": (C.c_int, [vp, vp, vp, i64, vp, vp]),
     "lkg_laplacian_init": (C.c_int, [C.POINTER(LkgGraph), C.c_int, vp, vp, vp]),
     "lkg_attn_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),

@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
     __syncthreads();
     (void)nwarps;
 
-    const int n = (int)p.g.n_entities;
+    const int n = (int)p.g.row_end;
     for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, kRows);
+        if (lane == 0) base = (int)p.g.row_begin + atomicAdd(p.counter, kRows);
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) break;
 
@@ -281,6 +281,7 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(g && ego && pb && ln_weight && ln_bias && x_out && workspace, "null argument");
     LKG_REQUIRE(g->nnz == 0 || a_values != nullptr, "a_values is null");
+    LKG_REQUIRE(g->row_begin >= 0 && g->row_begin <= g->row_end && g->row_end <= g->n_entities, "bad row range");
     LKG_REQUIRE(d_in > 0 && d_in % 4 == 0, "d_in must be a positive multiple of 4 (got %d)", d_in);
     LKG_REQUIRE(ld_ego % 4 == 0 && aligned16(ego), "ego rows must be 16-byte aligned");
     LKG_REQUIRE(d_out > 0, "d_out must be positive");

@@ -25,11 +25,11 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
                    const float* __restrict__ rel, int64_t ld_rel, int nvec /* dim/4 */,
                    float* __restrict__ val, int* __restrict__ row_counter) {
     const int lane = threadIdx.x & 31;
-    const int n = (int)g.n_entities;
+    const int row0 = (int)g.row_begin, n = (int)g.row_end;
 
     for (;;) {
         int row = 0;
-        if (lane == 0) row = atomicAdd(row_counter, 1);
+        if (lane == 0) row = row0 + atomicAdd(row_counter, 1);
         row = __shfl_sync(kFull, row, 0);
         if (row >= n) break;
         const int e0 = g.att_rowptr[row], e1 = g.att_rowptr[row + 1];
@@ -141,6 +141,7 @@ extern "C" int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(g && entity && relation && workspace, "null argument");
     LKG_REQUIRE(g->nnz == 0 || values != nullptr, "values is null");
+    LKG_REQUIRE(g->row_begin >= 0 && g->row_begin <= g->row_end && g->row_end <= g->n_entities, "bad row range");
     LKG_REQUIRE(dim > 0 && dim % 4 == 0, "dim must be a positive multiple of 4 (got %d)", dim);
     LKG_REQUIRE(ld_entity % 4 == 0 && ld_relation % 4 == 0 && aligned16(entity) && aligned16(relation),
                 "entity / relation rows must be 16-byte aligned");

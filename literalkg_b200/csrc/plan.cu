@@ -322,3 +322,41 @@ extern "C" int lkg_segment_scatter_add(const float* values_in, const int32_t* fi
     LKG_LAUNCH_CHECK("scatter_add_kernel");
     return LKG_OK;
 }
+
+namespace lkg {
+namespace {
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__global__ void fingerprint_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ t,
+                                   const int64_t* __restrict__ r, int64_t n, unsigned long long* __restrict__ fp) {
+    uint64_t a = 0, b = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = mix64((uint64_t)h[i] * 0x9e3779b97f4a7c15ull + (uint64_t)t[i]) ^ mix64((uint64_t)r[i] + 0x165667b19e3779f9ull * (uint64_t)t[i]);
+        a += x;                       // commutative: independent of the edge order
+        b += mix64(x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(kFull, a, o);
+        b += __shfl_xor_sync(kFull, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(fp, (unsigned long long)a);
+        atomicAdd(fp + 1, (unsigned long long)b);
+    }
+}
+}  // namespace
+}  // namespace lkg
+
+extern "C" int lkg_edge_fingerprint(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
+                                    uint64_t* fp_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(fp_dev != nullptr, "fp_dev is null");
+    LKG_REQUIRE(n_edges == 0 || (h && t && r), "null edge array");
+    LKG_CUDA(cudaMemsetAsync(fp_dev, 0, 2 * sizeof(uint64_t), stream));
+    if (n_edges == 0) return LKG_OK;
+    fingerprint_kernel<<<grid_for(n_edges), 256, 0, stream>>>(h, t, r, n_edges, (unsigned long long*)fp_dev);
+    LKG_LAUNCH_CHECK("fingerprint_kernel");
+    return LKG_OK;
+}

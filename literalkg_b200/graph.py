@@ -67,7 +67,7 @@ class GraphPlan:
         self.col = self.col[:self.nnz]
         self.file_seg = self.file_seg[:e]
         self.indices = coo[:, :self.nnz]          # int64 [2, nnz]: A_in.coalesce().indices()
-        self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations,
+        self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations, 0, self.n_entities,
                                self.att_rowptr.data_ptr(), self.att_tail.data_ptr(), self.att_rel.data_ptr(),
                                self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr())
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
@@ -83,6 +83,22 @@ class GraphPlan:
     # -- helpers ------------------------------------------------------------------------------
     def byref(self):
         return C.byref(self.c)
+
+    def set_row_range(self, begin: int, end: int) -> None:
+        """Restrict the attention / aggregation kernels to head rows [begin, end) (multi-GPU row partition)."""
+        if not (0 <= begin <= end <= self.n_entities):
+            raise ValueError("bad row range")
+        self.c.row_begin, self.c.row_end = int(begin), int(end)
+
+    @staticmethod
+    def fingerprint(h: torch.Tensor, t: torch.Tensor, r: torch.Tensor):
+        """Order-independent content fingerprint of a device edge list (one tiny kernel + one host sync)."""
+        _lib.require_cuda(h, "h_list")
+        fp = torch.empty(2, dtype=torch.int64, device=h.device)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.load().lkg_edge_fingerprint(h.data_ptr(), t.data_ptr(), r.data_ptr(), h.numel(),
+                                                        fp.data_ptr(), _lib.stream()))
+        return (h.numel(), *fp.tolist())
 
     def scratch(self) -> int:
         return self._scratch.data_ptr()

@@ -355,11 +355,12 @@ class LiteralKG(nn.Module):
     def update_attention(self, h_list, t_list, r_list, relations):
         """model.py:444-471.  Entirely on device: no host round trip, no per-relation Python loop."""
         dev = self._param_device()
-        key = (h_list.data_ptr(), t_list.data_ptr(), r_list.data_ptr(), h_list.numel(),
-               h_list._version, t_list._version, r_list._version, tuple(int(x) for x in relations))
+        i64 = dict(device=dev, dtype=torch.int64, non_blocking=True)
+        h, t, r = h_list.to(**i64).contiguous(), t_list.to(**i64).contiguous(), r_list.to(**i64).contiguous()
+        # the CSR plan only depends on the edge list: recognise an unchanged list by content, not by address
+        key = (GraphPlan.fingerprint(h, t, r), tuple(int(x) for x in relations))
         if self._att_plan is None or self._att_key != key:
-            self._att_plan = GraphPlan(h_list.to(dev), t_list.to(dev), r_list.to(dev), self.n_entities,
-                                       self.n_relations, relations)
+            self._att_plan = GraphPlan(h, t, r, self.n_entities, self.n_relations, relations)
             self._att_key = key
         plan = self._att_plan
         with torch.no_grad():

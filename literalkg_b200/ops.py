@@ -13,9 +13,47 @@ from . import _lib
 from .graph import GraphPlan
 
 
-def _dev_guard(t: torch.Tensor):
-    _lib.require_cuda(t)
-    return torch.cuda.device(t.device)
+class Profile:
+    """Optional per-entry-point CUDA-event timing + kernel-launch counting (used by bench.py).  Events are
+    recorded on the current stream, which is the stream every kernel of this library is launched on."""
+
+    def __init__(self):
+        self.events = []          # (name, start_event, end_event)
+        self.launches = 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            tot, cnt = out.get(name, (0.0, 0))
+            out[name] = (tot + a.elapsed_time(b), cnt + 1)
+        return {k: {"ms_total": v[0], "calls": v[1], "ms_avg": v[0] / v[1]} for k, v in out.items()}
+
+
+PROFILE: Optional[Profile] = None
+
+
+class _dev_guard:
+    """Sets the CUDA device of ``t`` for the call and, when profiling is on, brackets it with events."""
+
+    def __init__(self, t: torch.Tensor, name: Optional[str] = None, kernels: int = 1):
+        _lib.require_cuda(t)
+        self.guard = torch.cuda.device(t.device)
+        self.name, self.kernels = name, kernels
+
+    def __enter__(self):
+        self.guard.__enter__()
+        if PROFILE is not None and self.name:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and self.name:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.events.append((self.name, self.start, end))
+            PROFILE.launches += self.kernels
+        return self.guard.__exit__(*exc)
 
 
 def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
@@ -26,7 +64,7 @@ def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
         raise ValueError("update_att needs embed_dim == relation_dim (model.py:441 adds the two tables)")
     if out is None:
         out = torch.empty(max(plan.nnz, 1), dtype=torch.float32, device=entity.device)[:plan.nnz]
-    with _dev_guard(entity):
+    with _dev_guard(entity, "attn_update"):
         _lib.check(_lib.load().lkg_attn_update(plan.byref(), entity.data_ptr(), entity.stride(0),
                                                relation.data_ptr(), relation.stride(0), entity.shape[1],
                                                out.data_ptr(), plan.scratch(), _lib.stream()))
@@ -46,7 +84,7 @@ def linear(segments: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optiona
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
     op = _lib.operand(segs, rows)
-    with _dev_guard(weight):
+    with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
         _lib.check(_lib.load().lkg_linear_fwd(C.byref(op), m, weight.data_ptr(), weight.stride(0), n,
                                               _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
                                               out.data_ptr(), out.stride(0), _lib.stream()))
@@ -63,7 +101,7 @@ def gate(segments: Sequence[torch.Tensor], w_pair: torch.Tensor, bias_pair: torc
     if out is None:
         out = torch.empty((m, dim), dtype=torch.float32, device=x_ent.device)
     op = _lib.operand(segs)
-    with _dev_guard(x_ent):
+    with _dev_guard(x_ent, "gate"):
         _lib.check(_lib.load().lkg_gate_fwd(C.byref(op), m, w_pair.data_ptr(), w_pair.stride(0),
                                             bias_pair.data_ptr(), dim, x_ent.data_ptr(), x_ent.stride(0),
                                             out.data_ptr(), out.stride(0), _lib.stream()))
@@ -89,7 +127,7 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
     pb_c = _lib.f32c(pb)
     pa_c = pb_c if same else (None if pa is None else _lib.f32c(pa))
     p2_c = None if p2 is None else _lib.f32c(p2)
-    with _dev_guard(ego):
+    with _dev_guard(ego, f"aggregate_d{d_in}"):
         _lib.check(_lib.load().lkg_aggregate_fwd(
             plan.byref(), _lib.ptr(a_values), ego.data_ptr(), ego.stride(0), d_in, d_out,
             _lib.ptr(pa_c), pb_c.data_ptr(), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
@@ -106,7 +144,7 @@ def score(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor,
     heads = heads.to(device=emb.device, dtype=torch.int64).contiguous()
     tails = tails.to(device=emb.device, dtype=torch.int64).contiguous()
     out = torch.empty((heads.numel(), tails.numel()), dtype=torch.float32, device=emb.device)
-    with _dev_guard(emb):
+    with _dev_guard(emb, "score", 1 if minmax is None else 2):
         lib = _lib.load()
         if minmax is not None:
             _lib.check(lib.lkg_minmax_reset(minmax.data_ptr(), _lib.stream()))
@@ -122,7 +160,7 @@ def predict(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor, milesto
     s = score(emb, heads, tails, mm)
     pred = torch.empty(s.shape, dtype=torch.int32, device=emb.device)
     if s.numel():
-        with _dev_guard(emb):
+        with _dev_guard(emb, "predict_threshold"):
             _lib.check(_lib.load().lkg_predict_threshold(s.data_ptr(), s.stride(0), s.shape[0], s.shape[1],
                                                          mm.data_ptr(), float(milestone), pred.data_ptr(),
                                                          pred.stride(0), _lib.stream()))
@@ -140,7 +178,7 @@ def topk_rows(scores: torch.Tensor, k: int, target_cols: Optional[torch.Tensor] 
     if target_cols is not None:
         target_cols = target_cols.to(device=scores.device, dtype=torch.int64).contiguous()
         ranks = torch.empty(rows, dtype=torch.int64, device=scores.device)
-    with _dev_guard(scores):
+    with _dev_guard(scores, "topk_rows"):
         _lib.check(_lib.load().lkg_topk_rows(scores.data_ptr(), scores.stride(0), rows, cols, k, vals.data_ptr(),
                                              idx.data_ptr(), _lib.ptr(target_cols), _lib.ptr(ranks), _lib.stream()))
     return vals, idx, ranks
