@@ -60,16 +60,19 @@ typedef struct {
     const int32_t* col;         /* [nnz] */
 } lkg_graph;
 
-/* K-concatenated row-major operand: logical A[m, :] = [ src0[row(m), 0:k0] | src1[row(m), 0:k1] | ... ]
- * where row(m) = rows ? rows[m] : m.  Used for the virtual torch.cat of gate.py:23 / model.py:309. */
+/* bf16 "planes" operand of the tensor-core GEMMs.  A value x is stored as hi = bf16(x) and
+ * lo = bf16(x - hi): two bf16 matrices [rows, ld] that are `plane_stride` elements apart (hi first).
+ * An operand is a K-concatenation of up to LKG_MAX_SEGMENTS such matrices (the virtual torch.cat of
+ * gate.py:23 / model.py:309): logical A[m, :] = [ seg0[m, 0:k0] | seg1[m, 0:k1] | ... ].
+ * Base pointers, row strides and plane strides must be 16-byte aligned (ld % 8 == 0). */
 #define LKG_MAX_SEGMENTS 4
 typedef struct {
     int32_t n_segments;
-    const float* ptr[LKG_MAX_SEGMENTS];
+    const uint16_t* ptr[LKG_MAX_SEGMENTS];
     int64_t ld[LKG_MAX_SEGMENTS];
+    int64_t plane_stride[LKG_MAX_SEGMENTS];
     int32_t k[LKG_MAX_SEGMENTS];
-    const int64_t* rows;        /* optional gather indices [M] (nullable) */
-} lkg_operand;
+} lkg_planes;
 
 typedef enum { LKG_ACT_NONE = 0, LKG_ACT_LEAKY_RELU = 1 } lkg_activation;
 typedef enum { LKG_AGG_GCN = 0, LKG_AGG_GRAPHSAGE = 1, LKG_AGG_BI_INTERACTION = 2 } lkg_aggregator;
@@ -119,18 +122,29 @@ int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t ld_entity,
                     const float* relation, int64_t ld_relation, int32_t dim,
                     float* values, void* workspace, void* stream);
 
-/* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) (torch Linear layout: B is [out, in]) ------- */
-/* out = act(A @ B^T + bias)  (linear_gat model.py:309-310; h0 residual pre-projection) */
-int lkg_linear_fwd(const lkg_operand* a, int64_t m, const float* b, int64_t ldb, int32_t n,
-                   const float* bias /*nullable [n]*/, int32_t activation,
-                   float* out, int64_t ldo, void* stream);
-/* Literal gate (gate.py:22-28 / :45-51).  `x` is the K-concatenation (entity | literals...);
- * w_pair is [2*dim, K] with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of
- * output j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]).  x_ent is the entity table used
- * by the mix  out = (1 - z) * x_ent + z * tanh(g). */
-int lkg_gate_fwd(const lkg_operand* x, int64_t m, const float* w_pair, int64_t ldw,
-                 const float* bias_pair, int32_t dim, const float* x_ent, int64_t ld_ent,
-                 float* out, int64_t ldo, void* stream);
+/* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores, three bf16 products per
+ *      k-step (hi*hi + lo*hi + hi*lo) accumulated in fp32 TMEM (torch Linear layout: B is [out, in]) ---- */
+/* fp32 [m, k] (row stride ld, optional row gather) -> planes [2][m][ld_planes], columns >= k zero filled. */
+int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
+                     uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream);
+/* Number of columns of a packed weight: every K segment is padded to a multiple of 64. Host call. */
+int lkg_packed_weight_cols(const int32_t* seg_k /*host*/, int32_t n_segments, int32_t* cols /*host out*/);
+/* fp32 weight [n, sum(seg_k)] -> planes [2][n][packed cols] with per-segment zero padding. */
+int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k /*host*/, int32_t n_segments,
+                    uint16_t* planes, int64_t plane_stride, void* stream);
+/* out = act(A @ B^T + bias)  (linear_gat model.py:309-310; the h0 @ Q residual terms).  b: packed weight
+ * planes (one segment descriptor whose k is the packed column count).  out_planes (nullable) receives
+ * the hi/lo split of the result for a following GEMM. */
+int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n,
+                   const float* bias /*nullable [n]*/, int32_t activation, float* out, int64_t ldo,
+                   uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream);
+/* Literal gate (gate.py:22-28 / :45-51).  x = (entity | literals...) planes; w_pair = packed planes of
+ * the [2*dim, K] matrix with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of output
+ * j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]); x_ent = fp32 entity table for the mix
+ * out = (1 - z) * x_ent + z * tanh(g). */
+int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
+                 int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
+                 uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream);
 
 /* ---- one aggregator layer, forward (model.py:101-164 + F.normalize of model.py:305) ----------
  * side = A_in @ ego fused with the combine, LeakyReLU, LayerNorm, optional dropout mask and the
@@ -148,14 +162,15 @@ int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* eg
                       const float* ln_weight, const float* ln_bias,
                       const float* drop_mask /*nullable [N,d_out] multiplicative*/,
                       float* x_out, int64_t ld_x, float* xn_out /*nullable*/, int64_t ld_xn,
+                      uint16_t* xn_planes /*nullable: hi/lo copy of xn*/, int64_t ld_planes, int64_t plane_stride,
                       void* workspace, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
-/* scores[B,Nt] = emb[heads] @ emb[tails]^T; minmax_dev (nullable) is an opaque uint32[2] running
+/* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final
+ * embeddings, tails: the candidate rows); minmax_dev (nullable) is an opaque uint32[2] running
  * {min, max} state (order-preserving encoding) that must be reset with lkg_minmax_reset first. */
-int lkg_score(const float* emb, int64_t ld_emb, int32_t dim, const int64_t* heads, int64_t n_heads,
-              const int64_t* tails, int64_t n_tails, float* scores, int64_t ld_scores,
-              uint32_t* minmax_dev, void* stream);
+int lkg_score(const lkg_planes* heads, int64_t n_heads, const lkg_planes* tails, int64_t n_tails,
+              float* scores, int64_t ld_scores, uint32_t* minmax_dev, void* stream);
 int lkg_minmax_reset(uint32_t* minmax_dev, void* stream);
 /* pred = ((s - min) / (max - min) > milestone) as int32 (model.py:490-491); NaN compares false. */
 int lkg_predict_threshold(const float* scores, int64_t ld_scores, int64_t n_heads, int64_t n_tails,

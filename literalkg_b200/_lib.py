@@ -23,9 +23,9 @@ class LkgGraph(C.Structure):
                 ("rowptr", vp), ("col", vp)]
 
 
-class LkgOperand(C.Structure):
+class LkgPlanes(C.Structure):
     _fields_ = [("n_segments", i32), ("ptr", vp * LKG_MAX_SEGMENTS), ("ld", i64 * LKG_MAX_SEGMENTS),
-                ("k", i32 * LKG_MAX_SEGMENTS), ("rows", vp)]
+                ("plane_stride", i64 * LKG_MAX_SEGMENTS), ("k", i32 * LKG_MAX_SEGMENTS)]
 
 
 # name -> (restype, argtypes); mirrors include/lkg.h one to one
@@ -41,12 +41,17 @@ SIGNATURES = {
     "lkg_laplacian_init": (C.c_int, [C.POINTER(LkgGraph), C.c_int, vp, vp, vp]),
     "lkg_attn_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),
-    "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgOperand), i64, vp, i64, i32, vp, i32, vp, i64, vp]),
-    "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgOperand), i64, vp, i64, vp, i32, vp, i64, vp, i64, vp]),
+    "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, i64, vp]),
+    "lkg_packed_weight_cols": (C.c_int, [C.POINTER(i32), i32, C.POINTER(i32)]),
+    "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, vp, i64, vp]),
+    "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64,
+                                 i64, vp]),
+    "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), vp, i32, vp, i64, vp, i64, vp, i64,
+                               i64, vp]),
     "lkg_aggregate_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "lkg_aggregate_fwd": (C.c_int, [C.POINTER(LkgGraph), vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp,
-                                    vp, vp, i64, vp, i64, vp, vp]),
-    "lkg_score": (C.c_int, [vp, i64, i32, vp, i64, vp, i64, vp, i64, vp, vp]),
+                                    vp, vp, i64, vp, i64, vp, i64, i64, vp, vp]),
+    "lkg_score": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i64, vp, i64, vp, vp]),
     "lkg_minmax_reset": (C.c_int, [vp, vp]),
     "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),
     "lkg_topk_rows": (C.c_int, [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp]),
@@ -106,14 +111,52 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-def operand(segments, rows: Optional[torch.Tensor] = None) -> LkgOperand:
-    """segments: list of 2-D fp32 CUDA tensors with unit inner stride (row stride = leading dim)."""
-    op = LkgOperand()
+class Planes:
+    """bf16 hi/lo planes of an fp32 matrix: tensor [2, rows, ld] (ld % 8 == 0) with logical width k."""
+
+    def __init__(self, rows: int, k: int, device, ld: Optional[int] = None):
+        self.rows, self.k = int(rows), int(k)
+        self.ld = int(ld) if ld is not None else (self.k + 7) // 8 * 8
+        assert self.ld % 8 == 0 and self.ld >= self.k
+        self.t = torch.empty((2, max(self.rows, 1), self.ld), dtype=torch.bfloat16, device=device)
+
+    @property
+    def plane_stride(self) -> int:
+        return self.t.stride(0)
+
+    def ptr(self, col: int = 0) -> int:
+        """Base address of a TMA-readable window: needs a 16-byte aligned column."""
+        assert col % 8 == 0
+        return self.t.data_ptr() + 2 * col
+
+    def elem_ptr(self, col: int = 0) -> int:
+        """Address of column ``col`` for kernels that write planes element-wise (no alignment needed)."""
+        return self.t.data_ptr() + 2 * col
+
+    def view(self, col: int, k: int) -> "PlanesView":
+        return PlanesView(self, col, k)
+
+
+class PlanesView:
+    """Column window [col, col + k) of a Planes buffer (col % 8 == 0)."""
+
+    def __init__(self, base, col: int, k: int):
+        self.base, self.col, self.k = base, int(col), int(k)
+        self.rows, self.ld, self.plane_stride = base.rows, base.ld, base.plane_stride
+
+    def ptr(self, col: int = 0) -> int:
+        return self.base.ptr(self.col + col)
+
+    def elem_ptr(self, col: int = 0) -> int:
+        return self.base.elem_ptr(self.col + col)
+
+
+def planes_operand(segments) -> LkgPlanes:
+    op = LkgPlanes()
     op.n_segments = len(segments)
     for i, s in enumerate(segments):
-        assert s.dim() == 2 and s.stride(1) == 1 and s.dtype == torch.float32
-        op.ptr[i] = s.data_ptr()
-        op.ld[i] = s.stride(0)
-        op.k[i] = s.shape[1]
-    op.rows = ptr(rows)
+        op.ptr[i] = s.ptr()
+        op.ld[i] = s.ld
+        op.plane_stride[i] = s.plane_stride
+        op.k[i] = s.k
     return op

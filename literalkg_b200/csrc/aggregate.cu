@@ -10,6 +10,8 @@
 //   phase 3  leaky / add / LayerNorm / mask / L2 normalise, all in registers + warp shuffles
 // Folding (host side): linear(res(hi)) = hi @ P + h0 @ Q + c, P = (1-a) M W^T.
 // HBM bound: algorithmic bytes = nnz*(4 col + 4 val + 4 d_in) + N*(4 d_in + 8 + r terms + 2*4*d_out).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace lkg {
@@ -38,6 +40,8 @@ struct AggParams {
     int64_t ld_x;
     float* xn_out;
     int64_t ld_xn;
+    __nv_bfloat16* xn_planes;   // optional hi/lo bf16 copy of xn (operand of the linear_gat tensor-core GEMM)
+    int64_t ld_planes, plane_stride;
     int* counter;
     int p_stride;      // padded row stride (floats) of P in shared memory
 };
@@ -228,12 +232,21 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
                 emb[c] = x;
                 sq = fmaf(x, x, sq);
             }
-            if (p.xn_out) {
+            if (p.xn_out || p.xn_planes) {
                 const float inv = 1.f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     const int ch = lane + 32 * c;
-                    if (ch < d_out) p.xn_out[(int64_t)row * p.ld_xn + ch] = emb[c] * inv;
+                    if (ch < d_out) {
+                        const float xn = emb[c] * inv;
+                        if (p.xn_out) p.xn_out[(int64_t)row * p.ld_xn + ch] = xn;
+                        if (p.xn_planes) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(xn);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(xn - __bfloat162float(h));
+                            p.xn_planes[(int64_t)row * p.ld_planes + ch] = h;
+                            p.xn_planes[p.plane_stride + (int64_t)row * p.ld_planes + ch] = l;
+                        }
+                    }
                 }
             }
         }
@@ -277,7 +290,8 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
                                  int32_t d_in, int32_t d_out, const float* pa, const float* pb, const float* p2,
                                  const float* r1, const float* r2, int64_t ld_r, const float* ln_weight,
                                  const float* ln_bias, const float* drop_mask, float* x_out, int64_t ld_x,
-                                 float* xn_out, int64_t ld_xn, void* workspace, void* stream_) {
+                                 float* xn_out, int64_t ld_xn, uint16_t* xn_planes, int64_t ld_planes,
+                                 int64_t plane_stride, void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(g && ego && pb && ln_weight && ln_bias && x_out && workspace, "null argument");
     LKG_REQUIRE(g->nnz == 0 || a_values != nullptr, "a_values is null");
@@ -324,6 +338,9 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     p.ld_x = ld_x;
     p.xn_out = xn_out;
     p.ld_xn = ld_xn;
+    p.xn_planes = reinterpret_cast<__nv_bfloat16*>(xn_planes);
+    p.ld_planes = ld_planes;
+    p.plane_stride = plane_stride;
     p.counter = static_cast<int*>(workspace);
     // lane c reads sp[d * ps + c]: any stride is conflict free for 32 consecutive channels; pad to a
     // multiple of 4 floats to keep rows 16-byte aligned

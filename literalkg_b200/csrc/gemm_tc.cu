@@ -1,0 +1,571 @@
+// Tensor-core GEMM engine of the path:  C[M,N] = epilogue( A[M,K] @ B[N,K]^T ), fp32-class accuracy.
+//
+//   lkg_linear_fwd : act(A B^T + bias)                      linear_gat (model.py:309-310) and the h0 @ Q residual terms
+//   lkg_gate_fwd   : literal gate, tanh / sigmoid / mix      GateMul / Gate (gate.py:22-28, 45-51)
+//   lkg_score      : emb[heads] @ emb[tails]^T (+ min/max)   calc_score / predict_links (model.py:473-491)
+//
+// sm_100a design
+//   * operands live in HBM as bf16 "planes": x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  (2 x 2 bytes, the
+//     same footprint as the fp32 value).  Three tcgen05.mma per k-step  hi*hi + lo*hi + hi*lo  accumulate in
+//     fp32 TMEM; the dropped lo*lo term and the residual of the split are ~2^-17 relative, two orders below
+//     the 1e-3 parity bound (a single bf16 pass would be ~2^-9 and break it);
+//   * TMA (cp.async.bulk.tensor.3d, 128-byte swizzle) stages {hi, lo} x 64-wide K chunks of A (128 rows) and
+//     B (N-tile rows) into shared memory; a 2-stage mbarrier ring feeds one MMA-issuing thread;
+//   * accumulators: 2 x 256 TMEM columns, double buffered so the epilogue of tile i overlaps the MMAs of
+//     tile i+1; 4 epilogue warps read them back with tcgen05.ld (32 lanes x 16 columns per instruction);
+//   * persistent CTAs (one per SM), static tile round-robin, N fastest so that co-running CTAs share A tiles in L2;
+//   * the virtual torch.cat of the reference is a list of K segments, each with its own tensor map.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace lkg {
+namespace {
+
+constexpr int kBM = 128;          // rows per tile == TMEM lanes
+constexpr int kBK = 64;           // bf16 elements per K chunk == one 128-byte swizzle row
+constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
+constexpr int kStages = 2;
+constexpr int kThreads = 192;     // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
+constexpr uint32_t kStageBytes = kABytes + 2 * kMaxBN * kBK * 2;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum EpiKind { kEpiLinear = 0, kEpiGate = 1, kEpiScore = 2 };
+
+struct TcParams {
+    CUtensorMap a_map[LKG_MAX_SEGMENTS];
+    CUtensorMap b_map;
+    int n_segments;
+    int seg_chunks[LKG_MAX_SEGMENTS];   // number of 64-wide chunks of each A segment
+    int seg_bcol[LKG_MAX_SEGMENTS];     // first column of the segment inside the packed B planes
+    int64_t m;
+    int n;                              // valid output columns (GEMM N)
+    int bn;                             // N tile (multiple of 16, <= 256)
+    int tiles_m, tiles_n;
+    int m_fastest;
+    // epilogue
+    const float* bias;                  // linear: [n]; gate: interleaved pairs [n]
+    int act;
+    float* out;
+    int64_t ldo;
+    __nv_bfloat16* out_planes;          // optional hi/lo copy of the output (feeds the next GEMM)
+    int64_t ld_planes, plane_stride;
+    const float* x_ent;                 // gate mix input
+    int64_t ld_ent;
+    uint32_t* minmax;                   // score: ordered-encoded running {min, max}
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared memory matrix descriptor (start >> 4, SBO = 8 rows * 128 B, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t order_enc(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ---- epilogues: one thread = one output row, 16 consecutive accumulator columns per call -----------
+template <int EPI>
+__device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int col0, const float (&acc)[16],
+                                           float& lo, float& hi) {
+    if (row >= p.m) return;
+    if (EPI == kEpiGate) {
+        // columns come in (g, z) pairs; 16 accumulator columns -> 8 output channels
+        const int c0 = col0 >> 1;
+        const int dim = p.n >> 1;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            o[j] = 0.f;
+            if (c < dim) {
+                const float g = tanh_acc(acc[2 * j] + __ldg(p.bias + 2 * c));
+                const float z = sigmoid_acc(acc[2 * j + 1] + __ldg(p.bias + 2 * c + 1));
+                const float e = __ldg(p.x_ent + row * p.ld_ent + c);
+                o[j] = (1.f - z) * e + z * g;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < dim) p.out[row * p.ldo + c0 + j] = o[j];
+        if (p.out_planes) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < dim) {
+                    __nv_bfloat16 h, l;
+                    split_bf16(o[j], h, l);
+                    p.out_planes[row * p.ld_planes + c0 + j] = h;
+                    p.out_planes[p.plane_stride + row * p.ld_planes + c0 + j] = l;
+                }
+        }
+    } else {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = col0 + j;
+            float v = acc[j];
+            if (EPI == kEpiLinear) {
+                if (p.bias && c < p.n) v += __ldg(p.bias + c);
+                if (p.act == LKG_ACT_LEAKY_RELU) v = leaky(v);
+            }
+            o[j] = v;
+            if (EPI == kEpiScore && c < p.n) {
+                lo = fminf(lo, v);
+                hi = fmaxf(hi, v);
+            }
+        }
+        float* dst = p.out + row * p.ldo + col0;
+        if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.n) dst[j] = o[j];
+        }
+        if (EPI == kEpiLinear && p.out_planes) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.n) {
+                    __nv_bfloat16 h, l;
+                    split_bf16(o[j], h, l);
+                    p.out_planes[row * p.ld_planes + col0 + j] = h;
+                    p.out_planes[p.plane_stride + row * p.ld_planes + col0 + j] = l;
+                }
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full = bars;                 // [kStages]  TMA bytes landed
+    uint64_t* empty = bars + kStages;      // [kStages]  MMAs that read the stage retired
+    uint64_t* acc_full = bars + 2 * kStages;       // [2]  accumulator complete
+    uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2]  accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+    int n_chunks = 0;
+    for (int s = 0; s < p.n_segments; ++s) n_chunks += p.seg_chunks[s];
+
+    if (warp == 4 && lane == 0) {
+        for (int s = 0; s < p.n_segments; ++s)
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.b_map) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_bytes = 2u * (uint32_t)p.bn * kBK * 2u;
+
+    auto tile_coords = [&](int tile, int& mb, int& nb) {
+        if (p.m_fastest) {
+            mb = tile % p.tiles_m;
+            nb = tile / p.tiles_m;
+        } else {
+            nb = tile % p.tiles_n;
+            mb = tile / p.tiles_n;
+        }
+    };
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int mb, nb;
+                tile_coords(tile, mb, nb);
+                for (int s = 0; s < p.n_segments; ++s) {
+                    for (int j = 0; j < p.seg_chunks[s]; ++j) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* st = smem + stage * kStageBytes;
+                        mbar_expect_tx(&full[stage], kABytes + b_bytes);
+                        tma_load_3d(&p.a_map[s], &full[stage], st, j * kBK, mb * kBM, 0);
+                        tma_load_3d(&p.b_map, &full[stage], st + kABytes, p.seg_bcol[s] + j * kBK, nb * p.bn, 0);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(p.bn);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kMaxBN;
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t a_lo = a_hi + kBM * kBK * 2;
+                    const uint32_t b_hi = a_hi + kABytes;
+                    const uint32_t b_lo = b_hi + (uint32_t)p.bn * kBK * 2;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint32_t koff = k * 32;   // 16 bf16 = 32 bytes inside the swizzle row
+                        const uint64_t dah = umma_desc(a_hi + koff), dal = umma_desc(a_lo + koff);
+                        const uint64_t dbh = umma_desc(b_hi + koff), dbl = umma_desc(b_lo + koff);
+                        tc_mma_bf16(tmem_d, dah, dbh, idesc, (c | k) != 0);
+                        tc_mma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+                    }
+                    tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&acc_full[acc]);             // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-3: TMEM lane = tile row =====
+        int it = 0;
+        float lo = INFINITY, hi = -INFINITY;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int mb, nb;
+            tile_coords(tile, mb, nb);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const int64_t row = (int64_t)mb * kBM + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * kMaxBN;
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                epilogue16<EPI>(p, row, nb * p.bn + c0, v, lo, hi);
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+        }
+        if (EPI == kEpiScore && p.minmax) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(kFull, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(kFull, hi, o));
+            }
+            if (lane == 0 && lo <= hi) {
+                atomicMin(p.minmax, order_enc(lo));
+                atomicMax(p.minmax + 1, order_enc(hi));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// planes tensor: bf16 [2 planes][rows][ld] with `plane_stride` elements between the planes; logical width k
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld, int64_t plane_stride, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    LKG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (ld * 2) % 16 == 0 && (plane_stride * 2) % 16 == 0,
+                "bf16 planes must be 16-byte aligned (base, row stride, plane stride)");
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LKG_OK;
+}
+
+int pick_bn(int n) {
+    // smallest number of N tiles, then the smallest tile (multiple of 16) that covers n
+    const int tiles = (n + kMaxBN - 1) / kMaxBN;
+    int bn = ((n + tiles - 1) / tiles + 15) / 16 * 16;
+    return bn < 16 ? 16 : bn;
+}
+
+template <int EPI>
+int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, int n, cudaStream_t stream) {
+    LKG_REQUIRE(a && b && a->n_segments >= 1 && a->n_segments <= LKG_MAX_SEGMENTS && b->n_segments == 1, "bad operands");
+    LKG_REQUIRE(m > 0 && n > 0, "empty GEMM");
+    p.n_segments = a->n_segments;
+    p.m = m;
+    p.n = n;
+    p.bn = pick_bn(n);
+    p.tiles_m = (int)((m + kBM - 1) / kBM);
+    p.tiles_n = (n + p.bn - 1) / p.bn;
+    int bcol = 0;
+    for (int s = 0; s < a->n_segments; ++s) {
+        LKG_REQUIRE(a->ptr[s] && a->k[s] > 0, "bad A segment %d", s);
+        p.seg_chunks[s] = (a->k[s] + kBK - 1) / kBK;
+        p.seg_bcol[s] = bcol;
+        bcol += p.seg_chunks[s] * kBK;
+        if (int rc = make_map(&p.a_map[s], a->ptr[s], m, a->k[s], a->ld[s], a->plane_stride[s], kBM)) return rc;
+    }
+    LKG_REQUIRE(b->k[0] == bcol || (a->n_segments == 1 && b->k[0] == a->k[0]),
+                "B has %d columns, the A segments need %d", b->k[0], bcol);
+    if (int rc = make_map(&p.b_map, b->ptr[0], n, b->k[0], b->ld[0], b->plane_stride[0], p.bn)) return rc;
+    auto kern = tc_gemm_kernel<EPI>;
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    LKG_LAUNCH_CHECK("tc_gemm_kernel");
+    return LKG_OK;
+}
+
+// ---- operand preparation -------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
+                                    int64_t m, int k, __nv_bfloat16* __restrict__ dst, int64_t ldp, int64_t plane_stride) {
+    const int64_t total = m * ldp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ldp;
+        const int c = (int)(i - r * ldp);
+        float x = 0.f;
+        if (c < k) x = src[(rows ? rows[r] : r) * ld + c];
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        dst[i] = h;
+        dst[plane_stride + i] = l;
+    }
+}
+
+// weight [n, sum(seg_k)] fp32 -> planes [2][n][sum(ceil64(seg_k))], every segment zero padded to a multiple of 64
+struct PackSegs {
+    int n_segments;
+    int k[LKG_MAX_SEGMENTS];
+};
+__global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int n, PackSegs segs,
+                                   __nv_bfloat16* __restrict__ dst, int kb, int64_t plane_stride) {
+    const int64_t total = (int64_t)n * kb;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kb);
+        int c = (int)(i - (int64_t)r * kb);
+        int src_col = 0;
+        float x = 0.f;
+        for (int s = 0; s < segs.n_segments; ++s) {
+            const int padded = (segs.k[s] + kBK - 1) / kBK * kBK;
+            if (c < padded) {
+                if (c < segs.k[s]) x = w[(int64_t)r * ldw + src_col + c];
+                break;
+            }
+            c -= padded;
+            src_col += segs.k[s];
+        }
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        dst[i] = h;
+        dst[plane_stride + i] = l;
+    }
+}
+
+inline int grid_1d(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+}  // namespace lkg
+
+using namespace lkg;
+
+extern "C" int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
+                                uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(src && planes && m >= 0 && k > 0 && ld_planes >= k && plane_stride >= m * ld_planes, "bad split arguments");
+    if (m == 0) return LKG_OK;
+    split_planes_kernel<<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, (__nv_bfloat16*)planes,
+                                                                    ld_planes, plane_stride);
+    LKG_LAUNCH_CHECK("split_planes_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_packed_weight_cols(const int32_t* seg_k, int32_t n_segments, int32_t* cols) {
+    LKG_REQUIRE(seg_k && cols && n_segments >= 1 && n_segments <= LKG_MAX_SEGMENTS, "bad segment list");
+    int c = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        LKG_REQUIRE(seg_k[s] > 0, "bad segment width");
+        c += (seg_k[s] + kBK - 1) / kBK * kBK;
+    }
+    *cols = c;
+    return LKG_OK;
+}
+
+extern "C" int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k, int32_t n_segments,
+                               uint16_t* planes, int64_t plane_stride, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t kb = 0;
+    if (int rc = lkg_packed_weight_cols(seg_k, n_segments, &kb)) return rc;
+    LKG_REQUIRE(w && planes && n > 0 && plane_stride >= (int64_t)n * kb, "bad pack arguments");
+    PackSegs segs{};
+    segs.n_segments = n_segments;
+    for (int s = 0; s < n_segments; ++s) segs.k[s] = seg_k[s];
+    pack_weight_kernel<<<grid_1d((int64_t)n * kb), 256, 0, stream>>>(w, ldw, n, segs, (__nv_bfloat16*)planes, kb, plane_stride);
+    LKG_LAUNCH_CHECK("pack_weight_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n, const float* bias,
+                              int32_t activation, float* out, int64_t ldo, uint16_t* out_planes, int64_t ld_planes,
+                              int64_t plane_stride, void* stream_) {
+    LKG_REQUIRE(out && ldo >= n, "bad linear output");
+    if (m == 0) return LKG_OK;
+    TcParams p{};
+    p.bias = bias;
+    p.act = activation;
+    p.out = out;
+    p.ldo = ldo;
+    p.out_planes = (__nv_bfloat16*)out_planes;
+    p.ld_planes = ld_planes;
+    p.plane_stride = plane_stride;
+    return launch_tc<kEpiLinear>(p, a, m, b, n, (cudaStream_t)stream_);
+}
+
+extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
+                            int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
+                            uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream_) {
+    LKG_REQUIRE(bias_pair && x_ent && out && dim > 0 && ldo >= dim, "bad gate arguments");
+    if (m == 0) return LKG_OK;
+    TcParams p{};
+    p.bias = bias_pair;
+    p.out = out;
+    p.ldo = ldo;
+    p.out_planes = (__nv_bfloat16*)out_planes;
+    p.ld_planes = ld_planes;
+    p.plane_stride = plane_stride;
+    p.x_ent = x_ent;
+    p.ld_ent = ld_ent;
+    return launch_tc<kEpiGate>(p, x, m, w_pair, 2 * dim, (cudaStream_t)stream_);
+}
+
+extern "C" int lkg_score(const lkg_planes* heads, int64_t n_heads, const lkg_planes* tails, int64_t n_tails,
+                         float* scores, int64_t ld_scores, uint32_t* minmax_dev, void* stream_) {
+    LKG_REQUIRE(scores && n_heads >= 0 && n_tails >= 0 && n_tails < (1ll << 31) && ld_scores >= n_tails, "bad score shape");
+    if (n_heads == 0 || n_tails == 0) return LKG_OK;
+    LKG_REQUIRE(heads && tails && heads->n_segments == 1 && tails->n_segments == 1 && heads->k[0] == tails->k[0],
+                "score operands must be single-segment planes of equal width");
+    TcParams p{};
+    p.out = scores;
+    p.ldo = ld_scores;
+    p.minmax = minmax_dev;
+    p.m_fastest = 1;    // all head tiles of one tail tile run together: the big operand streams through L2 once
+    return launch_tc<kEpiScore>(p, heads, n_heads, tails, (int)n_tails, (cudaStream_t)stream_);
+}

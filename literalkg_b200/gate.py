@@ -41,9 +41,9 @@ class GateMul(nn.Module):
         return _pair(self.g.weight, (self.gate_ent.weight, self.gate_num_lit.weight, self.gate_txt_lit.weight),
                      self.g.bias, self.gate_bias)
 
-    def forward(self, x_ent, x_lit_num, x_lit_txt, out=None):
+    def forward(self, x_ent, x_lit_num, x_lit_txt, out=None, **planes):
         from .autograd import gate_apply
-        return gate_apply(self, (x_ent, x_lit_num, x_lit_txt), out)
+        return gate_apply(self, (x_ent, x_lit_num, x_lit_txt), out, **planes)
 
 
 class Gate(nn.Module):
@@ -63,6 +63,6 @@ class Gate(nn.Module):
     def packed(self):
         return _pair(self.g.weight, (self.gate_ent.weight, self.gate_lit.weight), self.g.bias, self.gate_bias)
 
-    def forward(self, x_ent, x_lit, out=None):
+    def forward(self, x_ent, x_lit, out=None, **planes):
         from .autograd import gate_apply
-        return gate_apply(self, (x_ent, x_lit), out)
+        return gate_apply(self, (x_ent, x_lit), out, **planes)

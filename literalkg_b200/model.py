@@ -129,11 +129,11 @@ class Aggregator(nn.Module):
 
     def run(self, plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, f: Dict[str, Optional[torch.Tensor]],
             r1: Optional[torch.Tensor], r2: Optional[torch.Tensor], x_out: torch.Tensor,
-            xn_out: Optional[torch.Tensor], fold_ego: bool = False) -> torch.Tensor:
+            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None) -> torch.Tensor:
         pa = None if fold_ego else f["pa"]
         return ops.aggregate(plan, a_values, ego, self.out_dim, pa, f["pb"], f["p2"], r1, r2,
                              self.layer_normalize.weight, self.layer_normalize.bias,
-                             self._drop_mask(ego.shape[0], ego.device), x_out, xn_out)
+                             self._drop_mask(ego.shape[0], ego.device), x_out, xn_out, xn_planes)
 
     def forward(self, ego_embeddings, A_in, all_layers, lamda, alpha, l):
         """Reference signature (model.py:101): ``A_in`` is a sparse COO tensor, ``all_layers[0]`` the gate
@@ -148,7 +148,7 @@ class Aggregator(nn.Module):
                 h0 = _lib.f32c(all_layers[0])
                 qs = [f["q1"]] + ([f["q2"]] if f["q2"] is not None else [])
                 cs = [f["c1"]] + ([f["c2"]] if f["c2"] is not None else [])
-                r = ops.linear([h0], torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs))
+                r = ops.linear([ops.split_planes(h0)], torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs))
                 r1 = r[:, :self.out_dim]
                 r2 = r[:, self.out_dim:] if f["q2"] is not None else None
             x = torch.empty((ego.shape[0], self.out_dim), dtype=torch.float32, device=ego.device)
@@ -224,6 +224,8 @@ class LiteralKG(nn.Module):
         self._agg_values: Optional[torch.Tensor] = None   # its values, plan order (shared with A_in.data)
         self._att_plan: Optional[GraphPlan] = None        # plan of the (h, t, r) lists given to update_att
         self._att_key = None
+        self._lit_planes = None                           # bf16 hi/lo planes of the (constant) literal tables
+        self._lit_key = None
 
     # ---- helpers -------------------------------------------------------------------------------
     def _param_device(self) -> torch.device:
@@ -260,20 +262,36 @@ class LiteralKG(nn.Module):
         return plan, values
 
     # ---- gate ------------------------------------------------------------------------------------
-    def gate_embeddings(self, out: Optional[torch.Tensor] = None):
+    def _literal_planes(self, tables):
+        """The literal tables are constants (plain attributes in the reference): their bf16 hi/lo planes for
+        the gate GEMM are built once and reused, like the reference caches the ``.to(device)`` copy."""
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tables)
+        if self._lit_key != key:
+            src = tables[0] if len(tables) == 1 else torch.cat(tables, dim=1)
+            self._lit_planes = ops.split_planes(src)
+            self._lit_key = key
+        return self._lit_planes
+
+    def gate_embeddings(self, out: Optional[torch.Tensor] = None, out_planes=None):
         """model.py:265-279."""
         ent = self.entity_embed.weight
         self._param_device()
-        if self.args.use_num_lit and self.args.use_txt_lit:
-            return self.emb_mul_lit(ent, self._literal("numerical_literals_embed"),
-                                    self._literal("text_literals_embed"), out=out)
-        if self.args.use_num_lit:
-            return self.emb_num_lit(ent, self._literal("numerical_literals_embed"), out=out)
-        if self.args.use_txt_lit:
-            return self.emb_txt_lit(ent, self._literal("text_literals_embed"), out=out)
-        if out is not None:
-            out.copy_(ent.detach())
-            return out
+        with torch.no_grad():
+            if self.args.use_num_lit and self.args.use_txt_lit:
+                num, txt = self._literal("numerical_literals_embed"), self._literal("text_literals_embed")
+                return self.emb_mul_lit(ent, num, txt, out=out, out_planes=out_planes,
+                                        lit_planes=self._literal_planes((num, txt)))
+            if self.args.use_num_lit:
+                num = self._literal("numerical_literals_embed")
+                return self.emb_num_lit(ent, num, out=out, out_planes=out_planes, lit_planes=self._literal_planes((num,)))
+            if self.args.use_txt_lit:
+                txt = self._literal("text_literals_embed")
+                return self.emb_txt_lit(ent, txt, out=out, out_planes=out_planes, lit_planes=self._literal_planes((txt,)))
+            if out is not None:
+                out.copy_(ent.detach())
+                if out_planes is not None:
+                    ops.split_planes(ent.detach(), out=out_planes)
+                return out
         return ent
 
     # ---- full-graph embedding pass -------------------------------------------------------------
@@ -288,7 +306,10 @@ class LiteralKG(nn.Module):
         n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
         cat = torch.empty((n, total), dtype=torch.float32, device=dev)
         h0 = cat[:, :d]                                   # gate output lives in the concat buffer
-        self.gate_embeddings(out=h0)
+        # bf16 hi/lo planes of the concat buffer: operand of the h0 @ Q and linear_gat tensor-core GEMMs
+        cat_planes = _lib.Planes(n, total, dev)
+        h0_planes = cat_planes.view(0, d)
+        self.gate_embeddings(out=h0, out_planes=h0_planes)
 
         folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
         h0q = None
@@ -301,7 +322,7 @@ class LiteralKG(nn.Module):
                 qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
                 if f["q2"] is not None:
                     qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
-            h0q = ops.linear([h0], torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs))
+            h0q = ops.linear([h0_planes], torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs))
 
         x = h0
         col = d
@@ -313,13 +334,14 @@ class LiteralKG(nn.Module):
             else:
                 r1, r2 = f["c1"], f["c2"]
             x_out = torch.empty((n, c), dtype=torch.float32, device=dev)
-            layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0))
+            layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
+                      xn_planes=cat_planes.view(col, c))
             x = x_out
             col += c
         if keep is not None:
             keep["cat"] = cat
         if self.scale_gat_dim is not None:
-            return ops.linear([cat], self.linear_gat.weight, self.linear_gat.bias, _lib.ACT_LEAKY_RELU)
+            return ops.linear([cat_planes], self.linear_gat.weight, self.linear_gat.bias, _lib.ACT_LEAKY_RELU)
         return cat
 
     # ---- losses ----------------------------------------------------------------------------------

@@ -71,40 +71,78 @@ def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
     return out
 
 
-def linear(segments: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor],
-           activation: int = _lib.ACT_NONE, out: Optional[torch.Tensor] = None,
-           rows: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = act([seg0 | seg1 | ...] @ weight^T + bias); weight is [out_features, sum(k)] (nn.Linear layout)."""
-    segs = [s if (s.dtype == torch.float32 and s.stride(1) == 1) else _lib.f32c(s) for s in segments]
-    weight = _lib.f32c(weight)
-    m = segs[0].shape[0] if rows is None else rows.numel()
-    n = weight.shape[0]
-    if sum(s.shape[1] for s in segs) != weight.shape[1]:
-        raise ValueError("segment widths do not add up to weight.shape[1]")
+def split_planes(src: torch.Tensor, rows: Optional[torch.Tensor] = None, out: Optional[_lib.Planes] = None) -> _lib.Planes:
+    """fp32 [m, k] (unit inner stride; optional row gather) -> bf16 hi/lo planes, pad columns zero filled."""
+    if not (src.dtype == torch.float32 and src.stride(1) == 1):
+        src = _lib.f32c(src)
+    m = src.shape[0] if rows is None else rows.numel()
+    k = src.shape[1]
     if out is None:
-        out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
-    op = _lib.operand(segs, rows)
-    with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
-        _lib.check(_lib.load().lkg_linear_fwd(C.byref(op), m, weight.data_ptr(), weight.stride(0), n,
-                                              _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
-                                              out.data_ptr(), out.stride(0), _lib.stream()))
+        out = _lib.Planes(m, k, src.device)
+    if rows is not None:
+        rows = rows.to(device=src.device, dtype=torch.int64).contiguous()
+    with _dev_guard(src, "split_planes"):
+        _lib.check(_lib.load().lkg_split_planes(src.data_ptr(), src.stride(0), _lib.ptr(rows), m, k, out.ptr(), out.ld,
+                                                out.plane_stride, _lib.stream()))
     return out
 
 
-def gate(segments: Sequence[torch.Tensor], w_pair: torch.Tensor, bias_pair: torch.Tensor,
-         x_ent: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_weight(weight: torch.Tensor, seg_k: Sequence[int]) -> _lib.Planes:
+    """nn.Linear weight [n, sum(seg_k)] -> packed planes: every K segment zero padded to a multiple of 64."""
+    weight = _lib.f32c(weight)
+    n = weight.shape[0]
+    if sum(seg_k) != weight.shape[1]:
+        raise ValueError("segment widths do not add up to weight.shape[1]")
+    arr = (C.c_int32 * len(seg_k))(*[int(x) for x in seg_k])
+    cols = C.c_int32(0)
+    _lib.check(_lib.load().lkg_packed_weight_cols(arr, len(seg_k), C.byref(cols)))
+    out = _lib.Planes(n, cols.value, weight.device, ld=cols.value)
+    with _dev_guard(weight, "pack_weight"):
+        _lib.check(_lib.load().lkg_pack_weight(weight.data_ptr(), weight.stride(0), n, arr, len(seg_k), out.ptr(),
+                                               out.plane_stride, _lib.stream()))
+    return out
+
+
+def _planes_out(out_planes):
+    if out_planes is None:
+        return None, 0, 0
+    return out_planes.elem_ptr(), out_planes.ld, out_planes.plane_stride
+
+
+def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor], activation: int = _lib.ACT_NONE,
+           out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
+    """out = act([seg0 | seg1 | ...] @ weight^T + bias) on the tensor cores.  ``segments``: Planes / PlanesView
+    of the A operand; ``weight``: fp32 [out_features, sum(k)] (nn.Linear layout), packed per call."""
+    seg_k = [s.k for s in segments]
+    wp = pack_weight(weight, seg_k)
+    m, n = segments[0].rows, weight.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
+    a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
+    op_ptr, op_ld, op_ps = _planes_out(out_planes)
+    with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
+        _lib.check(_lib.load().lkg_linear_fwd(C.byref(a), m, C.byref(b), n,
+                                              _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
+                                              out.data_ptr(), out.stride(0), op_ptr, op_ld, op_ps, _lib.stream()))
+    return out
+
+
+def gate(segments: Sequence, w_pair: torch.Tensor, bias_pair: torch.Tensor, x_ent: torch.Tensor,
+         out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
     """Literal gate (gate.py:22-28): out = (1 - z) * x_ent + z * tanh(g) with (g, z) interleaved in w_pair."""
-    segs = [s if (s.dtype == torch.float32 and s.stride(1) == 1) else _lib.f32c(s) for s in segments]
-    w_pair, bias_pair = _lib.f32c(w_pair), _lib.f32c(bias_pair)
+    seg_k = [s.k for s in segments]
+    wp = pack_weight(w_pair, seg_k)
+    bias_pair = _lib.f32c(bias_pair)
     x_ent = x_ent if (x_ent.dtype == torch.float32 and x_ent.stride(1) == 1) else _lib.f32c(x_ent)
     m, dim = x_ent.shape
     if out is None:
         out = torch.empty((m, dim), dtype=torch.float32, device=x_ent.device)
-    op = _lib.operand(segs)
+    a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
+    op_ptr, op_ld, op_ps = _planes_out(out_planes)
     with _dev_guard(x_ent, "gate"):
-        _lib.check(_lib.load().lkg_gate_fwd(C.byref(op), m, w_pair.data_ptr(), w_pair.stride(0),
-                                            bias_pair.data_ptr(), dim, x_ent.data_ptr(), x_ent.stride(0),
-                                            out.data_ptr(), out.stride(0), _lib.stream()))
+        _lib.check(_lib.load().lkg_gate_fwd(C.byref(a), m, C.byref(b), bias_pair.data_ptr(), dim, x_ent.data_ptr(),
+                                            x_ent.stride(0), out.data_ptr(), out.stride(0), op_ptr, op_ld, op_ps,
+                                            _lib.stream()))
     return out
 
 
@@ -112,7 +150,7 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
               pa: Optional[torch.Tensor], pb: torch.Tensor, p2: Optional[torch.Tensor],
               r1: Optional[torch.Tensor], r2: Optional[torch.Tensor],
               ln_weight: torch.Tensor, ln_bias: torch.Tensor, drop_mask: Optional[torch.Tensor],
-              x_out: torch.Tensor, xn_out: Optional[torch.Tensor]) -> torch.Tensor:
+              x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None) -> torch.Tensor:
     """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases."""
     assert ego.dtype == torch.float32 and ego.stride(1) == 1
     d_in = ego.shape[1]
@@ -133,7 +171,7 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
             _lib.ptr(pa_c), pb_c.data_ptr(), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
             _lib.f32c(ln_weight).data_ptr(), _lib.f32c(ln_bias).data_ptr(), _lib.ptr(drop_mask),
             x_out.data_ptr(), x_out.stride(0), _lib.ptr(xn_out), 0 if xn_out is None else xn_out.stride(0),
-            plan.scratch(), _lib.stream()))
+            *_planes_out(xn_planes), plan.scratch(), _lib.stream()))
     return x_out
 
 
@@ -141,15 +179,17 @@ def score(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor,
           minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scores = emb[heads] @ emb[tails]^T (model.py:473-486); ``minmax``: opaque uint32[2] state."""
     assert emb.dtype == torch.float32 and emb.stride(1) == 1
-    heads = heads.to(device=emb.device, dtype=torch.int64).contiguous()
-    tails = tails.to(device=emb.device, dtype=torch.int64).contiguous()
-    out = torch.empty((heads.numel(), tails.numel()), dtype=torch.float32, device=emb.device)
+    hp = split_planes(emb, heads)
+    tp = split_planes(emb, tails)
+    out = torch.empty((hp.rows, tp.rows), dtype=torch.float32, device=emb.device)
+    if out.numel() == 0:
+        return out
+    a, b = _lib.planes_operand([hp]), _lib.planes_operand([tp])
     with _dev_guard(emb, "score", 1 if minmax is None else 2):
         lib = _lib.load()
         if minmax is not None:
             _lib.check(lib.lkg_minmax_reset(minmax.data_ptr(), _lib.stream()))
-        _lib.check(lib.lkg_score(emb.data_ptr(), emb.stride(0), emb.shape[1], heads.data_ptr(), heads.numel(),
-                                 tails.data_ptr(), tails.numel(), out.data_ptr(), out.stride(0) if out.numel() else max(tails.numel(), 1),
+        _lib.check(lib.lkg_score(C.byref(a), hp.rows, C.byref(b), tp.rows, out.data_ptr(), out.stride(0),
                                  _lib.ptr(minmax), _lib.stream()))
     return out
 

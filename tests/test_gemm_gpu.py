@@ -1,0 +1,92 @@
+"""The tcgen05 GEMM engine (hi/lo bf16 planes, three products per k-step, fp32 TMEM accumulation) against a
+float64 torch reference of the same op.  Claimed bound: 1e-4 relative to max|C| (measured ~1e-6); the path-level
+bound of BASELINE.json is 1e-3."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("m,n,ks", [(128, 64, [64]), (300, 192, [300]), (1000, 256, [396]), (257, 600, [300, 302]),
+                                    (77, 16, [12]), (513, 40, [12, 10]), (4096, 272, [300, 2, 300])])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear(m, n, ks, act):
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    segs = [torch.randn(m, k, generator=g, device="cuda") for k in ks]
+    w = torch.randn(n, sum(ks), generator=g, device="cuda") / sum(ks) ** 0.5
+    b = torch.randn(n, generator=g, device="cuda")
+    out = ops.linear([ops.split_planes(s) for s in segs], w, b, act)
+    ref = torch.cat(segs, 1).double() @ w.double().t() + b.double()
+    if act:
+        ref = torch.nn.functional.leaky_relu(ref, 0.01)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < TOL
+
+
+def test_linear_planes_output_and_strided_out():
+    from literalkg_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(700, 300, generator=g, device="cuda")
+    w = torch.randn(96, 300, generator=g, device="cuda") * 0.05
+    big = torch.zeros(700, 200, device="cuda")
+    planes = _lib.Planes(700, 96, "cuda")
+    out = ops.linear([ops.split_planes(x)], w, None, 0, out=big[:, 40:136], out_planes=planes)
+    ref = x.double() @ w.double().t()
+    assert rel(out, ref) < TOL
+    assert (big[:, :40] == 0).all() and (big[:, 136:] == 0).all()
+    recon = planes.t[0, :, :96].float() + planes.t[1, :, :96].float()
+    assert rel(recon, ref) < 1e-4
+
+
+@pytest.mark.parametrize("m,dim,lits", [(500, 300, [2, 300]), (130, 12, [2, 8]), (64, 12, [8])])
+def test_gate(m, dim, lits):
+    import literalkg_b200 as L
+    g = torch.Generator().manual_seed(dim + m)
+    mod = (L.GateMul(dim, *lits) if len(lits) == 2 else L.Gate(dim, lits[0]))
+    with torch.no_grad():
+        mod.gate_bias.add_(torch.randn(dim, generator=g) * 0.2)
+    mod = mod.cuda()
+    xs = [torch.randn(m, dim, generator=g).cuda()] + [torch.randn(m, k, generator=g).cuda() for k in lits]
+    out = mod(*xs)
+    d = lambda t: t.double()
+    x = torch.cat([d(t) for t in xs], 1)
+    gg = torch.tanh(x @ d(mod.g.weight).t() + d(mod.g.bias))
+    if len(lits) == 2:
+        z = d(xs[0]) @ d(mod.gate_ent.weight).t() + d(xs[1]) @ d(mod.gate_num_lit.weight).t() + d(xs[2]) @ d(mod.gate_txt_lit.weight).t()
+    else:
+        z = d(xs[0]) @ d(mod.gate_ent.weight).t() + d(xs[1]) @ d(mod.gate_lit.weight).t()
+    z = torch.sigmoid(z + d(mod.gate_bias))
+    ref = (1 - z) * d(xs[0]) + z * gg
+    assert rel(out, ref) < TOL
+
+
+@pytest.mark.parametrize("nh,nt,dim", [(9, 23, 16), (300, 5000, 256), (2048, 3000, 256)])
+def test_score_minmax(nh, nt, dim):
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(nh)
+    emb = torch.randn(6000, dim, generator=g, device="cuda")
+    heads = torch.randint(0, 6000, (nh,), generator=g, device="cuda")
+    tails = torch.randint(0, 6000, (nt,), generator=g, device="cuda")
+    mm = torch.empty(2, dtype=torch.int32, device="cuda")
+    s = ops.score(emb, heads, tails, mm)
+    ref = emb[heads].double() @ emb[tails].double().t()
+    assert rel(s, ref) < TOL
+    pred = ops.predict(emb, heads, tails, 0.5)
+    norm = (s - s.min()) / (s.max() - s.min())
+    assert torch.equal(pred, (norm > 0.5).int())            # min / max / threshold are exact on our own scores
+
+
+def test_exact_integers():
+    """Small integers are exact in bf16 and in fp32 accumulation: the engine must be bit exact."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randint(-8, 9, (640, 128), generator=g, device="cuda").float()
+    w = torch.randint(-8, 9, (256, 128), generator=g, device="cuda").float()
+    out = ops.linear([ops.split_planes(x)], w, None, 0)
+    assert torch.equal(out, x @ w.t())
