@@ -72,6 +72,8 @@ typedef struct {
     int64_t ld[LKG_MAX_SEGMENTS];
     int64_t plane_stride[LKG_MAX_SEGMENTS];
     int32_t k[LKG_MAX_SEGMENTS];
+    int32_t fp16;            /* 1: the planes hold fp16 (packed, scaled weights from lkg_pack_weight) */
+    const float* inv_scale;  /* device scalar that undoes the weight scale in the epilogue (nullable)  */
 } lkg_planes;
 
 typedef enum { LKG_ACT_NONE = 0, LKG_ACT_LEAKY_RELU = 1 } lkg_activation;
@@ -129,9 +131,10 @@ int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows /*nullabl
                      uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream);
 /* Number of columns of a packed weight: every K segment is padded to a multiple of 64. Host call. */
 int lkg_packed_weight_cols(const int32_t* seg_k /*host*/, int32_t n_segments, int32_t* cols /*host out*/);
-/* fp32 weight [n, sum(seg_k)] -> planes [2][n][packed cols] with per-segment zero padding. */
+/* fp32 weight [n, sum(seg_k)] -> fp16 hi/lo planes [2][n][packed cols] with per-segment zero padding,
+ * scaled by a power of two chosen from max|w|; scale_dev float[3] receives {scale, 1/scale, scratch}. */
 int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k /*host*/, int32_t n_segments,
-                    uint16_t* planes, int64_t plane_stride, void* stream);
+                    uint16_t* planes, int64_t plane_stride, float* scale_dev, void* stream);
 /* out = act(A @ B^T + bias)  (linear_gat model.py:309-310; the h0 @ Q residual terms).  b: packed weight
  * planes (one segment descriptor whose k is the packed column count).  out_planes (nullable) receives
  * the hi/lo split of the result for a following GEMM. */

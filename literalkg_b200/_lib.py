@@ -25,7 +25,8 @@ class LkgGraph(C.Structure):
 
 class LkgPlanes(C.Structure):
     _fields_ = [("n_segments", i32), ("ptr", vp * LKG_MAX_SEGMENTS), ("ld", i64 * LKG_MAX_SEGMENTS),
-                ("plane_stride", i64 * LKG_MAX_SEGMENTS), ("k", i32 * LKG_MAX_SEGMENTS)]
+                ("plane_stride", i64 * LKG_MAX_SEGMENTS), ("k", i32 * LKG_MAX_SEGMENTS), ("fp16", i32),
+                ("inv_scale", vp)]
 
 
 # name -> (restype, argtypes); mirrors include/lkg.h one to one
@@ -43,7 +44,7 @@ SIGNATURES = {
     "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),
     "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, i64, vp]),
     "lkg_packed_weight_cols": (C.c_int, [C.POINTER(i32), i32, C.POINTER(i32)]),
-    "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, vp, i64, vp]),
+    "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, vp, i64, vp, vp]),
     "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64,
                                  i64, vp]),
     "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), vp, i32, vp, i64, vp, i64, vp, i64,
@@ -119,6 +120,7 @@ class Planes:
         self.ld = int(ld) if ld is not None else (self.k + 7) // 8 * 8
         assert self.ld % 8 == 0 and self.ld >= self.k
         self.t = torch.empty((2, max(self.rows, 1), self.ld), dtype=torch.bfloat16, device=device)
+        self.scale = None        # packed weights: device float[3] = {scale, 1 / scale, scratch}, planes are fp16
 
     @property
     def plane_stride(self) -> int:
@@ -159,4 +161,9 @@ def planes_operand(segments) -> LkgPlanes:
         op.ld[i] = s.ld
         op.plane_stride[i] = s.plane_stride
         op.k[i] = s.k
+    scale = getattr(segments[0], "scale", None)
+    if scale is not None:
+        assert len(segments) == 1
+        op.fp16 = 1
+        op.inv_scale = scale.data_ptr() + 4
     return op

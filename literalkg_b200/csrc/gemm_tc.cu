@@ -17,6 +17,7 @@
 //   * the virtual torch.cat of the reference is a list of K segments, each with its own tensor map.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -55,6 +56,8 @@ struct TcParams {
     const float* x_ent;                 // gate mix input
     int64_t ld_ent;
     uint32_t* minmax;                   // score: ordered-encoded running {min, max}
+    const float* b_inv_scale;           // device scalar the accumulator is multiplied by (fp16 weights), nullable
+    int b_fp16;                         // B planes hold fp16 (scaled weights) instead of bf16
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -122,8 +125,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t umma_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int bn, int b_fp16) {
+    return (1u << 4) | (1u << 7) | ((b_fp16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(kBM >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t order_enc(float f) {
@@ -144,30 +148,60 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
         // columns come in (g, z) pairs; 16 accumulator columns -> 8 output channels
         const int c0 = col0 >> 1;
         const int dim = p.n >> 1;
-        float o[8];
+        if (c0 >= dim) return;
+        const float* erow = p.x_ent + row * p.ld_ent + c0;
+        float* orow = p.out + row * p.ldo + c0;
+        const bool full = c0 + 8 <= dim;
+        float e[8], b[16], o[8];
+        if (full && ((reinterpret_cast<uintptr_t>(erow) & 15u) == 0)) {
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(erow) + 1);
+            e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            o[j] = 0.f;
-            if (c < dim) {
-                const float g = tanh_acc(acc[2 * j] + __ldg(p.bias + 2 * c));
-                const float z = sigmoid_acc(acc[2 * j + 1] + __ldg(p.bias + 2 * c + 1));
-                const float e = __ldg(p.x_ent + row * p.ld_ent + c);
-                o[j] = (1.f - z) * e + z * g;
+            for (int j = 0; j < 8; ++j) e[j] = c0 + j < dim ? __ldg(erow + j) : 0.f;
+        }
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));   // warp-uniform address
+                b[j] = bb.x; b[j + 1] = bb.y; b[j + 2] = bb.z; b[j + 3] = bb.w;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) b[j] = col0 + j < p.n ? __ldg(p.bias + col0 + j) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (c0 + j < dim) p.out[row * p.ldo + c0 + j] = o[j];
-        if (p.out_planes) {
+        for (int j = 0; j < 8; ++j) {
+            const float g = tanh_acc(acc[2 * j] + b[2 * j]);
+            const float z = sigmoid_acc(acc[2 * j + 1] + b[2 * j + 1]);
+            o[j] = (1.f - z) * e[j] + z * g;
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+            reinterpret_cast<float4*>(orow)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(orow)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (c0 + j < dim) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(o[j], h, l);
-                    p.out_planes[row * p.ld_planes + c0 + j] = h;
-                    p.out_planes[p.plane_stride + row * p.ld_planes + c0 + j] = l;
-                }
+                if (c0 + j < dim) orow[j] = o[j];
+        }
+        if (p.out_planes) {
+            __nv_bfloat16* hrow = p.out_planes + row * p.ld_planes + c0;
+            __nv_bfloat16* lrow = hrow + p.plane_stride;
+            __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_bf16(o[j], h[j], l[j]);
+            if (full && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
+                *reinterpret_cast<uint4*>(hrow) = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(lrow) = *reinterpret_cast<const uint4*>(l);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < dim) {
+                        hrow[j] = h[j];
+                        lrow[j] = l[j];
+                    }
+            }
         }
     } else {
         float o[16];
@@ -176,7 +210,7 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
             const int c = col0 + j;
             float v = acc[j];
             if (EPI == kEpiLinear) {
-                if (p.bias && c < p.n) v += __ldg(p.bias + c);
+                if (p.bias && c < p.n) v += __ldg(p.bias + c);      // warp-uniform address: one broadcast load
                 if (p.act == LKG_ACT_LEAKY_RELU) v = leaky(v);
             }
             o[j] = v;
@@ -196,14 +230,25 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
                 if (col0 + j < p.n) dst[j] = o[j];
         }
         if (EPI == kEpiLinear && p.out_planes) {
+            __nv_bfloat16* hrow = p.out_planes + row * p.ld_planes + col0;
+            __nv_bfloat16* lrow = hrow + p.plane_stride;
+            __align__(16) __nv_bfloat16 h[16], l[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.n) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(o[j], h, l);
-                    p.out_planes[row * p.ld_planes + col0 + j] = h;
-                    p.out_planes[p.plane_stride + row * p.ld_planes + col0 + j] = l;
-                }
+            for (int j = 0; j < 16; ++j) split_bf16(o[j], h[j], l[j]);
+            if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) &&
+                ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
+                reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(h)[0];
+                reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(h)[1];
+                reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(l)[0];
+                reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(l)[1];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (col0 + j < p.n) {
+                        hrow[j] = h[j];
+                        lrow[j] = l[j];
+                    }
+            }
         }
     }
 }
@@ -284,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     } else if (warp == 5) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(p.bn);
+            const uint32_t idesc = umma_idesc(p.bn, p.b_fp16);
             uint32_t stage = 0, phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -322,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         // ===== epilogue warps 0-3: TMEM lane = tile row =====
         int it = 0;
         float lo = INFINITY, hi = -INFINITY;
+        const float acc_scale = p.b_inv_scale ? __ldg(p.b_inv_scale) : 1.f;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int mb, nb;
             tile_coords(tile, mb, nb);
@@ -334,6 +380,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             for (int c0 = 0; c0 < p.bn; c0 += 16) {
                 float v[16];
                 tc_ld16(taddr + c0, v);
+                if (EPI != kEpiScore) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= acc_scale;     // exact: power of two
+                }
                 epilogue16<EPI>(p, row, nb * p.bn + c0, v, lo, hi);
             }
             tc_fence_before();
@@ -406,6 +456,9 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
     LKG_REQUIRE(a && b && a->n_segments >= 1 && a->n_segments <= LKG_MAX_SEGMENTS && b->n_segments == 1, "bad operands");
     LKG_REQUIRE(m > 0 && n > 0, "empty GEMM");
     p.n_segments = a->n_segments;
+    p.b_fp16 = b->fp16;
+    p.b_inv_scale = b->inv_scale;
+    LKG_REQUIRE(!a->fp16 && a->inv_scale == nullptr, "the A operand must be plain bf16 planes");
     p.m = m;
     p.n = n;
     p.bn = pick_bn(n);
@@ -447,13 +500,40 @@ __global__ void split_planes_kernel(const float* __restrict__ src, int64_t ld, c
     }
 }
 
-// weight [n, sum(seg_k)] fp32 -> planes [2][n][sum(ceil64(seg_k))], every segment zero padded to a multiple of 64
+// weight [n, sum(seg_k)] fp32 -> fp16 planes [2][n][sum(ceil64(seg_k))], every segment zero padded to a multiple
+// of 64.  Weight rounding errors are coherent across the rows of A (every row meets the same W), so the weights
+// get the 11-bit fp16 significand (hi + lo = 22 bits) and a power-of-two scale that parks max|W| at 2^12..2^13,
+// far from fp16's subnormals; the epilogue multiplies the accumulator by the exact inverse.
 struct PackSegs {
     int n_segments;
     int k[LKG_MAX_SEGMENTS];
 };
+__global__ void absmax_kernel(const float* __restrict__ w, int64_t ldw, int n, int k, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    const int64_t total = (int64_t)n * k;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / k;
+        const float v = fabsf(w[r * ldw + (i - r * k)]);
+        m = fmaxf(m, v == v ? v : 0.f);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
 __global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int n, PackSegs segs,
-                                   __nv_bfloat16* __restrict__ dst, int kb, int64_t plane_stride) {
+                                   __half* __restrict__ dst, int kb, int64_t plane_stride,
+                                   const uint32_t* __restrict__ absmax, float* __restrict__ scale_out) {
+    const float amax = __uint_as_float(*absmax);
+    int e = 0;
+    if (amax > 0.f && amax < 3.0e38f) {
+        int ex;
+        frexpf(amax, &ex);          // amax = f * 2^ex, f in [0.5, 1)
+        e = 13 - ex;                // amax * 2^e in [2^12, 2^13)
+    }
+    const float scale = ldexpf(1.f, e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scale_out[0] = scale;
+        scale_out[1] = ldexpf(1.f, -e);
+    }
     const int64_t total = (int64_t)n * kb;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / kb);
@@ -469,8 +549,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int
             c -= padded;
             src_col += segs.k[s];
         }
-        __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
+        x *= scale;
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
         dst[i] = h;
         dst[plane_stride + i] = l;
     }
@@ -510,15 +591,25 @@ extern "C" int lkg_packed_weight_cols(const int32_t* seg_k, int32_t n_segments, 
 }
 
 extern "C" int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k, int32_t n_segments,
-                               uint16_t* planes, int64_t plane_stride, void* stream_) {
+                               uint16_t* planes, int64_t plane_stride, float* scale_dev, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int32_t kb = 0;
     if (int rc = lkg_packed_weight_cols(seg_k, n_segments, &kb)) return rc;
-    LKG_REQUIRE(w && planes && n > 0 && plane_stride >= (int64_t)n * kb, "bad pack arguments");
+    LKG_REQUIRE(w && planes && scale_dev && n > 0 && plane_stride >= (int64_t)n * kb, "bad pack arguments");
     PackSegs segs{};
     segs.n_segments = n_segments;
-    for (int s = 0; s < n_segments; ++s) segs.k[s] = seg_k[s];
-    pack_weight_kernel<<<grid_1d((int64_t)n * kb), 256, 0, stream>>>(w, ldw, n, segs, (__nv_bfloat16*)planes, kb, plane_stride);
+    int ktot = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        segs.k[s] = seg_k[s];
+        ktot += seg_k[s];
+    }
+    // scale_dev[2] doubles as the absmax accumulator (uint bits) of this call; [0] = scale, [1] = 1 / scale
+    uint32_t* amax = reinterpret_cast<uint32_t*>(scale_dev + 2);
+    LKG_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), stream));
+    absmax_kernel<<<grid_1d((int64_t)n * ktot), 256, 0, stream>>>(w, ldw, n, ktot, amax);
+    LKG_LAUNCH_CHECK("absmax_kernel");
+    pack_weight_kernel<<<grid_1d((int64_t)n * kb), 256, 0, stream>>>(w, ldw, n, segs, (__half*)planes, kb, plane_stride,
+                                                                    amax, scale_dev);
     LKG_LAUNCH_CHECK("pack_weight_kernel");
     return LKG_OK;
 }

@@ -97,9 +97,10 @@ def pack_weight(weight: torch.Tensor, seg_k: Sequence[int]) -> _lib.Planes:
     cols = C.c_int32(0)
     _lib.check(_lib.load().lkg_packed_weight_cols(arr, len(seg_k), C.byref(cols)))
     out = _lib.Planes(n, cols.value, weight.device, ld=cols.value)
-    with _dev_guard(weight, "pack_weight"):
+    out.scale = torch.empty(3, dtype=torch.float32, device=weight.device)
+    with _dev_guard(weight, "pack_weight", 2):
         _lib.check(_lib.load().lkg_pack_weight(weight.data_ptr(), weight.stride(0), n, arr, len(seg_k), out.ptr(),
-                                               out.plane_stride, _lib.stream()))
+                                               out.plane_stride, out.scale.data_ptr(), _lib.stream()))
     return out
 
 
