@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LKG_ABI_VERSION 1
+#define LKG_ABI_VERSION 2
 
 typedef enum {
     LKG_OK = 0,
@@ -58,22 +58,30 @@ typedef struct {
     const int32_t* att_seg;     /* [E]   index into the agg arrays                          */
     const int32_t* rowptr;      /* [N+1] */
     const int32_t* col;         /* [nnz] */
+    const int32_t* row_order;   /* [row_end - row_begin] the rows of the partition, most triples first: the
+                                   kernels take rows in this order so that the heaviest rows of a power-law
+                                   graph start first (nullable: natural order) */
 } lkg_graph;
 
-/* bf16 "planes" operand of the tensor-core GEMMs.  A value x is stored as hi = bf16(x) and
- * lo = bf16(x - hi): two bf16 matrices [rows, ld] that are `plane_stride` elements apart (hi first).
+/* fp16 "planes" operand of the tensor-core GEMMs.  A value x is stored as hi = fp16(s*x) and
+ * lo = fp16(s*x - hi): two fp16 matrices [rows, ld] that are `plane_stride` elements apart (hi first), 22
+ * significand bits in the footprint of the fp32 value.  s is a power of two kept in a device "scale
+ * record" (below) that parks max|s*x| in [2^11, 2^12), far from fp16's overflow and subnormal ranges.
  * An operand is a K-concatenation of up to LKG_MAX_SEGMENTS such matrices (the virtual torch.cat of
  * gate.py:23 / model.py:309): logical A[m, :] = [ seg0[m, 0:k0] | seg1[m, 0:k1] | ... ].
  * Base pointers, row strides and plane strides must be 16-byte aligned (ld % 8 == 0). */
 #define LKG_MAX_SEGMENTS 4
+/* Scale record: device float[LKG_SCALE_FLOATS] = { absmax, scale, 1/scale, (scratch) ... }; written by
+ * lkg_scale_from_data / lkg_scale_from_bound / lkg_pack_weight, read by every kernel that writes or
+ * multiplies planes.  Never read by the host: no call of this library synchronises. */
+#define LKG_SCALE_FLOATS 8
 typedef struct {
     int32_t n_segments;
     const uint16_t* ptr[LKG_MAX_SEGMENTS];
     int64_t ld[LKG_MAX_SEGMENTS];
     int64_t plane_stride[LKG_MAX_SEGMENTS];
     int32_t k[LKG_MAX_SEGMENTS];
-    int32_t fp16;            /* 1: the planes hold fp16 (packed, scaled weights from lkg_pack_weight) */
-    const float* inv_scale;  /* device scalar that undoes the weight scale in the epilogue (nullable)  */
+    const float* scale[LKG_MAX_SEGMENTS];   /* scale record of each segment (device) */
 } lkg_planes;
 
 typedef enum { LKG_ACT_NONE = 0, LKG_ACT_LEAKY_RELU = 1 } lkg_activation;
@@ -89,7 +97,8 @@ int lkg_device_check(int device);
  *      torch.sparse.softmax performs inside update_attention (dataloader.py:369-424,
  *      model.py:462-470) ------------------------------------------------------------------------ */
 int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, size_t* bytes /*host out*/);
-/* h,t,r: int64 [n_edges] in file order.  rel_keep: optional uint8 [n_relations]; triples whose
+/* h,t,r: int64 [n_edges] in file order.  row_order (nullable) int32 [n_entities]: all rows by decreasing
+ * triple count (stable).  rel_keep: optional uint8 [n_relations]; triples whose
  * relation has rel_keep == 0 are dropped (a `relations` list that omits ids, model.py:451).
  * Outputs are caller-allocated: att_* and col sized for n_edges, rowptrs for n_entities+1,
  * coo_rows/coo_cols (nullable) int64 [n_edges] receive the coalesced COO indices, file_seg
@@ -98,7 +107,7 @@ int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, size_t* bytes 
 int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
                    int64_t n_entities, int32_t n_relations, const uint8_t* rel_keep,
                    int32_t* att_rowptr, int32_t* att_tail, int32_t* att_rel, int32_t* att_seg,
-                   int32_t* rowptr, int32_t* col, int64_t* coo_rows, int64_t* coo_cols,
+                   int32_t* rowptr, int32_t* col, int32_t* row_order, int64_t* coo_rows, int64_t* coo_cols,
                    int32_t* file_seg, int64_t* counts_dev, void* workspace, size_t workspace_bytes,
                    void* stream);
 /* values_out[file_seg[i]] += values_in[i]: imports an un-coalesced COO value list (e.g. an A_in taken
@@ -119,35 +128,48 @@ int lkg_laplacian_init(const lkg_graph* g, int symmetric, float* values, double*
 /* ---- attention update (model.py:430-471): per triple v = sum_d e_t[d]*tanh(e_h[d]+e_r[d]) on the
  *      raw tables, duplicate (h,t) logits summed, max-subtracted softmax per head row.
  *      values: [nnz] in agg order. ------------------------------------------------------------ */
-int lkg_attn_workspace_bytes(size_t* bytes /*host out*/);
+int lkg_attn_workspace_bytes(int32_t n_relations, int32_t dim, size_t* bytes /*host out*/);
 int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t ld_entity,
                     const float* relation, int64_t ld_relation, int32_t dim,
                     float* values, void* workspace, void* stream);
 
-/* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores, three bf16 products per
+/* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores, three fp16 products per
  *      k-step (hi*hi + lo*hi + hi*lo) accumulated in fp32 TMEM (torch Linear layout: B is [out, in]) ---- */
-/* fp32 [m, k] (row stride ld, optional row gather) -> planes [2][m][ld_planes], columns >= k zero filled. */
+/* rec <- record of max(|src[rows or all, 0:k]|, floor).  src fp32 [*, ld], optional int64 row gather. */
+int lkg_scale_from_data(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
+                        float floor, float* rec, void* stream);
+/* rec <- record of max(bound, other[0]) where `other` is an optional existing record (e.g. the gate output
+ * is bounded by max(1, max|entity|): a convex mix of the entity row and a tanh). */
+int lkg_scale_from_bound(float bound, const float* other /*nullable*/, float* rec, void* stream);
+/* fp32 [m, k] (row stride ld, optional row gather) -> planes [2][m][ld_planes] scaled by rec, columns >= k
+ * zero filled. */
 int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
-                     uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream);
+                     const float* rec, uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream);
 /* Number of columns of a packed weight: every K segment is padded to a multiple of 64. Host call. */
 int lkg_packed_weight_cols(const int32_t* seg_k /*host*/, int32_t n_segments, int32_t* cols /*host out*/);
-/* fp32 weight [n, sum(seg_k)] -> fp16 hi/lo planes [2][n][packed cols] with per-segment zero padding,
- * scaled by a power of two chosen from max|w|; scale_dev float[3] receives {scale, 1/scale, scratch}. */
+/* fp32 weight [n, sum(seg_k)] -> fp16 hi/lo planes [2][n][packed cols] with per-segment zero padding.
+ * a_recs (host array of n_segments device pointers): the scale records of the A segments this weight will
+ * meet; segment i of the weight is scaled by S / a_scale_i with one power of two S chosen so that the
+ * largest scaled weight lands in [2^11, 2^12): every product of the GEMM then carries the same factor S,
+ * and w_rec receives {., S, 1/S} for the epilogue. */
 int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k /*host*/, int32_t n_segments,
-                    uint16_t* planes, int64_t plane_stride, float* scale_dev, void* stream);
+                    const float* const* a_recs /*host array of device ptrs*/, uint16_t* planes,
+                    int64_t plane_stride, float* w_rec, void* stream);
 /* out = act(A @ B^T + bias)  (linear_gat model.py:309-310; the h0 @ Q residual terms).  b: packed weight
- * planes (one segment descriptor whose k is the packed column count).  out_planes (nullable) receives
- * the hi/lo split of the result for a following GEMM. */
+ * planes (one segment descriptor whose k is the packed column count and whose scale is w_rec).
+ * out_planes (nullable) receives the split of the result scaled by out_rec for a following GEMM. */
 int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n,
                    const float* bias /*nullable [n]*/, int32_t activation, float* out, int64_t ldo,
-                   uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream);
+                   uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
+                   void* stream);
 /* Literal gate (gate.py:22-28 / :45-51).  x = (entity | literals...) planes; w_pair = packed planes of
  * the [2*dim, K] matrix with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of output
  * j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]); x_ent = fp32 entity table for the mix
  * out = (1 - z) * x_ent + z * tanh(g). */
 int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
                  int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
-                 uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream);
+                 uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
+                 void* stream);
 
 /* ---- one aggregator layer, forward (model.py:101-164 + F.normalize of model.py:305) ----------
  * side = A_in @ ego fused with the combine, LeakyReLU, LayerNorm, optional dropout mask and the
@@ -166,7 +188,7 @@ int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* eg
                       const float* drop_mask /*nullable [N,d_out] multiplicative*/,
                       float* x_out, int64_t ld_x, float* xn_out /*nullable*/, int64_t ld_xn,
                       uint16_t* xn_planes /*nullable: hi/lo copy of xn*/, int64_t ld_planes, int64_t plane_stride,
-                      void* workspace, void* stream);
+                      const float* xn_rec /*scale record of xn_planes (bound 1)*/, void* workspace, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
 /* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final

@@ -12,6 +12,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblkg.so")
 
 LKG_MAX_SEGMENTS = 4
+LKG_SCALE_FLOATS = 8
+ABI_VERSION = 2
 ACT_NONE, ACT_LEAKY_RELU = 0, 1
 
 i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
@@ -20,13 +22,13 @@ i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 class LkgGraph(C.Structure):
     _fields_ = [("n_entities", i64), ("n_edges", i64), ("nnz", i64), ("n_relations", i32),
                 ("row_begin", i64), ("row_end", i64), ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
-                ("rowptr", vp), ("col", vp)]
+                ("rowptr", vp), ("col", vp), ("row_order", vp)]
 
 
 class LkgPlanes(C.Structure):
     _fields_ = [("n_segments", i32), ("ptr", vp * LKG_MAX_SEGMENTS), ("ld", i64 * LKG_MAX_SEGMENTS),
-                ("plane_stride", i64 * LKG_MAX_SEGMENTS), ("k", i32 * LKG_MAX_SEGMENTS), ("fp16", i32),
-                ("inv_scale", vp)]
+                ("plane_stride", i64 * LKG_MAX_SEGMENTS), ("k", i32 * LKG_MAX_SEGMENTS),
+                ("scale", vp * LKG_MAX_SEGMENTS)]
 
 
 # name -> (restype, argtypes); mirrors include/lkg.h one to one
@@ -35,23 +37,25 @@ SIGNATURES = {
     "lkg_last_error": (C.c_char_p, []),
     "lkg_device_check": (C.c_int, [C.c_int]),
     "lkg_plan_workspace_bytes": (C.c_int, [i64, i64, C.POINTER(C.c_size_t)]),
-    "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+    "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  C.c_size_t, vp]),
     "lkg_segment_scatter_add": (C.c_int, [vp, vp, i64, vp, i64, vp]),
     "lkg_edge_fingerprint": (C.c_int, [vp, vp, vp, i64, vp, vp]),
     "lkg_laplacian_init": (C.c_int, [C.POINTER(LkgGraph), C.c_int, vp, vp, vp]),
-    "lkg_attn_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
+    "lkg_attn_workspace_bytes": (C.c_int, [i32, i32, C.POINTER(C.c_size_t)]),
     "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),
-    "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, i64, vp]),
+    "lkg_scale_from_data": (C.c_int, [vp, i64, vp, i64, i32, C.c_float, vp, vp]),
+    "lkg_scale_from_bound": (C.c_int, [C.c_float, vp, vp, vp]),
+    "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, vp, i64, i64, vp]),
     "lkg_packed_weight_cols": (C.c_int, [C.POINTER(i32), i32, C.POINTER(i32)]),
-    "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, vp, i64, vp, vp]),
+    "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, C.POINTER(vp), vp, i64, vp, vp]),
     "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64,
-                                 i64, vp]),
+                                 i64, vp, vp]),
     "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), vp, i32, vp, i64, vp, i64, vp, i64,
-                               i64, vp]),
+                               i64, vp, vp]),
     "lkg_aggregate_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "lkg_aggregate_fwd": (C.c_int, [C.POINTER(LkgGraph), vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp,
-                                    vp, vp, i64, vp, i64, vp, i64, i64, vp, vp]),
+                                    vp, vp, i64, vp, i64, vp, i64, i64, vp, vp, vp]),
     "lkg_score": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i64, vp, i64, vp, vp]),
     "lkg_minmax_reset": (C.c_int, [vp, vp]),
     "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),
@@ -75,7 +79,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.lkg_abi_version() != 1:
+        if lib.lkg_abi_version() != ABI_VERSION:
             raise RuntimeError("liblkg.so ABI version mismatch; rebuild with `python -m literalkg_b200.build`")
         _lib = lib
     return _lib
@@ -113,14 +117,15 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 class Planes:
-    """bf16 hi/lo planes of an fp32 matrix: tensor [2, rows, ld] (ld % 8 == 0) with logical width k."""
+    """Scaled fp16 hi/lo planes of an fp32 matrix: tensor [2, rows, ld] (ld % 8 == 0) with logical width k, plus
+    the device scale record (float[8]: absmax, scale, 1/scale, scratch...) every kernel that touches them reads."""
 
-    def __init__(self, rows: int, k: int, device, ld: Optional[int] = None):
+    def __init__(self, rows: int, k: int, device, ld: Optional[int] = None, rec: Optional[torch.Tensor] = None):
         self.rows, self.k = int(rows), int(k)
         self.ld = int(ld) if ld is not None else (self.k + 7) // 8 * 8
         assert self.ld % 8 == 0 and self.ld >= self.k
-        self.t = torch.empty((2, max(self.rows, 1), self.ld), dtype=torch.bfloat16, device=device)
-        self.scale = None        # packed weights: device float[3] = {scale, 1 / scale, scratch}, planes are fp16
+        self.t = torch.empty((2, max(self.rows, 1), self.ld), dtype=torch.float16, device=device)
+        self.rec = rec if rec is not None else torch.zeros(LKG_SCALE_FLOATS, dtype=torch.float32, device=device)
 
     @property
     def plane_stride(self) -> int:
@@ -135,16 +140,22 @@ class Planes:
         """Address of column ``col`` for kernels that write planes element-wise (no alignment needed)."""
         return self.t.data_ptr() + 2 * col
 
-    def view(self, col: int, k: int) -> "PlanesView":
-        return PlanesView(self, col, k)
+    def view(self, col: int, k: int, rec: Optional[torch.Tensor] = None) -> "PlanesView":
+        return PlanesView(self, col, k, rec)
+
+    def dequant(self) -> torch.Tensor:
+        """fp32 reconstruction (hi + lo) / scale -- test / debugging helper (one host sync)."""
+        return (self.t[0, :self.rows, :self.k].float() + self.t[1, :self.rows, :self.k].float()) * self.rec[2]
 
 
 class PlanesView:
-    """Column window [col, col + k) of a Planes buffer (col % 8 == 0)."""
+    """Column window [col, col + k) of a Planes buffer (col % 8 == 0) with its own scale record: the windows of
+    the concat buffer (gate output | normalised layer outputs) have different magnitudes."""
 
-    def __init__(self, base, col: int, k: int):
+    def __init__(self, base, col: int, k: int, rec: Optional[torch.Tensor] = None):
         self.base, self.col, self.k = base, int(col), int(k)
         self.rows, self.ld, self.plane_stride = base.rows, base.ld, base.plane_stride
+        self.rec = rec if rec is not None else base.rec
 
     def ptr(self, col: int = 0) -> int:
         return self.base.ptr(self.col + col)
@@ -161,9 +172,5 @@ def planes_operand(segments) -> LkgPlanes:
         op.ld[i] = s.ld
         op.plane_stride[i] = s.plane_stride
         op.k[i] = s.k
-    scale = getattr(segments[0], "scale", None)
-    if scale is not None:
-        assert len(segments) == 1
-        op.fp16 = 1
-        op.inv_scale = scale.data_ptr() + 4
+        op.scale[i] = s.rec.data_ptr()
     return op

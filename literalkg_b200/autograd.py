@@ -17,7 +17,7 @@ def _needs_grad(*tensors) -> bool:
 
 def gate_apply(module, inputs, out=None, out_planes=None, ent_planes=None, lit_planes=None):
     """Fused literal gate forward for ``Gate`` / ``GateMul`` (gate.py:22-28, 45-51).  The A operand is the K
-    concatenation (entity | literals); ``ent_planes`` / ``lit_planes`` let the caller reuse cached bf16 planes."""
+    concatenation (entity | literals); ``ent_planes`` / ``lit_planes`` let the caller reuse cached fp16 planes."""
     x_ent = inputs[0]
     with torch.no_grad():
         w_pair, b_pair = module.packed()

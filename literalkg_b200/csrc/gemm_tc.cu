@@ -5,10 +5,13 @@
 //   lkg_score      : emb[heads] @ emb[tails]^T (+ min/max)   calc_score / predict_links (model.py:473-491)
 //
 // sm_100a design
-//   * operands live in HBM as bf16 "planes": x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  (2 x 2 bytes, the
-//     same footprint as the fp32 value).  Three tcgen05.mma per k-step  hi*hi + lo*hi + hi*lo  accumulate in
-//     fp32 TMEM; the dropped lo*lo term and the residual of the split are ~2^-17 relative, two orders below
-//     the 1e-3 parity bound (a single bf16 pass would be ~2^-9 and break it);
+//   * operands live in HBM as fp16 "planes": s*x = hi + lo with hi = fp16(s*x), lo = fp16(s*x - hi)  (2 x 2 bytes,
+//     the same footprint as the fp32 value; s = power of two from the operand's scale record, so the split is
+//     exact up to 22 significand bits).  Three tcgen05.mma per k-step  hi*hi + lo*hi + hi*lo  accumulate in fp32
+//     TMEM; the dropped lo*lo term and the residual of the split are ~2^-22 relative, i.e. fp32-class: the GEMMs
+//     that feed LayerNorm over 32 features get amplified on the way to the final embeddings (the fp32 reference
+//     itself sits ~1e-4 from fp64 there), so a bf16 split (2^-17) eats the 1e-3 parity
+//     budget and a single bf16 pass (2^-9) is far above it;
 //   * TMA (cp.async.bulk.tensor.3d, 128-byte swizzle) stages {hi, lo} x 64-wide K chunks of A (128 rows) and
 //     B (N-tile rows) into shared memory; a 2-stage mbarrier ring feeds one MMA-issuing thread;
 //   * accumulators: 2 x 256 TMEM columns, double buffered so the epilogue of tile i overlaps the MMAs of
@@ -16,7 +19,6 @@
 //   * persistent CTAs (one per SM), static tile round-robin, N fastest so that co-running CTAs share A tiles in L2;
 //   * the virtual torch.cat of the reference is a list of K segments, each with its own tensor map.
 #include <cuda.h>
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -25,7 +27,7 @@ namespace lkg {
 namespace {
 
 constexpr int kBM = 128;          // rows per tile == TMEM lanes
-constexpr int kBK = 64;           // bf16 elements per K chunk == one 128-byte swizzle row
+constexpr int kBK = 64;           // fp16 elements per K chunk == one 128-byte swizzle row
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
 constexpr int kStages = 2;
 constexpr int kThreads = 192;     // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
@@ -51,13 +53,14 @@ struct TcParams {
     int act;
     float* out;
     int64_t ldo;
-    __nv_bfloat16* out_planes;          // optional hi/lo copy of the output (feeds the next GEMM)
+    __half* out_planes;                 // optional hi/lo copy of the output (feeds the next GEMM)
     int64_t ld_planes, plane_stride;
     const float* x_ent;                 // gate mix input
     int64_t ld_ent;
     uint32_t* minmax;                   // score: ordered-encoded running {min, max}
-    const float* b_inv_scale;           // device scalar the accumulator is multiplied by (fp16 weights), nullable
-    int b_fp16;                         // B planes hold fp16 (scaled weights) instead of bf16
+    const float* mul_a;                 // scale records whose [2] (= 1/scale) the accumulator is multiplied by:
+    const float* mul_b;                 //   mul_b = packed weight (1/S) or tails; mul_a = heads (score only), nullable
+    const float* out_rec;               // scale record of out_planes
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -98,7 +101,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -124,25 +127,26 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t umma_idesc(int bn, int b_fp16) {
-    return (1u << 4) | (1u << 7) | ((b_fp16 ? 0u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) |
-           ((uint32_t)(kBM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0 in bits 7-9 / 10-12; the two formats
+// must agree -- a bf16 x fp16 mix traps as an illegal instruction), both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t umma_idesc(int bn) {
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t order_enc(float f) {
     const uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// x is already multiplied by the operand's power-of-two scale
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
 }
 
 // ---- epilogues: one thread = one output row, 16 consecutive accumulator columns per call -----------
 template <int EPI>
 __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int col0, const float (&acc)[16],
-                                           float& lo, float& hi) {
+                                           float out_scale, float& lo, float& hi) {
     if (row >= p.m) return;
     if (EPI == kEpiGate) {
         // columns come in (g, z) pairs; 16 accumulator columns -> 8 output channels
@@ -186,11 +190,11 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
                 if (c0 + j < dim) orow[j] = o[j];
         }
         if (p.out_planes) {
-            __nv_bfloat16* hrow = p.out_planes + row * p.ld_planes + c0;
-            __nv_bfloat16* lrow = hrow + p.plane_stride;
-            __align__(16) __nv_bfloat16 h[8], l[8];
+            __half* hrow = p.out_planes + row * p.ld_planes + c0;
+            __half* lrow = hrow + p.plane_stride;
+            __align__(16) __half h[8], l[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) split_bf16(o[j], h[j], l[j]);
+            for (int j = 0; j < 8; ++j) split_f16(o[j] * out_scale, h[j], l[j]);
             if (full && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
                 *reinterpret_cast<uint4*>(hrow) = *reinterpret_cast<const uint4*>(h);
                 *reinterpret_cast<uint4*>(lrow) = *reinterpret_cast<const uint4*>(l);
@@ -230,11 +234,11 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
                 if (col0 + j < p.n) dst[j] = o[j];
         }
         if (EPI == kEpiLinear && p.out_planes) {
-            __nv_bfloat16* hrow = p.out_planes + row * p.ld_planes + col0;
-            __nv_bfloat16* lrow = hrow + p.plane_stride;
-            __align__(16) __nv_bfloat16 h[16], l[16];
+            __half* hrow = p.out_planes + row * p.ld_planes + col0;
+            __half* lrow = hrow + p.plane_stride;
+            __align__(16) __half h[16], l[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_bf16(o[j], h[j], l[j]);
+            for (int j = 0; j < 16; ++j) split_f16(o[j] * out_scale, h[j], l[j]);
             if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) &&
                 ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
                 reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(h)[0];
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     } else if (warp == 5) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(p.bn, p.b_fp16);
+            const uint32_t idesc = umma_idesc(p.bn);
             uint32_t stage = 0, phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -347,12 +351,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const uint32_t b_lo = b_hi + (uint32_t)p.bn * kBK * 2;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        const uint32_t koff = k * 32;   // 16 bf16 = 32 bytes inside the swizzle row
+                        const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes inside the swizzle row
                         const uint64_t dah = umma_desc(a_hi + koff), dal = umma_desc(a_lo + koff);
                         const uint64_t dbh = umma_desc(b_hi + koff), dbl = umma_desc(b_lo + koff);
-                        tc_mma_bf16(tmem_d, dah, dbh, idesc, (c | k) != 0);
-                        tc_mma_bf16(tmem_d, dal, dbh, idesc, 1);
-                        tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+                        tc_mma_f16(tmem_d, dah, dbh, idesc, (c | k) != 0);
+                        tc_mma_f16(tmem_d, dal, dbh, idesc, 1);
+                        tc_mma_f16(tmem_d, dah, dbl, idesc, 1);
                     }
                     tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
                     if (++stage == kStages) {
@@ -367,7 +371,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         // ===== epilogue warps 0-3: TMEM lane = tile row =====
         int it = 0;
         float lo = INFINITY, hi = -INFINITY;
-        const float acc_scale = p.b_inv_scale ? __ldg(p.b_inv_scale) : 1.f;
+        // powers of two: the rescale is exact
+        const float acc_scale = (p.mul_a ? __ldg(p.mul_a + 2) : 1.f) * (p.mul_b ? __ldg(p.mul_b + 2) : 1.f);
+        const float out_scale = (p.out_planes && p.out_rec) ? __ldg(p.out_rec + 1) : 1.f;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int mb, nb;
             tile_coords(tile, mb, nb);
@@ -380,11 +386,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             for (int c0 = 0; c0 < p.bn; c0 += 16) {
                 float v[16];
                 tc_ld16(taddr + c0, v);
-                if (EPI != kEpiScore) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= acc_scale;     // exact: power of two
-                }
-                epilogue16<EPI>(p, row, nb * p.bn + c0, v, lo, hi);
+                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
+                epilogue16<EPI>(p, row, nb * p.bn + c0, v, out_scale, lo, hi);
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
@@ -427,17 +431,17 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// planes tensor: bf16 [2 planes][rows][ld] with `plane_stride` elements between the planes; logical width k
+// planes tensor: fp16 [2 planes][rows][ld] with `plane_stride` elements between the planes; logical width k
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld, int64_t plane_stride, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     LKG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (ld * 2) % 16 == 0 && (plane_stride * 2) % 16 == 0,
-                "bf16 planes must be 16-byte aligned (base, row stride, plane stride)");
+                "fp16 planes must be 16-byte aligned (base, row stride, plane stride)");
     cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
     cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 2};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -456,9 +460,12 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
     LKG_REQUIRE(a && b && a->n_segments >= 1 && a->n_segments <= LKG_MAX_SEGMENTS && b->n_segments == 1, "bad operands");
     LKG_REQUIRE(m > 0 && n > 0, "empty GEMM");
     p.n_segments = a->n_segments;
-    p.b_fp16 = b->fp16;
-    p.b_inv_scale = b->inv_scale;
-    LKG_REQUIRE(!a->fp16 && a->inv_scale == nullptr, "the A operand must be plain bf16 planes");
+    LKG_REQUIRE(b->scale[0] != nullptr, "the B operand needs a scale record");
+    p.mul_b = b->scale[0];
+    if (EPI == kEpiScore) {
+        LKG_REQUIRE(a->scale[0] != nullptr, "the heads operand needs a scale record");
+        p.mul_a = a->scale[0];
+    }
     p.m = m;
     p.n = n;
     p.bn = pick_bn(n);
@@ -485,55 +492,114 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------
+// Scale record {absmax, scale, 1/scale, counter, seg absmax x4}: scale = 2^e parks absmax * scale in [2^11, 2^12).
+__device__ __forceinline__ void write_record(float* rec, float amax) {
+    int e = 0;
+    if (amax > 0.f && amax < 3.0e38f) {
+        int ex;
+        frexpf(amax, &ex);                 // amax = f * 2^ex, f in [0.5, 1)
+        e = 12 - ex;
+        e = e > 60 ? 60 : (e < -60 ? -60 : e);
+    }
+    rec[0] = amax;
+    rec[1] = ldexpf(1.f, e);
+    rec[2] = ldexpf(1.f, -e);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows, int64_t m,
+                              int k, float floor_, float* __restrict__ rec) {
+    float mx = 0.f;
+    const int64_t total = m * k;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / k;
+        const float v = fabsf(src[(rows ? rows[r] : r) * ld + (i - r * k)]);
+        mx = fmaxf(mx, v == v ? v : 0.f);
+    }
+    mx = warp_max(mx);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(rec);
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(bits, __float_as_uint(mx));   // non-negative floats order like uints
+    // the last block to finish turns the absmax into the record
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(bits + 3, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const float amax = fmaxf(__uint_as_float(atomicMax(bits, 0u)), floor_);
+        write_record(rec, amax);
+    }
+}
+
+__global__ void bound_record_kernel(float bound, const float* __restrict__ other, float* __restrict__ rec) {
+    write_record(rec, other ? fmaxf(bound, other[0]) : bound);
+}
+
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
-                                    int64_t m, int k, __nv_bfloat16* __restrict__ dst, int64_t ldp, int64_t plane_stride) {
+                                    int64_t m, int k, const float* __restrict__ rec, __half* __restrict__ dst,
+                                    int64_t ldp, int64_t plane_stride) {
+    const float scale = __ldg(rec + 1);
     const int64_t total = m * ldp;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / ldp;
         const int c = (int)(i - r * ldp);
         float x = 0.f;
-        if (c < k) x = src[(rows ? rows[r] : r) * ld + c];
-        __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
+        if (c < k) x = src[(rows ? rows[r] : r) * ld + c] * scale;
+        __half h, l;
+        split_f16(x, h, l);
         dst[i] = h;
         dst[plane_stride + i] = l;
     }
 }
 
-// weight [n, sum(seg_k)] fp32 -> fp16 planes [2][n][sum(ceil64(seg_k))], every segment zero padded to a multiple
-// of 64.  Weight rounding errors are coherent across the rows of A (every row meets the same W), so the weights
-// get the 11-bit fp16 significand (hi + lo = 22 bits) and a power-of-two scale that parks max|W| at 2^12..2^13,
-// far from fp16's subnormals; the epilogue multiplies the accumulator by the exact inverse.
+// weight [n, sum(seg_k)] fp32 -> fp16 planes [2][n][sum(ceil64(seg_k))], every segment zero padded to a multiple of
+// 64.  Segment i is multiplied by S / a_scale_i so that every product of the GEMM carries the same factor S.
 struct PackSegs {
     int n_segments;
     int k[LKG_MAX_SEGMENTS];
+    const float* a_rec[LKG_MAX_SEGMENTS];
 };
-__global__ void absmax_kernel(const float* __restrict__ w, int64_t ldw, int n, int k, uint32_t* __restrict__ out) {
-    float m = 0.f;
-    const int64_t total = (int64_t)n * k;
+__global__ void seg_absmax_kernel(const float* __restrict__ w, int64_t ldw, int n, int ktot, PackSegs segs,
+                                  float* __restrict__ w_rec) {
+    float m[LKG_MAX_SEGMENTS] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t total = (int64_t)n * ktot;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / k;
-        const float v = fabsf(w[r * ldw + (i - r * k)]);
-        m = fmaxf(m, v == v ? v : 0.f);
+        const int64_t r = i / ktot;
+        int c = (int)(i - r * ktot);
+        const float v = fabsf(w[r * ldw + c]);
+        int sgm = 0;
+        while (sgm < segs.n_segments - 1 && c >= segs.k[sgm]) c -= segs.k[sgm++];
+#pragma unroll
+        for (int s = 0; s < LKG_MAX_SEGMENTS; ++s)
+            if (s == sgm) m[s] = fmaxf(m[s], v == v ? v : 0.f);
     }
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+    uint32_t* bits = reinterpret_cast<uint32_t*>(w_rec) + 4;
+#pragma unroll
+    for (int s = 0; s < LKG_MAX_SEGMENTS; ++s) {
+        const float x = warp_max(m[s]);
+        if ((threadIdx.x & 31) == 0 && x > 0.f) atomicMax(bits + s, __float_as_uint(x));
+    }
+}
+// S = 2^e with max_i (wmax_i / a_scale_i) * S in [2^11, 2^12)
+__device__ __forceinline__ float pack_total_scale(const PackSegs& segs, const float* w_rec) {
+    float cmax = 0.f;
+    for (int s = 0; s < segs.n_segments; ++s) cmax = fmaxf(cmax, w_rec[4 + s] * __ldg(segs.a_rec[s] + 2));
+    int e = 0;
+    if (cmax > 0.f && cmax < 3.0e38f) {
+        int ex;
+        frexpf(cmax, &ex);
+        e = 12 - ex;
+        e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    }
+    return ldexpf(1.f, e);
 }
 __global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int n, PackSegs segs,
-                                   __half* __restrict__ dst, int kb, int64_t plane_stride,
-                                   const uint32_t* __restrict__ absmax, float* __restrict__ scale_out) {
-    const float amax = __uint_as_float(*absmax);
-    int e = 0;
-    if (amax > 0.f && amax < 3.0e38f) {
-        int ex;
-        frexpf(amax, &ex);          // amax = f * 2^ex, f in [0.5, 1)
-        e = 13 - ex;                // amax * 2^e in [2^12, 2^13)
-    }
-    const float scale = ldexpf(1.f, e);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        scale_out[0] = scale;
-        scale_out[1] = ldexpf(1.f, -e);
-    }
+                                   __half* __restrict__ dst, int kb, int64_t plane_stride, float* __restrict__ w_rec) {
+    const float S = pack_total_scale(segs, w_rec);
+    float seg_scale[LKG_MAX_SEGMENTS];
+    for (int s = 0; s < LKG_MAX_SEGMENTS; ++s) seg_scale[s] = s < segs.n_segments ? S * __ldg(segs.a_rec[s] + 2) : 0.f;
     const int64_t total = (int64_t)n * kb;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / kb);
@@ -543,18 +609,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int
         for (int s = 0; s < segs.n_segments; ++s) {
             const int padded = (segs.k[s] + kBK - 1) / kBK * kBK;
             if (c < padded) {
-                if (c < segs.k[s]) x = w[(int64_t)r * ldw + src_col + c];
+                if (c < segs.k[s]) x = w[(int64_t)r * ldw + src_col + c] * seg_scale[s];
                 break;
             }
             c -= padded;
             src_col += segs.k[s];
         }
-        x *= scale;
-        const __half h = __float2half_rn(x);
-        const __half l = __float2half_rn(x - __half2float(h));
+        __half h, l;
+        split_f16(x, h, l);
         dst[i] = h;
         dst[plane_stride + i] = l;
     }
+}
+// runs after pack_weight_kernel on the same stream: publishes {., S, 1/S} for the GEMM epilogue
+__global__ void pack_finalize_kernel(PackSegs segs, float* __restrict__ w_rec) {
+    const float S = pack_total_scale(segs, w_rec);
+    w_rec[0] = 0.f;
+    w_rec[1] = S;
+    w_rec[2] = 1.f / S;
 }
 
 inline int grid_1d(int64_t n) {
@@ -568,12 +640,31 @@ inline int grid_1d(int64_t n) {
 
 using namespace lkg;
 
-extern "C" int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
-                                uint16_t* planes, int64_t ld_planes, int64_t plane_stride, void* stream_) {
+extern "C" int lkg_scale_from_data(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
+                                   float floor_, float* rec, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    LKG_REQUIRE(src && planes && m >= 0 && k > 0 && ld_planes >= k && plane_stride >= m * ld_planes, "bad split arguments");
+    LKG_REQUIRE(rec && m >= 0 && k > 0 && (m == 0 || src) && floor_ >= 0.f, "bad scale arguments");
+    LKG_CUDA(cudaMemsetAsync(rec, 0, LKG_SCALE_FLOATS * sizeof(float), stream));
+    absmax_kernel<<<grid_1d(m * k), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
+    LKG_LAUNCH_CHECK("absmax_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_scale_from_bound(float bound, const float* other, float* rec, void* stream_) {
+    LKG_REQUIRE(rec && bound >= 0.f, "bad scale arguments");
+    bound_record_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(bound, other, rec);
+    LKG_LAUNCH_CHECK("bound_record_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_split_planes(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
+                                const float* rec, uint16_t* planes, int64_t ld_planes, int64_t plane_stride,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(src && rec && planes && m >= 0 && k > 0 && ld_planes >= k && plane_stride >= m * ld_planes,
+                "bad split arguments");
     if (m == 0) return LKG_OK;
-    split_planes_kernel<<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, (__nv_bfloat16*)planes,
+    split_planes_kernel<<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
                                                                     ld_planes, plane_stride);
     LKG_LAUNCH_CHECK("split_planes_kernel");
     return LKG_OK;
@@ -591,57 +682,65 @@ extern "C" int lkg_packed_weight_cols(const int32_t* seg_k, int32_t n_segments, 
 }
 
 extern "C" int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int32_t* seg_k, int32_t n_segments,
-                               uint16_t* planes, int64_t plane_stride, float* scale_dev, void* stream_) {
+                               const float* const* a_recs, uint16_t* planes, int64_t plane_stride, float* w_rec,
+                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int32_t kb = 0;
     if (int rc = lkg_packed_weight_cols(seg_k, n_segments, &kb)) return rc;
-    LKG_REQUIRE(w && planes && scale_dev && n > 0 && plane_stride >= (int64_t)n * kb, "bad pack arguments");
+    LKG_REQUIRE(w && planes && w_rec && a_recs && n > 0 && plane_stride >= (int64_t)n * kb, "bad pack arguments");
     PackSegs segs{};
     segs.n_segments = n_segments;
     int ktot = 0;
     for (int s = 0; s < n_segments; ++s) {
+        LKG_REQUIRE(a_recs[s] != nullptr, "segment %d has no scale record", s);
         segs.k[s] = seg_k[s];
+        segs.a_rec[s] = a_recs[s];
         ktot += seg_k[s];
     }
-    // scale_dev[2] doubles as the absmax accumulator (uint bits) of this call; [0] = scale, [1] = 1 / scale
-    uint32_t* amax = reinterpret_cast<uint32_t*>(scale_dev + 2);
-    LKG_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), stream));
-    absmax_kernel<<<grid_1d((int64_t)n * ktot), 256, 0, stream>>>(w, ldw, n, ktot, amax);
-    LKG_LAUNCH_CHECK("absmax_kernel");
+    LKG_CUDA(cudaMemsetAsync(w_rec, 0, LKG_SCALE_FLOATS * sizeof(float), stream));
+    seg_absmax_kernel<<<grid_1d((int64_t)n * ktot), 256, 0, stream>>>(w, ldw, n, ktot, segs, w_rec);
+    LKG_LAUNCH_CHECK("seg_absmax_kernel");
     pack_weight_kernel<<<grid_1d((int64_t)n * kb), 256, 0, stream>>>(w, ldw, n, segs, (__half*)planes, kb, plane_stride,
-                                                                    amax, scale_dev);
+                                                                    w_rec);
     LKG_LAUNCH_CHECK("pack_weight_kernel");
+    pack_finalize_kernel<<<1, 1, 0, stream>>>(segs, w_rec);
+    LKG_LAUNCH_CHECK("pack_finalize_kernel");
     return LKG_OK;
 }
 
 extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n, const float* bias,
                               int32_t activation, float* out, int64_t ldo, uint16_t* out_planes, int64_t ld_planes,
-                              int64_t plane_stride, void* stream_) {
+                              int64_t plane_stride, const float* out_rec, void* stream_) {
     LKG_REQUIRE(out && ldo >= n, "bad linear output");
+    LKG_REQUIRE(!out_planes || out_rec, "out_planes needs a scale record");
     if (m == 0) return LKG_OK;
     TcParams p{};
     p.bias = bias;
     p.act = activation;
     p.out = out;
     p.ldo = ldo;
-    p.out_planes = (__nv_bfloat16*)out_planes;
+    p.out_planes = (__half*)out_planes;
     p.ld_planes = ld_planes;
     p.plane_stride = plane_stride;
+    p.out_rec = out_rec;
     return launch_tc<kEpiLinear>(p, a, m, b, n, (cudaStream_t)stream_);
 }
 
 extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
                             int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
-                            uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, void* stream_) {
+                            uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
+                            void* stream_) {
     LKG_REQUIRE(bias_pair && x_ent && out && dim > 0 && ldo >= dim, "bad gate arguments");
+    LKG_REQUIRE(!out_planes || out_rec, "out_planes needs a scale record");
     if (m == 0) return LKG_OK;
     TcParams p{};
     p.bias = bias_pair;
     p.out = out;
     p.ldo = ldo;
-    p.out_planes = (__nv_bfloat16*)out_planes;
+    p.out_planes = (__half*)out_planes;
     p.ld_planes = ld_planes;
     p.plane_stride = plane_stride;
+    p.out_rec = out_rec;
     p.x_ent = x_ent;
     p.ld_ent = ld_ent;
     return launch_tc<kEpiGate>(p, x, m, w_pair, 2 * dim, (cudaStream_t)stream_);

@@ -29,6 +29,8 @@ struct PlanScratch {
     int32_t* seg_ht;   // [E] segment id of each triple in (h,t) order
     int32_t* deg_e;    // [N+1]
     int32_t* deg_u;    // [N+1]
+    int32_t* ord_key;  // [N] sorted degrees (discarded)
+    int32_t* ord_val;  // [N] row ids 0..N-1
     void* cub;         // cub temp storage
     size_t cub_bytes;
     size_t total;
@@ -40,8 +42,12 @@ size_t cub_temp_bytes(int64_t e, int64_t n) {
                                     (int32_t*)nullptr, (int)e, 0, 64);
     cub::DeviceScan::InclusiveSum(nullptr, b, (int32_t*)nullptr, (int32_t*)nullptr, (int)e);
     cub::DeviceScan::ExclusiveSum(nullptr, c, (int32_t*)nullptr, (int32_t*)nullptr, (int)(n + 1));
+    size_t d = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, d, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
+                                              (int32_t*)nullptr, (int)n, 0, 32);
     size_t m = a > b ? a : b;
-    return m > c ? m : c;
+    m = m > c ? m : c;
+    return m > d ? m : d;
 }
 
 PlanScratch carve(void* base, int64_t e, int64_t n) {
@@ -62,6 +68,8 @@ PlanScratch carve(void* base, int64_t e, int64_t n) {
     s.seg_ht = (int32_t*)take(ee * 4);
     s.deg_e = (int32_t*)take((size_t)(n + 1) * 4);
     s.deg_u = (int32_t*)take((size_t)(n + 1) * 4);
+    s.ord_key = (int32_t*)take((size_t)n * 4);
+    s.ord_val = (int32_t*)take((size_t)n * 4);
     s.cub_bytes = cub_temp_bytes(e, n);
     s.cub = take(s.cub_bytes);
     s.total = off;
@@ -159,6 +167,11 @@ __global__ void gather_att(const uint64_t* __restrict__ key_hr_sorted, const int
     }
 }
 
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int32_t)i;
+}
+
 inline int grid_for(int64_t n, int block = 256) {
     int64_t b = (n + block - 1) / block;
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -234,9 +247,9 @@ extern "C" int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, siz
 extern "C" int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
                               int64_t n_entities, int32_t n_relations, const uint8_t* rel_keep,
                               int32_t* att_rowptr, int32_t* att_tail, int32_t* att_rel, int32_t* att_seg,
-                              int32_t* rowptr, int32_t* col, int64_t* coo_rows, int64_t* coo_cols,
-                              int32_t* file_seg, int64_t* counts_dev, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
+                              int32_t* rowptr, int32_t* col, int32_t* row_order, int64_t* coo_rows,
+                              int64_t* coo_cols, int32_t* file_seg, int64_t* counts_dev, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(n_edges >= 0 && n_edges < (1ll << 31) - 1, "n_edges out of range");
     LKG_REQUIRE(n_entities > 0 && n_entities < (1ll << 31) - 1, "n_entities out of range");
@@ -279,6 +292,14 @@ extern "C" int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t*
         LKG_LAUNCH_CHECK("gather_att");
     }
     size_t tb = s.cub_bytes;
+    if (row_order) {
+        // rows by decreasing triple count; the LSD radix sort is stable, so equal degrees keep ascending row ids
+        iota_kernel<<<grid_for(n_entities), 256, 0, stream>>>(s.ord_val, n_entities);
+        LKG_LAUNCH_CHECK("iota_kernel");
+        LKG_CUDA(cub::DeviceRadixSort::SortPairsDescending(s.cub, tb, s.deg_e, s.ord_key, s.ord_val, row_order,
+                                                           (int)n_entities, 0, 32, stream));
+        tb = s.cub_bytes;
+    }
     LKG_CUDA(cub::DeviceScan::ExclusiveSum(s.cub, tb, s.deg_e, att_rowptr, (int)n1, stream));
     tb = s.cub_bytes;
     LKG_CUDA(cub::DeviceScan::ExclusiveSum(s.cub, tb, s.deg_u, rowptr, (int)n1, stream));

@@ -43,6 +43,7 @@ class GraphPlan:
         self.att_rel = torch.empty(max(e, 1), **i32)
         self.att_seg = torch.empty(max(e, 1), **i32)
         self.col = torch.empty(max(e, 1), **i32)
+        self.row_order = torch.empty(n_entities, **i32)     # rows by decreasing triple count (LPT schedule)
         coo = torch.empty((2, max(e, 1)), dtype=torch.int64, device=dev)
         self.file_seg = torch.empty(max(e, 1), **i32)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
@@ -53,7 +54,8 @@ class GraphPlan:
             _lib.check(lib.lkg_plan_build(h.data_ptr(), t.data_ptr(), r.data_ptr(), e, n_entities, n_relations,
                                           _lib.ptr(keep), self.att_rowptr.data_ptr(), self.att_tail.data_ptr(),
                                           self.att_rel.data_ptr(), self.att_seg.data_ptr(), self.rowptr.data_ptr(),
-                                          self.col.data_ptr(), coo[0].data_ptr(), coo[1].data_ptr(),
+                                          self.col.data_ptr(), self.row_order.data_ptr(), coo[0].data_ptr(),
+                                          coo[1].data_ptr(),
                                           self.file_seg.data_ptr(), counts.data_ptr(), ws.data_ptr(), nbytes.value,
                                           _lib.stream()))
         kept, nnz, bad = counts.tolist()          # one host sync per plan build
@@ -69,8 +71,11 @@ class GraphPlan:
         self.indices = coo[:, :self.nnz]          # int64 [2, nnz]: A_in.coalesce().indices()
         self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations, 0, self.n_entities,
                                self.att_rowptr.data_ptr(), self.att_tail.data_ptr(), self.att_rel.data_ptr(),
-                               self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr())
+                               self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr(),
+                               self.row_order.data_ptr())
+        self._part_order = None
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
+        self._attn_ws = None
 
     # -- constructors ---------------------------------------------------------------------------
     @classmethod
@@ -89,6 +94,13 @@ class GraphPlan:
         if not (0 <= begin <= end <= self.n_entities):
             raise ValueError("bad row range")
         self.c.row_begin, self.c.row_end = int(begin), int(end)
+        if begin == 0 and end == self.n_entities:
+            self._part_order = None
+            self.c.row_order = self.row_order.data_ptr()
+        else:   # the partition's rows, still heaviest first
+            keep = (self.row_order >= begin) & (self.row_order < end)
+            self._part_order = self.row_order[keep].contiguous()
+            self.c.row_order = self._part_order.data_ptr()
 
     @staticmethod
     def fingerprint(h: torch.Tensor, t: torch.Tensor, r: torch.Tensor):
@@ -102,6 +114,14 @@ class GraphPlan:
 
     def scratch(self) -> int:
         return self._scratch.data_ptr()
+
+    def attn_workspace(self, dim: int) -> int:
+        """Workspace of lkg_attn_update: row counter + the exp(2 e_r) table."""
+        nbytes = C.c_size_t(0)
+        _lib.check(_lib.load().lkg_attn_workspace_bytes(self.n_relations, int(dim), C.byref(nbytes)))
+        if self._attn_ws is None or self._attn_ws.numel() < nbytes.value:
+            self._attn_ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        return self._attn_ws.data_ptr()
 
     def import_values(self, values: torch.Tensor) -> torch.Tensor:
         """Values given per INPUT entry -> plan (coalesced) order, duplicates summed."""

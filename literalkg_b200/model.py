@@ -224,7 +224,8 @@ class LiteralKG(nn.Module):
         self._agg_values: Optional[torch.Tensor] = None   # its values, plan order (shared with A_in.data)
         self._att_plan: Optional[GraphPlan] = None        # plan of the (h, t, r) lists given to update_att
         self._att_key = None
-        self._lit_planes = None                           # bf16 hi/lo planes of the (constant) literal tables
+        self._lit_planes = None                           # fp16 hi/lo planes of the (constant) literal tables
+        self._unit_rec = None                             # scale record of planes bounded by 1 (normalised rows)
         self._lit_key = None
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -272,25 +273,42 @@ class LiteralKG(nn.Module):
             self._lit_key = key
         return self._lit_planes
 
-    def gate_embeddings(self, out: Optional[torch.Tensor] = None, out_planes=None):
-        """model.py:265-279."""
+    def _unit_record(self, dev) -> torch.Tensor:
+        if self._unit_rec is None or self._unit_rec.device != dev:
+            self._unit_rec = ops.scale_from_bound(1.0, dev)
+        return self._unit_rec
+
+    def gate_embeddings(self, out: Optional[torch.Tensor] = None, planes_window=None):
+        """model.py:265-279.  ``planes_window``: optional (Planes, col, k) column window that receives the scaled
+        fp16 hi/lo copy of the result (A operand of the GEMMs that follow)."""
         ent = self.entity_embed.weight
-        self._param_device()
+        dev = self._param_device()
         with torch.no_grad():
+            gate_mod, tables = None, ()
             if self.args.use_num_lit and self.args.use_txt_lit:
-                num, txt = self._literal("numerical_literals_embed"), self._literal("text_literals_embed")
-                return self.emb_mul_lit(ent, num, txt, out=out, out_planes=out_planes,
-                                        lit_planes=self._literal_planes((num, txt)))
-            if self.args.use_num_lit:
-                num = self._literal("numerical_literals_embed")
-                return self.emb_num_lit(ent, num, out=out, out_planes=out_planes, lit_planes=self._literal_planes((num,)))
-            if self.args.use_txt_lit:
-                txt = self._literal("text_literals_embed")
-                return self.emb_txt_lit(ent, txt, out=out, out_planes=out_planes, lit_planes=self._literal_planes((txt,)))
+                gate_mod = self.emb_mul_lit
+                tables = (self._literal("numerical_literals_embed"), self._literal("text_literals_embed"))
+            elif self.args.use_num_lit:
+                gate_mod, tables = self.emb_num_lit, (self._literal("numerical_literals_embed"),)
+            elif self.args.use_txt_lit:
+                gate_mod, tables = self.emb_txt_lit, (self._literal("text_literals_embed"),)
+            if gate_mod is not None:
+                ent_planes = ops.split_planes(ent.detach())
+                out_planes = None
+                if planes_window is not None:
+                    # |gate output| <= max(1, max|entity|): convex mix of the entity row and a tanh
+                    base, col, k = planes_window
+                    out_planes = base.view(col, k, rec=ops.scale_from_bound(1.0, dev, other=ent_planes.rec))
+                res = gate_mod(ent, *tables, out=out, out_planes=out_planes, ent_planes=ent_planes,
+                               lit_planes=self._literal_planes(tables))
+                return (res, out_planes) if planes_window is not None else res
             if out is not None:
                 out.copy_(ent.detach())
-                if out_planes is not None:
-                    ops.split_planes(ent.detach(), out=out_planes)
+                if planes_window is not None:
+                    base, col, k = planes_window
+                    view = base.view(col, k, rec=torch.empty(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=dev))
+                    ops.split_planes(ent.detach(), out=view)
+                    return out, view
                 return out
         return ent
 
@@ -306,10 +324,13 @@ class LiteralKG(nn.Module):
         n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
         cat = torch.empty((n, total), dtype=torch.float32, device=dev)
         h0 = cat[:, :d]                                   # gate output lives in the concat buffer
-        # bf16 hi/lo planes of the concat buffer: operand of the h0 @ Q and linear_gat tensor-core GEMMs
-        cat_planes = _lib.Planes(n, total, dev)
-        h0_planes = cat_planes.view(0, d)
-        self.gate_embeddings(out=h0, out_planes=h0_planes)
+        # scaled fp16 hi/lo planes of the concat buffer: A operand of the h0 @ Q and linear_gat tensor-core GEMMs.
+        # Two K segments with their own scale records: the gate output and the L2-normalised layer outputs
+        # (|x| <= 1); the second window starts on a 16-byte boundary.
+        xcol = (d + 7) // 8 * 8
+        cat_planes = _lib.Planes(n, xcol + (total - d), dev)
+        _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d))
+        xn_all = cat_planes.view(xcol, total - d, rec=self._unit_record(dev))
 
         folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
         h0q = None
@@ -335,13 +356,14 @@ class LiteralKG(nn.Module):
                 r1, r2 = f["c1"], f["c2"]
             x_out = torch.empty((n, c), dtype=torch.float32, device=dev)
             layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
-                      xn_planes=cat_planes.view(col, c))
+                      xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec))
             x = x_out
             col += c
         if keep is not None:
             keep["cat"] = cat
         if self.scale_gat_dim is not None:
-            return ops.linear([cat_planes], self.linear_gat.weight, self.linear_gat.bias, _lib.ACT_LEAKY_RELU)
+            segs = [h0_planes] + ([xn_all] if total > d else [])
+            return ops.linear(segs, self.linear_gat.weight, self.linear_gat.bias, _lib.ACT_LEAKY_RELU)
         return cat
 
     # ---- losses ----------------------------------------------------------------------------------

@@ -64,85 +64,112 @@ def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
         raise ValueError("update_att needs embed_dim == relation_dim (model.py:441 adds the two tables)")
     if out is None:
         out = torch.empty(max(plan.nnz, 1), dtype=torch.float32, device=entity.device)[:plan.nnz]
-    with _dev_guard(entity, "attn_update"):
+    with _dev_guard(entity, "attn_update", 2):
         _lib.check(_lib.load().lkg_attn_update(plan.byref(), entity.data_ptr(), entity.stride(0),
                                                relation.data_ptr(), relation.stride(0), entity.shape[1],
-                                               out.data_ptr(), plan.scratch(), _lib.stream()))
+                                               out.data_ptr(), plan.attn_workspace(entity.shape[1]), _lib.stream()))
     return out
 
 
-def split_planes(src: torch.Tensor, rows: Optional[torch.Tensor] = None, out: Optional[_lib.Planes] = None) -> _lib.Planes:
-    """fp32 [m, k] (unit inner stride; optional row gather) -> bf16 hi/lo planes, pad columns zero filled."""
+def scale_from_data(src: torch.Tensor, rows: Optional[torch.Tensor] = None, floor: float = 0.0,
+                    rec: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device scale record (float[8]) of max(|src[rows]|, floor); no host sync."""
+    m = src.shape[0] if rows is None else rows.numel()
+    if rec is None:
+        rec = torch.empty(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=src.device)
+    with _dev_guard(src, "scale_from_data"):
+        _lib.check(_lib.load().lkg_scale_from_data(src.data_ptr(), src.stride(0), _lib.ptr(rows), m, src.shape[1],
+                                                   float(floor), rec.data_ptr(), _lib.stream()))
+    return rec
+
+
+def scale_from_bound(bound: float, device, other: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Scale record of max(bound, other.absmax) -- for planes whose magnitude is known a priori."""
+    rec = torch.empty(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=device)
+    with _dev_guard(rec, "scale_from_bound"):
+        _lib.check(_lib.load().lkg_scale_from_bound(float(bound), _lib.ptr(other), rec.data_ptr(), _lib.stream()))
+    return rec
+
+
+def split_planes(src: torch.Tensor, rows: Optional[torch.Tensor] = None, out=None, rec: Optional[torch.Tensor] = None):
+    """fp32 [m, k] (unit inner stride; optional row gather) -> scaled fp16 hi/lo planes, pad columns zero filled.
+    ``rec``: an existing scale record that bounds the data (default: measured from the data on device)."""
     if not (src.dtype == torch.float32 and src.stride(1) == 1):
         src = _lib.f32c(src)
     m = src.shape[0] if rows is None else rows.numel()
     k = src.shape[1]
-    if out is None:
-        out = _lib.Planes(m, k, src.device)
     if rows is not None:
         rows = rows.to(device=src.device, dtype=torch.int64).contiguous()
+    if out is None:
+        out = _lib.Planes(m, k, src.device, rec=rec)
+        if rec is None:
+            scale_from_data(src, rows, rec=out.rec)
+    elif rec is None:
+        scale_from_data(src, rows, rec=out.rec)
+    else:
+        assert out.rec is rec
     with _dev_guard(src, "split_planes"):
-        _lib.check(_lib.load().lkg_split_planes(src.data_ptr(), src.stride(0), _lib.ptr(rows), m, k, out.ptr(), out.ld,
-                                                out.plane_stride, _lib.stream()))
+        _lib.check(_lib.load().lkg_split_planes(src.data_ptr(), src.stride(0), _lib.ptr(rows), m, k, out.rec.data_ptr(),
+                                                out.ptr(), out.ld, out.plane_stride, _lib.stream()))
     return out
 
 
-def pack_weight(weight: torch.Tensor, seg_k: Sequence[int]) -> _lib.Planes:
-    """nn.Linear weight [n, sum(seg_k)] -> packed planes: every K segment zero padded to a multiple of 64."""
+def pack_weight(weight: torch.Tensor, segments: Sequence) -> _lib.Planes:
+    """nn.Linear weight [n, sum(k)] -> packed planes: every K segment zero padded to a multiple of 64 and scaled
+    against the scale record of the A segment it will meet (``segments``: the A operand's Planes / views)."""
     weight = _lib.f32c(weight)
     n = weight.shape[0]
+    seg_k = [s.k for s in segments]
     if sum(seg_k) != weight.shape[1]:
         raise ValueError("segment widths do not add up to weight.shape[1]")
     arr = (C.c_int32 * len(seg_k))(*[int(x) for x in seg_k])
+    recs = (C.c_void_p * len(seg_k))(*[s.rec.data_ptr() for s in segments])
     cols = C.c_int32(0)
     _lib.check(_lib.load().lkg_packed_weight_cols(arr, len(seg_k), C.byref(cols)))
     out = _lib.Planes(n, cols.value, weight.device, ld=cols.value)
-    out.scale = torch.empty(3, dtype=torch.float32, device=weight.device)
-    with _dev_guard(weight, "pack_weight", 2):
-        _lib.check(_lib.load().lkg_pack_weight(weight.data_ptr(), weight.stride(0), n, arr, len(seg_k), out.ptr(),
-                                               out.plane_stride, out.scale.data_ptr(), _lib.stream()))
+    with _dev_guard(weight, "pack_weight", 3):
+        _lib.check(_lib.load().lkg_pack_weight(weight.data_ptr(), weight.stride(0), n, arr, len(seg_k), recs, out.ptr(),
+                                               out.plane_stride, out.rec.data_ptr(), _lib.stream()))
     return out
 
 
 def _planes_out(out_planes):
     if out_planes is None:
-        return None, 0, 0
-    return out_planes.elem_ptr(), out_planes.ld, out_planes.plane_stride
+        return None, 0, 0, None
+    return out_planes.elem_ptr(), out_planes.ld, out_planes.plane_stride, out_planes.rec.data_ptr()
 
 
 def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor], activation: int = _lib.ACT_NONE,
            out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
     """out = act([seg0 | seg1 | ...] @ weight^T + bias) on the tensor cores.  ``segments``: Planes / PlanesView
-    of the A operand; ``weight``: fp32 [out_features, sum(k)] (nn.Linear layout), packed per call."""
-    seg_k = [s.k for s in segments]
-    wp = pack_weight(weight, seg_k)
+    of the A operand; ``weight``: fp32 [out_features, sum(k)] (nn.Linear layout), packed per call.
+    ``out_planes``: Planes whose scale record already bounds the result."""
+    wp = pack_weight(weight, segments)
     m, n = segments[0].rows, weight.shape[0]
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
     a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
-    op_ptr, op_ld, op_ps = _planes_out(out_planes)
     with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
         _lib.check(_lib.load().lkg_linear_fwd(C.byref(a), m, C.byref(b), n,
                                               _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
-                                              out.data_ptr(), out.stride(0), op_ptr, op_ld, op_ps, _lib.stream()))
+                                              out.data_ptr(), out.stride(0), *_planes_out(out_planes), _lib.stream()))
     return out
 
 
 def gate(segments: Sequence, w_pair: torch.Tensor, bias_pair: torch.Tensor, x_ent: torch.Tensor,
          out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
-    """Literal gate (gate.py:22-28): out = (1 - z) * x_ent + z * tanh(g) with (g, z) interleaved in w_pair."""
-    seg_k = [s.k for s in segments]
-    wp = pack_weight(w_pair, seg_k)
+    """Literal gate (gate.py:22-28): out = (1 - z) * x_ent + z * tanh(g) with (g, z) interleaved in w_pair.
+    ``out_planes``: its scale record must bound max(1, max|x_ent|) (see ``scale_from_bound``)."""
+    wp = pack_weight(w_pair, segments)
     bias_pair = _lib.f32c(bias_pair)
     x_ent = x_ent if (x_ent.dtype == torch.float32 and x_ent.stride(1) == 1) else _lib.f32c(x_ent)
     m, dim = x_ent.shape
     if out is None:
         out = torch.empty((m, dim), dtype=torch.float32, device=x_ent.device)
     a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
-    op_ptr, op_ld, op_ps = _planes_out(out_planes)
     with _dev_guard(x_ent, "gate"):
         _lib.check(_lib.load().lkg_gate_fwd(C.byref(a), m, C.byref(b), bias_pair.data_ptr(), dim, x_ent.data_ptr(),
-                                            x_ent.stride(0), out.data_ptr(), out.stride(0), op_ptr, op_ld, op_ps,
+                                            x_ent.stride(0), out.data_ptr(), out.stride(0), *_planes_out(out_planes),
                                             _lib.stream()))
     return out
 
@@ -180,8 +207,9 @@ def score(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor,
           minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scores = emb[heads] @ emb[tails]^T (model.py:473-486); ``minmax``: opaque uint32[2] state."""
     assert emb.dtype == torch.float32 and emb.stride(1) == 1
-    hp = split_planes(emb, heads)
-    tp = split_planes(emb, tails)
+    rec = scale_from_data(emb)                     # one record for both operands: they are rows of one matrix
+    hp = split_planes(emb, heads, rec=rec)
+    tp = split_planes(emb, tails, rec=rec)
     out = torch.empty((hp.rows, tp.rows), dtype=torch.float32, device=emb.device)
     if out.numel() == 0:
         return out

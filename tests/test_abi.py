@@ -45,7 +45,7 @@ def test_built_for_sm100a(lib_path):
 def test_loads_and_fails_loudly_without_gpu(lib_path):
     from literalkg_b200 import _lib
     lib = _lib.load()
-    assert lib.lkg_abi_version() == 1
+    assert lib.lkg_abi_version() == _lib.ABI_VERSION
     if not torch.cuda.is_available():
         assert lib.lkg_device_check(0) != 0
         assert b"cuda" in lib.lkg_last_error().lower()
