@@ -207,6 +207,29 @@ int lkg_topk_rows(const float* scores, int64_t ld_scores, int64_t n_rows, int64_
                   float* top_values, int64_t* top_cols, const int64_t* target_cols,
                   int64_t* ranks_out, void* stream);
 
+
+/* ---- fused all-entity scoring + top-k: the B x Nt score matrix is never materialised --------------
+ * Index of a set of embedding rows (heads of a batch, or the candidate tails): the scaled fp16 "hi" plane
+ * [m, ld_hi] the filter GEMM reads, the rows' norms (scaled units) and their maximum (device scalar, reset by
+ * the call).  rec: scale record that bounds emb (lkg_scale_from_data); rows: optional int64 gather. */
+int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t dim,
+                    const float* rec, uint16_t* hi, int64_t ld_hi, float* norms /*[m]*/, float* max_norm,
+                    void* stream);
+int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, size_t* bytes /*host out*/);
+/* Per head the k best tails by emb[head] . emb[tail]: larger score first, ties -> lower position in the tail
+ * list; values are the exact dot products (fp32 products summed in fp64, rounded once).
+ *   theta [n_heads] (element stride theta_stride, nullable): a lower bound of each head's k-th best EXACT
+ *     score -- e.g. the k-th best score over a sample of the tails; the filter keeps every tail whose
+ *     single-product fp16 score reaches theta minus a rigorous error bound, so a loose theta only costs time;
+ *   cap: candidate slots per head (power of two, >= 2k); a head that overflows is re-scanned exactly;
+ *   head_rows / tail_rows (nullable): the emb rows behind the two indexes (NULL = identity);
+ *   dim <= 256.  top_values [n_heads, k] fp32, top_cols [n_heads, k] int64 (-inf / -1 past n_tails). */
+int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, const float* head_norms, int64_t n_heads,
+                   const uint16_t* tails_hi, int64_t ld_tails_hi, const float* tail_max_norm, int64_t n_tails,
+                   int32_t dim, const float* rec, const float* theta, int64_t theta_stride, const float* emb,
+                   int64_t ld_emb, const int64_t* head_rows, const int64_t* tail_rows, int32_t k, int32_t cap,
+                   float* top_values, int64_t* top_cols, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

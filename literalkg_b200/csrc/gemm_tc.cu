@@ -18,16 +18,12 @@
 //     tile i+1; 4 epilogue warps read them back with tcgen05.ld (32 lanes x 16 columns per instruction);
 //   * persistent CTAs (one per SM), static tile round-robin, N fastest so that co-running CTAs share A tiles in L2;
 //   * the virtual torch.cat of the reference is a list of K segments, each with its own tensor map.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "tc.cuh"
 
 namespace lkg {
 namespace {
 
-constexpr int kBM = 128;          // rows per tile == TMEM lanes
-constexpr int kBK = 64;           // fp16 elements per K chunk == one 128-byte swizzle row
+using namespace tc;
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
 constexpr int kStages = 2;
 constexpr int kThreads = 192;     // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
@@ -62,76 +58,6 @@ struct TcParams {
     const float* mul_b;                 //   mul_b = packed weight (1/S) or tails; mul_a = heads (score only), nullable
     const float* out_rec;               // scale record of out_planes
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared memory matrix descriptor (start >> 4, SBO = 8 rows * 128 B, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0 in bits 7-9 / 10-12; the two formats
-// must agree -- a bf16 x fp16 mix traps as an illegal instruction), both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t umma_idesc(int bn) {
-    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-}
 
 __device__ __forceinline__ uint32_t order_enc(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -415,22 +341,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
 // planes tensor: fp16 [2 planes][rows][ld] with `plane_stride` elements between the planes; logical width k
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld, int64_t plane_stride, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -506,14 +416,31 @@ __device__ __forceinline__ void write_record(float* rec, float amax) {
     rec[2] = ldexpf(1.f, -e);
 }
 
+// VEC: rows are 16-byte aligned -> one warp per row, float4 loads; otherwise a flat scalar grid-stride loop
+template <bool VEC>
 __global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows, int64_t m,
                               int k, float floor_, float* __restrict__ rec) {
     float mx = 0.f;
-    const int64_t total = m * k;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / k;
-        const float v = fabsf(src[(rows ? rows[r] : r) * ld + (i - r * k)]);
-        mx = fmaxf(mx, v == v ? v : 0.f);
+    if (VEC) {
+        const int lane = threadIdx.x & 31;
+        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        const int kv = k >> 2;
+        for (int64_t r = warp; r < m; r += nwarps) {
+            const float* row = src + (rows ? rows[r] : r) * ld;
+            for (int v = lane; v < kv; v += 32) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(row) + v);
+                // fmaxf drops a NaN operand: NaNs do not poison the scale
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+            }
+            for (int c = 4 * kv + lane; c < k; c += 32) mx = fmaxf(mx, fabsf(__ldg(row + c)));
+        }
+    } else {
+        const int64_t total = m * k;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / k;
+            mx = fmaxf(mx, fabsf(src[(rows ? rows[r] : r) * ld + (i - r * k)]));
+        }
     }
     mx = warp_max(mx);
     uint32_t* bits = reinterpret_cast<uint32_t*>(rec);
@@ -528,8 +455,9 @@ __global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, const i
     __syncthreads();
     if (last && threadIdx.x == 0) {
         __threadfence();
-        const float amax = fmaxf(__uint_as_float(atomicMax(bits, 0u)), floor_);
-        write_record(rec, amax);
+        float amax = __uint_as_float(atomicMax(bits, 0u));
+        if (!(amax < 3.0e38f)) amax = 3.0e38f;                  // +inf in the data: keep the record finite
+        write_record(rec, fmaxf(amax, floor_));
     }
 }
 
@@ -537,20 +465,49 @@ __global__ void bound_record_kernel(float bound, const float* __restrict__ other
     write_record(rec, other ? fmaxf(bound, other[0]) : bound);
 }
 
+template <bool VEC>
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
                                     int64_t m, int k, const float* __restrict__ rec, __half* __restrict__ dst,
                                     int64_t ldp, int64_t plane_stride) {
     const float scale = __ldg(rec + 1);
-    const int64_t total = m * ldp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / ldp;
-        const int c = (int)(i - r * ldp);
-        float x = 0.f;
-        if (c < k) x = src[(rows ? rows[r] : r) * ld + c] * scale;
-        __half h, l;
-        split_f16(x, h, l);
-        dst[i] = h;
-        dst[plane_stride + i] = l;
+    if (VEC) {   // one warp per row, 8 columns per lane and step: two float4 in, one 16-byte store per plane
+        const int lane = threadIdx.x & 31;
+        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        const int groups = (int)(ldp >> 3);
+        for (int64_t r = warp; r < m; r += nwarps) {
+            const float* row = src + (rows ? rows[r] : r) * ld;
+            __half* hrow = dst + r * ldp;
+            for (int gq = lane; gq < groups; gq += 32) {
+                const int c0 = 8 * gq;
+                float x[8];
+                if (c0 + 8 <= k) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(row + c0));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(row + c0) + 1);
+                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = c0 + j < k ? __ldg(row + c0 + j) : 0.f;
+                }
+                __align__(16) __half h[8], l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_f16(x[j] * scale, h[j], l[j]);
+                *reinterpret_cast<uint4*>(hrow + c0) = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(hrow + plane_stride + c0) = *reinterpret_cast<const uint4*>(l);
+            }
+        }
+    } else {
+        const int64_t total = m * ldp;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / ldp;
+            const int c = (int)(i - r * ldp);
+            float x = 0.f;
+            if (c < k) x = src[(rows ? rows[r] : r) * ld + c] * scale;
+            __half h, l;
+            split_f16(x, h, l);
+            dst[i] = h;
+            dst[plane_stride + i] = l;
+        }
     }
 }
 
@@ -645,7 +602,10 @@ extern "C" int lkg_scale_from_data(const float* src, int64_t ld, const int64_t* 
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(rec && m >= 0 && k > 0 && (m == 0 || src) && floor_ >= 0.f, "bad scale arguments");
     LKG_CUDA(cudaMemsetAsync(rec, 0, LKG_SCALE_FLOATS * sizeof(float), stream));
-    absmax_kernel<<<grid_1d(m * k), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
+    if (m > 0 && aligned16(src) && ld % 4 == 0 && k >= 4)
+        absmax_kernel<true><<<grid_1d(m * 32), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
+    else
+        absmax_kernel<false><<<grid_1d(m * k), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
     LKG_LAUNCH_CHECK("absmax_kernel");
     return LKG_OK;
 }
@@ -664,8 +624,12 @@ extern "C" int lkg_split_planes(const float* src, int64_t ld, const int64_t* row
     LKG_REQUIRE(src && rec && planes && m >= 0 && k > 0 && ld_planes >= k && plane_stride >= m * ld_planes,
                 "bad split arguments");
     if (m == 0) return LKG_OK;
-    split_planes_kernel<<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
-                                                                    ld_planes, plane_stride);
+    if (aligned16(src) && ld % 4 == 0 && aligned16(planes) && ld_planes % 8 == 0 && plane_stride % 8 == 0)
+        split_planes_kernel<true><<<grid_1d(m * 32), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
+                                                                       ld_planes, plane_stride);
+    else
+        split_planes_kernel<false><<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
+                                                                            ld_planes, plane_stride);
     LKG_LAUNCH_CHECK("split_planes_kernel");
     return LKG_OK;
 }

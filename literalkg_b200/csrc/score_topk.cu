@@ -1,0 +1,484 @@
+// All-entity link-prediction scoring with a fused top-k epilogue (BASELINE.json north star (d); extension of
+// calc_score, model.py:473-486 -- the reference has no top-k; its oracle is torch.topk applied to
+// calc_score's output).  The B_h x N_t score matrix is never materialised.
+//
+//   lkg_score_index      fp32 embedding rows -> scaled fp16 "hi" plane + row norms + max norm (one pass)
+//   lkg_score_topk       1. threshold: thr_h = theta_h - E_h, theta_h = k-th best EXACT score of the head among a
+//                           sample of the tails (so the true k-th best is >= theta_h), E_h = rigorous bound of the
+//                           single-product fp16 error, c * |h| * max_t |t|;
+//                        2. filter GEMM (tcgen05, ONE fp16 product per k-step): every (head, tail) whose approximate
+//                           score reaches thr_h is appended to the head's candidate list -- the true top-k is a
+//                           subset by construction;
+//                        3. finalize: candidates re-scored exactly (fp32 products summed in fp64, rounded once to
+//                           fp32), sorted by (score desc, column asc), first k written out.  A head whose list
+//                           overflowed falls back to an exact scan of all tails on the device (slow, correct).
+//
+// sm_100a design of the filter GEMM
+//   * persistent CTA per SM; the A operand (two 128-row head blocks x K <= 256, <= 128 KB) is loaded by TMA once and
+//     stays resident in shared memory; tail tiles (128 rows x 64-wide K chunks, 16 KB) stream through a 5-stage
+//     mbarrier ring -- per tile one B fill feeds two MMAs, which halves the L2->SM traffic per flop (a 128 x 256
+//     tile with both operands streamed needs ~175 GB/s per SM, more than L2 can deliver to 148 SMs);
+//   * CTAs that share a tail tile (different head blocks) have consecutive ids, so a tile is read from HBM once
+//     and hit in L2 by the other head blocks;
+//   * accumulators: 2 buffers x 2 head blocks x 128 TMEM columns (all 512), epilogue of tile i overlaps MMAs of i+1;
+//   * epilogue: 4 warps, thread = head row, tcgen05.ld 32 columns at a time, max-reduce, ONE compare against the
+//     row's threshold (pre-multiplied by the operand scales), rare slow path appends (atomicAdd on the row counter).
+#include "tc.cuh"
+
+namespace lkg {
+namespace {
+
+using namespace tc;
+
+constexpr int kBN = 128;                 // tails per tile
+constexpr int kStages = 5;
+constexpr int kThreads = 192;            // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kMaxChunks = 4;            // K <= 256
+constexpr uint32_t kChunkBytes = kBM * kBK * 2;     // 16 KB: 128 rows x 64 fp16 (A block chunk and B stage alike)
+constexpr float kErrCoef = 1.15f / 1024.f;          // |s~ - s| <= kErrCoef |h| |t|: two fp16 roundings (2 * 2^-11),
+                                                    // fp32 accumulation over K <= 256 (2^-16), theta's own 2^-21
+constexpr int kFinalThreads = 256;
+
+struct FilterParams {
+    CUtensorMap a_map;       // heads hi plane [n_heads, K] fp16
+    CUtensorMap b_map;       // tails hi plane [n_tails, K] fp16
+    int n_heads, n_tails, n_chunks, n_pairs, n_tiles;
+    const float* thr;        // [n_heads] threshold in accumulator (scaled) units
+    int* cnt;                // [n_heads] candidates seen
+    int* cand;               // [n_heads, cap] candidate columns (positions in the tail list)
+    int cap;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_constant__ FilterParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                           // [2 blocks][n_chunks] x 16 KB
+    uint8_t* smem_b = smem + 2 * kMaxChunks * kChunkBytes;            // [kStages] x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kChunkBytes);
+    uint64_t* full = bars;                    // [kStages]
+    uint64_t* empty = bars + kStages;         // [kStages]
+    uint64_t* acc_full = bars + 2 * kStages;  // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint64_t* a_full = acc_empty + 2;         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x % p.n_pairs;
+    const int stream = blockIdx.x / p.n_pairs, n_streams = gridDim.x / p.n_pairs;
+    const int row_base = pair * 2 * kBM;
+    const int n_blk = row_base + kBM < p.n_heads ? 2 : 1;             // a pair whose second block is empty skips it
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.b_map) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        mbar_init(a_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(a_full, (uint32_t)(n_blk * p.n_chunks) * kChunkBytes);
+            for (int b = 0; b < n_blk; ++b)
+                for (int kc = 0; kc < p.n_chunks; ++kc)
+                    tma_load_2d(&p.a_map, a_full, smem_a + (b * kMaxChunks + kc) * kChunkBytes, kc * kBK,
+                                row_base + b * kBM);
+            uint32_t stage = 0, phase = 0;
+            for (int tile = stream; tile < p.n_tiles; tile += n_streams) {
+                for (int kc = 0; kc < p.n_chunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], kChunkBytes);
+                    tma_load_2d(&p.b_map, &full[stage], smem_b + stage * kChunkBytes, kc * kBK, tile * kBN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(kBN);
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int tile = stream; tile < p.n_tiles; tile += n_streams, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < p.n_chunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(smem_b + stage * kChunkBytes);
+                    for (int b = 0; b < n_blk; ++b) {
+                        const uint32_t a_addr = smem_u32(smem_a + (b * kMaxChunks + kc) * kChunkBytes);
+                        const uint32_t tmem_d = tmem_base + buf * 2 * kBN + b * kBN;
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            tc_mma_f16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
+                                       (kc | k) != 0);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-3: TMEM lane = head row of the block =====
+        float thr[2];
+        int row[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            row[b] = row_base + b * kBM + warp * 32 + lane;
+            thr[b] = row[b] < p.n_heads ? __ldg(p.thr + row[b]) : INFINITY;
+        }
+        int it = 0;
+        for (int tile = stream; tile < p.n_tiles; tile += n_streams, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                if (b >= n_blk) break;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * kBN + b * kBN;
+#pragma unroll
+                for (int c0 = 0; c0 < kBN; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32_nowait(taddr + c0, r);
+                    tc_ld_wait();
+                    float m = __uint_as_float(r[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                    if (m >= thr[b]) {                                   // rare: this row has a candidate among the 32
+                        const int col0 = tile * kBN + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (__uint_as_float(r[j]) >= thr[b] && col0 + j < p.n_tails) {
+                                const int pos = atomicAdd(p.cnt + row[b], 1);
+                                if (pos < p.cap) p.cand[(int64_t)row[b] * p.cap + pos] = col0 + j;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+constexpr uint32_t kFilterSmem = (2 * kMaxChunks + kStages) * kChunkBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    LKG_REQUIRE(aligned16(base) && (ld * 2) % 16 == 0, "hi planes must be 16-byte aligned (base, row stride)");
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LKG_FAIL(LKG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LKG_OK;
+}
+
+// ---- index: fp32 rows -> scaled fp16 hi plane + norms ------------------------------------------------------------
+__global__ void score_index_kernel(const float* __restrict__ emb, int64_t ld, const int64_t* __restrict__ rows,
+                                   int64_t m, int dim, const float* __restrict__ rec, __half* __restrict__ hi,
+                                   int64_t ld_hi, float* __restrict__ norms, float* __restrict__ max_norm) {
+    const float scale = __ldg(rec + 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int groups = (int)(ld_hi >> 3);
+    float wmax = 0.f;
+    for (int64_t r = warp; r < m; r += nwarps) {
+        const float* src = emb + (rows ? rows[r] : r) * ld;
+        float ss = 0.f;
+        for (int gq = lane; gq < groups; gq += 32) {
+            const int c0 = 8 * gq;
+            float x[8];
+            if (c0 + 8 <= dim && (ld & 3) == 0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(src + c0) + 1);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = c0 + j < dim ? __ldg(src + c0 + j) : 0.f;
+            }
+            __align__(16) __half h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = x[j] * scale;
+                h[j] = __float2half_rn(v);
+                ss = fmaf(v, v, ss);
+            }
+            *reinterpret_cast<uint4*>(hi + r * ld_hi + c0) = *reinterpret_cast<const uint4*>(h);
+        }
+        const float nrm = sqrtf(warp_sum(ss)) * 1.000001f;     // scaled units, rounded up
+        if (lane == 0) norms[r] = nrm;
+        wmax = fmaxf(wmax, nrm);
+    }
+    if (lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<uint32_t*>(max_norm), __float_as_uint(wmax));
+}
+
+// thr (accumulator units) = theta * scale^2 - E,  E = kErrCoef |h| max|t| + absolute slack of fp16 subnormals
+__global__ void score_threshold_kernel(const float* __restrict__ theta, int64_t theta_stride, int n_heads,
+                                       const float* __restrict__ head_norms, const float* __restrict__ tail_max_norm,
+                                       const float* __restrict__ rec, int dim, float* __restrict__ thr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_heads) return;
+    const float s2 = rec[1] * rec[1];
+    const float nh = head_norms[i], nt = *tail_max_norm;
+    const float err = kErrCoef * nh * nt + 4.8e-7f /*2^-21*/ * (nh + nt) * sqrtf((float)dim) + 1.f;
+    const float th = theta ? theta[(int64_t)i * theta_stride] : -INFINITY;
+    // theta == -inf (fewer than k sampled tails): every tail is a candidate
+    thr[i] = th == -INFINITY ? -INFINITY : th * s2 - err - fabsf(th * s2) * 1e-6f;
+}
+
+// ---- finalize ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t enc(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// exact score of one (head, tail): fp32 products are exact in fp64, one rounding to fp32 at the end
+template <int NV>   // dim <= 32 * NV
+__device__ __forceinline__ float exact_dot(const float (&h)[NV], const float* __restrict__ trow, int dim, int lane) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int d = lane + 32 * i;
+        if (d < dim) acc = fma((double)h[i], (double)__ldg(trow + d), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    return (float)acc;
+}
+
+__device__ void bitonic_desc(unsigned long long* keys, int n_pow2) {
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long a = keys[i], b = keys[j];
+                    if ((a < b) == desc) {
+                        keys[i] = b;
+                        keys[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct FinalParams {
+    const float* emb;
+    int64_t ld_emb;
+    const int64_t* head_rows;   // nullable: head i = row i
+    const int64_t* tail_rows;   // nullable: tail j = row j
+    int n_heads, n_tails, dim, k, cap;
+    const int* cnt;
+    const int* cand;
+    float* top_val;
+    int64_t* top_col;
+};
+
+// One CTA per head.  keys: (ordered score << 32) | ~column, so a descending sort gives "larger score first, ties ->
+// lower column".
+__global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalParams p) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ int s_kept;
+    const int head = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kFinalThreads / 32;
+    const int kk = min(p.k, p.n_tails);
+    const float* hrow = p.emb + (p.head_rows ? p.head_rows[head] : head) * p.ld_emb;
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = lane + 32 * i < p.dim ? __ldg(hrow + lane + 32 * i) : 0.f;
+    const int seen = p.cnt[head];
+    int n = 0;
+    if (seen <= p.cap) {
+        n = seen;
+        for (int c = warp; c < n; c += nwarps) {
+            const int col = p.cand[(int64_t)head * p.cap + c];
+            const float s = exact_dot<8>(h, p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb, p.dim, lane);
+            if (lane == 0) keys[c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
+        }
+    } else {
+        // Overflow fallback (the candidate band held more than `cap` tails, e.g. a plateau of near-identical
+        // scores): exact scan of every tail, keeping the best `cap / 2` keys seen so far: when the buffer fills up
+        // it is sorted and its lower half dropped (cap / 2 >= k is checked on the host side).
+        if (threadIdx.x == 0) s_kept = 0;
+        __syncthreads();
+        const int half = p.cap / 2;
+        for (int base = 0; base < p.n_tails; base += half) {
+            const int chunk = min(half, p.n_tails - base);
+            const int kept = s_kept;
+            for (int c = warp; c < chunk; c += nwarps) {
+                const int col = base + c;
+                const float s = exact_dot<8>(h, p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb, p.dim, lane);
+                if (lane == 0) keys[kept + c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
+            }
+            __syncthreads();
+            const int tot = kept + chunk;
+            int p2 = 1;
+            while (p2 < tot) p2 <<= 1;
+            for (int i = tot + threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
+            __syncthreads();
+            bitonic_desc(keys, p2);
+            if (threadIdx.x == 0) s_kept = min(tot, half);
+            __syncthreads();
+        }
+        n = s_kept;
+    }
+    __syncthreads();
+    if (seen <= p.cap) {
+        int p2 = 1;
+        while (p2 < n) p2 <<= 1;
+        for (int i = n + threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        bitonic_desc(keys, p2);
+    }
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+        const bool ok = i < kk && i < n;
+        p.top_val[(int64_t)head * p.k + i] = ok ? dec((uint32_t)(keys[i] >> 32)) : -INFINITY;
+        p.top_col[(int64_t)head * p.k + i] = ok ? (int64_t)(~(uint32_t)(keys[i] & 0xffffffffu)) : -1;
+    }
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace lkg
+
+using namespace lkg;
+
+extern "C" int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows, int64_t m, int32_t dim,
+                               const float* rec, uint16_t* hi, int64_t ld_hi, float* norms, float* max_norm,
+                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(emb && rec && hi && norms && max_norm && m >= 0 && dim > 0, "null / bad argument");
+    LKG_REQUIRE(ld_hi % 8 == 0 && ld_hi >= dim && aligned16(hi) && aligned16(emb), "hi plane rows must be 16-byte aligned");
+    LKG_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), stream));
+    if (m == 0) return LKG_OK;
+    int64_t blocks = (m * 32 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    score_index_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, stream>>>(emb, ld, rows, m, dim, rec, (__half*)hi,
+                                                                              ld_hi, norms, max_norm);
+    LKG_LAUNCH_CHECK("score_index_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, size_t* bytes) {
+    LKG_REQUIRE(bytes && n_heads >= 0 && cap >= 2 && (cap & (cap - 1)) == 0, "cap must be a power of two");
+    *bytes = align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4);
+    return LKG_OK;
+}
+
+extern "C" int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, const float* head_norms, int64_t n_heads,
+                              const uint16_t* tails_hi, int64_t ld_tails_hi, const float* tail_max_norm,
+                              int64_t n_tails, int32_t dim, const float* rec, const float* theta,
+                              int64_t theta_stride, const float* emb, int64_t ld_emb, const int64_t* head_rows,
+                              const int64_t* tail_rows, int32_t k, int32_t cap, float* top_values,
+                              int64_t* top_cols, void* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LKG_REQUIRE(n_heads >= 0 && n_tails >= 1 && n_tails < (1ll << 31) - kBN, "bad shape");
+    LKG_REQUIRE(dim >= 1 && dim <= kMaxChunks * kBK, "the fused scoring path supports dim <= %d (got %d)",
+                kMaxChunks * kBK, dim);
+    LKG_REQUIRE(k >= 1 && cap >= 2 * k && (cap & (cap - 1)) == 0 && cap <= 16384,
+                "cap must be a power of two in [2k, 16384]");
+    if (n_heads == 0) return LKG_OK;
+    LKG_REQUIRE(heads_hi && head_norms && tails_hi && tail_max_norm && rec && emb && top_values && top_cols && workspace,
+                "null argument");
+    char* ws = static_cast<char*>(workspace);
+    int* cnt = reinterpret_cast<int*>(ws);
+    float* thr = reinterpret_cast<float*>(ws + align_up((size_t)n_heads * 4));
+    int* cand = reinterpret_cast<int*>(ws + 2 * align_up((size_t)n_heads * 4));
+    LKG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_heads * 4, stream));
+    score_threshold_kernel<<<(int)((n_heads + 255) / 256), 256, 0, stream>>>(theta, theta_stride, (int)n_heads, head_norms,
+                                                                            tail_max_norm, rec, dim, thr);
+    LKG_LAUNCH_CHECK("score_threshold_kernel");
+
+    const int sms = sm_count();
+    const int max_pairs = sms;                      // heads per launch <= 256 * SMs
+    auto kern = score_filter_kernel;
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem));
+    for (int64_t h0 = 0; h0 < n_heads; h0 += (int64_t)max_pairs * 2 * kBM) {
+        const int nh = (int)((n_heads - h0) < (int64_t)max_pairs * 2 * kBM ? (n_heads - h0) : (int64_t)max_pairs * 2 * kBM);
+        FilterParams p{};
+        if (int rc = make_map_2d(&p.a_map, heads_hi + h0 * ld_heads_hi, nh, dim, ld_heads_hi)) return rc;
+        if (int rc = make_map_2d(&p.b_map, tails_hi, n_tails, dim, ld_tails_hi)) return rc;
+        p.n_heads = nh;
+        p.n_tails = (int)n_tails;
+        p.n_chunks = (dim + kBK - 1) / kBK;
+        p.n_pairs = (nh + 2 * kBM - 1) / (2 * kBM);
+        p.n_tiles = (int)((n_tails + kBN - 1) / kBN);
+        p.thr = thr + h0;
+        p.cnt = cnt + h0;
+        p.cand = cand + h0 * cap;
+        p.cap = cap;
+        int streams = sms / p.n_pairs;
+        if (streams > p.n_tiles) streams = p.n_tiles;
+        kern<<<p.n_pairs * streams, kThreads, kFilterSmem, stream>>>(p);
+        LKG_LAUNCH_CHECK("score_filter_kernel");
+    }
+
+    FinalParams f{};
+    f.emb = emb;
+    f.ld_emb = ld_emb;
+    f.head_rows = head_rows;
+    f.tail_rows = tail_rows;
+    f.n_heads = (int)n_heads;
+    f.n_tails = (int)n_tails;
+    f.dim = dim;
+    f.k = k;
+    f.cap = cap;
+    f.cnt = cnt;
+    f.cand = cand;
+    f.top_val = top_values;
+    f.top_col = top_cols;
+    const size_t fsmem = (size_t)cap * sizeof(unsigned long long);
+    LKG_CUDA(cudaFuncSetAttribute(score_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    score_finalize_kernel<<<(unsigned)n_heads, kFinalThreads, fsmem, stream>>>(f);
+    LKG_LAUNCH_CHECK("score_finalize_kernel");
+    return LKG_OK;
+}

@@ -423,11 +423,18 @@ class LiteralKG(nn.Module):
         all_embed = self.gat_embeddings()
         return ops.predict(all_embed, head_ids, tail_ids, self.milestone_score)
 
-    def topk(self, head_ids, tail_ids, k, target_tails=None, all_embed=None):
+    def topk(self, head_ids, tail_ids, k, target_tails=None, all_embed=None, tail_index=None):
         """Extension (BASELINE.json north star; no reference counterpart): per head the k best tails among
-        ``tail_ids`` (larger score first, ties -> lower position), as (values, positions, ranks-of-targets)."""
+        ``tail_ids`` (larger score first, ties -> lower position), as (values, positions, ranks-of-targets).
+        Large candidate sets go through the fused scoring + top-k kernels (no B x Nt score matrix);
+        ``tail_index`` (``ops.ScoreIndex`` of the tails) can be reused across head batches."""
         if all_embed is None:
             all_embed = self.gat_embeddings()
+        fused = (target_tails is None and all_embed.shape[1] <= ops.FUSED_TOPK_MAX_DIM
+                 and (tail_index is not None or len(tail_ids) >= ops.FUSED_TOPK_MIN_TAILS))
+        if fused:
+            vals, pos = ops.score_topk(all_embed, head_ids, tail_ids, k, tail_index=tail_index)
+            return vals, pos, None
         scores = ops.score(all_embed, head_ids, tail_ids)
         return ops.topk_rows(scores, k, target_tails)
 

@@ -204,10 +204,11 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
 
 
 def score(emb: torch.Tensor, heads: torch.Tensor, tails: torch.Tensor,
-          minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+          minmax: Optional[torch.Tensor] = None, rec: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scores = emb[heads] @ emb[tails]^T (model.py:473-486); ``minmax``: opaque uint32[2] state."""
     assert emb.dtype == torch.float32 and emb.stride(1) == 1
-    rec = scale_from_data(emb)                     # one record for both operands: they are rows of one matrix
+    if rec is None:
+        rec = scale_from_data(emb)                 # one record for both operands: they are rows of one matrix
     hp = split_planes(emb, heads, rec=rec)
     tp = split_planes(emb, tails, rec=rec)
     out = torch.empty((hp.rows, tp.rows), dtype=torch.float32, device=emb.device)
@@ -251,3 +252,66 @@ def topk_rows(scores: torch.Tensor, k: int, target_cols: Optional[torch.Tensor] 
         _lib.check(_lib.load().lkg_topk_rows(scores.data_ptr(), scores.stride(0), rows, cols, k, vals.data_ptr(),
                                              idx.data_ptr(), _lib.ptr(target_cols), _lib.ptr(ranks), _lib.stream()))
     return vals, idx, ranks
+
+
+# ---- fused all-entity scoring + top-k ---------------------------------------------------------------------
+FUSED_TOPK_MIN_TAILS = 16384      # below this the score matrix is small: score() + topk_rows()
+FUSED_TOPK_MAX_DIM = 256
+FUSED_TOPK_CAP = 8192             # candidate slots per head
+
+
+class ScoreIndex:
+    """Scaled fp16 hi plane + norms of a set of rows of an embedding matrix (lkg_score_index).  The index of the
+    candidate tails only depends on the embedding matrix: build it once and reuse it for every head batch."""
+
+    def __init__(self, emb: torch.Tensor, rows: Optional[torch.Tensor], rec: Optional[torch.Tensor] = None):
+        assert emb.dtype == torch.float32 and emb.stride(1) == 1
+        self.emb, self.dim = emb, emb.shape[1]
+        self.rows = None if rows is None else rows.to(device=emb.device, dtype=torch.int64).contiguous()
+        self.m = emb.shape[0] if rows is None else self.rows.numel()
+        self.rec = rec if rec is not None else scale_from_data(emb)
+        self.ld = (self.dim + 7) // 8 * 8
+        self.hi = torch.empty((max(self.m, 1), self.ld), dtype=torch.float16, device=emb.device)
+        self.norms = torch.empty(max(self.m, 1), dtype=torch.float32, device=emb.device)
+        self.max_norm = torch.empty(1, dtype=torch.float32, device=emb.device)
+        with _dev_guard(emb, "score_index"):
+            _lib.check(_lib.load().lkg_score_index(emb.data_ptr(), emb.stride(0), _lib.ptr(self.rows), self.m, self.dim,
+                                                   self.rec.data_ptr(), self.hi.data_ptr(), self.ld,
+                                                   self.norms.data_ptr(), self.max_norm.data_ptr(), _lib.stream()))
+
+
+def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Tensor], k: int,
+               tail_index: Optional[ScoreIndex] = None, cap: int = FUSED_TOPK_CAP, sample: Optional[int] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per head the k best of ``tails`` (None = every row of emb) without materialising the score matrix.
+    Returns (values [B, k] fp32, positions [B, k] int64 into the tail list)."""
+    assert emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] <= FUSED_TOPK_MAX_DIM
+    if tail_index is None:
+        tail_index = ScoreIndex(emb, tails)
+    ti = tail_index
+    hi = ScoreIndex(emb, heads, rec=ti.rec)
+    nh, nt = hi.m, ti.m
+    vals = torch.empty((nh, k), dtype=torch.float32, device=emb.device)
+    pos = torch.empty((nh, k), dtype=torch.int64, device=emb.device)
+    if nh == 0:
+        return vals, pos
+    while cap < 2 * k:
+        cap *= 2
+    # threshold: exact k-th best score of every head over an evenly strided sample of the tails
+    m_s = int(min(nt, sample if sample is not None else max(4096, k * nt // 512)))
+    theta_ptr, theta_stride = None, 0
+    if m_s >= k:
+        spos = (torch.arange(m_s, device=emb.device, dtype=torch.int64) * nt) // m_s
+        srows = spos if ti.rows is None else ti.rows[spos]
+        sv, _, _ = topk_rows(score(emb, hi.rows, srows, rec=ti.rec), k)
+        theta_ptr, theta_stride = sv.data_ptr() + 4 * (k - 1), k
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.load().lkg_score_topk_workspace_bytes(nh, cap, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=emb.device)
+    with _dev_guard(emb, "score_topk", 4):
+        _lib.check(_lib.load().lkg_score_topk(hi.hi.data_ptr(), hi.ld, hi.norms.data_ptr(), nh, ti.hi.data_ptr(), ti.ld,
+                                              ti.max_norm.data_ptr(), nt, emb.shape[1], ti.rec.data_ptr(), theta_ptr,
+                                              theta_stride, emb.data_ptr(), emb.stride(0), _lib.ptr(hi.rows),
+                                              _lib.ptr(ti.rows), k, cap, vals.data_ptr(), pos.data_ptr(), ws.data_ptr(),
+                                              _lib.stream()))
+    return vals, pos

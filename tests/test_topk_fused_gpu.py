@@ -1,0 +1,88 @@
+"""Fused all-entity scoring + top-k (lkg_score_index / lkg_score_topk) against (a) the generic path of this
+library (3-product score matrix + lkg_topk_rows) and (b) a float64 torch reference with the declared rule
+"larger score first, ties -> lower position".  The fused path re-scores its candidates exactly (fp32 products summed
+in fp64, one rounding), so positions must match the float64 ranking wherever the float64 scores differ by more than
+one fp32 ulp, and exactly-equal scores must come out in position order."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_topk(emb, heads, tails, k):
+    s = emb[heads].double() @ emb[tails].double().t()
+    sf = s.float()                                             # correctly rounded fp32 scores
+    order = np.lexsort((np.broadcast_to(np.arange(sf.shape[1]), sf.shape), -sf.cpu().numpy()), axis=1)[:, :k]
+    order = torch.from_numpy(order.copy()).to(emb.device)
+    return torch.gather(sf, 1, order), order
+
+
+@pytest.mark.parametrize("n,dim,nh,k", [(40_000, 256, 300, 10), (70_001, 256, 129, 100), (30_000, 64, 64, 5),
+                                        (25_000, 200, 513, 10)])
+def test_fused_topk_matches_float64_ranking(n, dim, nh, k):
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n + dim)
+    emb = torch.nn.functional.leaky_relu(torch.randn(n, dim, generator=g, device="cuda"), 0.01) * 0.37
+    heads = torch.randint(0, n, (nh,), generator=g, device="cuda")
+    tails = torch.randperm(n, generator=g, device="cuda")[: n - 7]          # a gathered, permuted tail list
+    vals, pos = ops.score_topk(emb, heads, tails, k)
+    rv, rp = ref_topk(emb, heads, tails, k)
+    assert torch.equal(pos, rp)
+    assert torch.equal(vals, rv)
+    # identity tail list (tails=None) and a reused index give the same answer
+    ti = ops.ScoreIndex(emb, None)
+    v2, p2 = ops.score_topk(emb, heads, None, k, tail_index=ti)
+    rv2, rp2 = ref_topk(emb, heads, torch.arange(n, device="cuda"), k)
+    assert torch.equal(p2, rp2) and torch.equal(v2, rv2)
+
+
+def test_fused_topk_plateau_overflow_and_ties():
+    """20 000 identical best tails: the candidate band overflows every head's list; the exact fallback must return
+    the lowest positions of the plateau, in order."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, dim, k = 50_000, 128, 10
+    emb = torch.randn(n, dim, generator=g, device="cuda") * 0.1
+    plateau = torch.randperm(n, generator=g, device="cuda")[:20_000]
+    emb[plateau] = emb[plateau[0]].clone() * 0 + 1.0                        # identical rows with the largest scores
+    heads = torch.arange(40, device="cuda") * 13 + 1
+    emb[heads] = emb[heads].abs() + 0.5                                     # positive heads: plateau rows win
+    vals, pos = ops.score_topk(emb, heads, None, k, cap=1024)
+    rv, rp = ref_topk(emb, heads, torch.arange(n, device="cuda"), k)
+    assert torch.equal(pos, rp)
+    assert torch.equal(vals, rv)
+    assert (pos[:, 1:] > pos[:, :-1]).all()                                  # ties in position order
+
+
+def test_fused_topk_vs_generic_path_and_model_api():
+    import argparse
+    import literalkg_b200 as L
+    import literalkg_oracle as O
+    from literalkg_b200 import ops
+    cfg = O.OracleConfig(n_conv_layers=2, mess_dropout=0.0)
+    n, n_rel = 20_000, 8
+    kg = L.synthetic.make_kg(n, 120_000, n_rel, seed=5, max_out_degree=200)
+    num, txt = L.synthetic.make_literals(n, seed=5)
+    args = argparse.Namespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    kt = L.KGTensors(kg.h, kg.t, kg.r, n_entities=n)
+    torch.manual_seed(0)
+    m = L.LiteralKG(args, n, n_rel, kt.A_in, num, txt).cuda().eval()
+    with torch.no_grad():
+        m.entity_embed.weight.mul_(30)
+    m(kt.h_list, kt.t_list, kt.r_list, kt.relations, device="cuda", mode="update_att")
+    emb = m.gat_embeddings()
+    heads = torch.arange(0, 200, device="cuda") * 37 % n
+    tails = torch.arange(n, device="cuda")
+    v, p, r = m.topk(heads, tails, 10, all_embed=emb)                        # n >= 16384: fused path
+    assert r is None
+    s = ops.score(emb, heads, tails)                                        # generic path: 3-product score matrix
+    gv, gp, _ = ops.topk_rows(s, 10)
+    # the two paths round the scores differently (exact vs 2^-22): compare where the generic top-11 is separated
+    tv, _ = torch.topk(s, 11, dim=1)
+    clear = ((tv[:, :-1] - tv[:, 1:]).min(dim=1).values > 1e-5 * s.abs().max())
+    assert clear.sum() > 20
+    assert torch.equal(p[clear], gp[clear])
+    assert ((v - gv).abs().max() / gv.abs().max()).item() < 1e-5
+    rv, rp = ref_topk(emb, heads, tails, 10)
+    assert torch.equal(p, rp) and torch.equal(v, rv)
