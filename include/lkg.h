@@ -188,7 +188,11 @@ int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* eg
                       const float* drop_mask /*nullable [N,d_out] multiplicative*/,
                       float* x_out, int64_t ld_x, float* xn_out /*nullable*/, int64_t ld_xn,
                       uint16_t* xn_planes /*nullable: hi/lo copy of xn*/, int64_t ld_planes, int64_t plane_stride,
-                      const float* xn_rec /*scale record of xn_planes (bound 1)*/, void* workspace, void* stream);
+                      const float* xn_rec /*scale record of xn_planes (bound 1)*/,
+                      int64_t local_row_base /*r1, r2, drop_mask, xn_out, xn_planes hold rows [local_row_base, ...):
+                                               the row partition's local buffers (0 on one GPU); ego and x_out
+                                               are indexed by the global row*/,
+                      void* workspace, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
 /* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final
@@ -215,20 +219,26 @@ int lkg_topk_rows(const float* scores, int64_t ld_scores, int64_t n_rows, int64_
 int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t dim,
                     const float* rec, uint16_t* hi, int64_t ld_hi, float* norms /*[m]*/, float* max_norm,
                     void* stream);
-int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, size_t* bytes /*host out*/);
+int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, int32_t sample_tiles, size_t* bytes /*host out*/);
 /* Per head the k best tails by emb[head] . emb[tail]: larger score first, ties -> lower position in the tail
  * list; values are the exact dot products (fp32 products summed in fp64, rounded once).
- *   theta [n_heads] (element stride theta_stride, nullable): a lower bound of each head's k-th best EXACT
- *     score -- e.g. the k-th best score over a sample of the tails; the filter keeps every tail whose
- *     single-product fp16 score reaches theta minus a rigorous error bound, so a loose theta only costs time;
+ *   theta [n_heads] (element stride theta_stride, nullable): a caller-supplied lower bound of each head's k-th
+ *     best EXACT score; the filter keeps every tail whose single-product fp16 score reaches theta minus a
+ *     rigorous error bound, so a loose theta only costs time;
+ *   sample_tiles (used when theta is NULL): the library derives the bound itself from the k-th largest tile
+ *     maximum over this many evenly strided 128-tail tiles (a first, short pass of the same GEMM kernel);
+ *     needs sample_tiles >= k to give a bound; 0 = no bound, every tail is a candidate;
  *   cap: candidate slots per head (power of two, >= 2k); a head that overflows is re-scanned exactly;
- *   head_rows / tail_rows (nullable): the emb rows behind the two indexes (NULL = identity);
- *   dim <= 256.  top_values [n_heads, k] fp32, top_cols [n_heads, k] int64 (-inf / -1 past n_tails). */
+ *   emb: the fp32 matrix behind the tails index; head_emb (nullable = emb): the one behind the heads index
+ *     (a separate matrix when the heads' rows were gathered from other ranks);
+ *   head_rows / tail_rows (nullable): the rows of those matrices behind the two indexes (NULL = identity);
+ *   dim <= 256, dim % 4 == 0.  top_values [n_heads, k] fp32, top_cols [n_heads, k] int64 (-inf / -1 past n_tails). */
 int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, const float* head_norms, int64_t n_heads,
                    const uint16_t* tails_hi, int64_t ld_tails_hi, const float* tail_max_norm, int64_t n_tails,
-                   int32_t dim, const float* rec, const float* theta, int64_t theta_stride, const float* emb,
-                   int64_t ld_emb, const int64_t* head_rows, const int64_t* tail_rows, int32_t k, int32_t cap,
-                   float* top_values, int64_t* top_cols, void* workspace, void* stream);
+                   int32_t dim, const float* rec, const float* theta, int64_t theta_stride, int32_t sample_tiles,
+                   const float* emb, int64_t ld_emb, const float* head_emb, int64_t ld_head_emb,
+                   const int64_t* head_rows, const int64_t* tail_rows, int32_t k, int32_t cap, float* top_values,
+                   int64_t* top_cols, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,8 @@ struct AggParams {
     const float* xn_rec;        // its scale record (|xn| <= 1)
     int* counter;
     int p_stride;      // padded row stride (floats) of P in shared memory
+    int64_t local_row_base;   // r1 / r2 / mask / xn_out / xn_planes are indexed by (row - local_row_base): the
+                              // row partition's local buffers; ego and x_out are indexed by the global row
 };
 
 template <int S, int NC, int MODE>
@@ -146,12 +148,12 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
         float acc1[kRows][NC], acc2[kRows][NC];
 #pragma unroll
         for (int rr = 0; rr < kRows; ++rr) {
-            const int row = row_of(min(base + rr, n - 1));
+            const int64_t lrow = row_of(min(base + rr, n - 1)) - p.local_row_base;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int ch = lane + 32 * c;
-                acc1[rr][c] = (ch < d_out && p.r1) ? __ldg(p.r1 + (int64_t)row * p.ld_r + ch) : 0.f;
-                acc2[rr][c] = (MODE == kBi && ch < d_out && p.r2) ? __ldg(p.r2 + (int64_t)row * p.ld_r + ch) : 0.f;
+                acc1[rr][c] = (ch < d_out && p.r1) ? __ldg(p.r1 + lrow * p.ld_r + ch) : 0.f;
+                acc2[rr][c] = (MODE == kBi && ch < d_out && p.r2) ? __ldg(p.r2 + lrow * p.ld_r + ch) : 0.f;
             }
         }
         for (int d4 = 0; d4 < nvec; ++d4) {
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
         for (int rr = 0; rr < kRows; ++rr) {
             if (base + rr >= n) break;
             const int row = row_of(base + rr);
+            const int64_t lrow = row - p.local_row_base;
             float emb[NC];
             float s1 = 0.f;
 #pragma unroll
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
                 float x = 0.f;
                 if (ch < d_out) {
                     x = (emb[c] - mean) * rstd * __ldg(p.ln_w + ch) + __ldg(p.ln_b + ch);
-                    if (p.mask) x *= __ldg(p.mask + (int64_t)row * d_out + ch);
+                    if (p.mask) x *= __ldg(p.mask + lrow * d_out + ch);
                     p.x_out[(int64_t)row * p.ld_x + ch] = x;
                 }
                 emb[c] = x;
@@ -243,13 +246,13 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
                     const int ch = lane + 32 * c;
                     if (ch < d_out) {
                         const float xn = emb[c] * inv;
-                        if (p.xn_out) p.xn_out[(int64_t)row * p.ld_xn + ch] = xn;
+                        if (p.xn_out) p.xn_out[lrow * p.ld_xn + ch] = xn;
                         if (p.xn_planes) {
                             const float xs = xn * pscale;
                             const __half h = __float2half_rn(xs);
                             const __half l = __float2half_rn(xs - __half2float(h));
-                            p.xn_planes[(int64_t)row * p.ld_planes + ch] = h;
-                            p.xn_planes[p.plane_stride + (int64_t)row * p.ld_planes + ch] = l;
+                            p.xn_planes[lrow * p.ld_planes + ch] = h;
+                            p.xn_planes[p.plane_stride + lrow * p.ld_planes + ch] = l;
                         }
                     }
                 }
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
         if (base >= n) break;
         const bool live = base + grp < n;
         const int row = live ? (p.g.row_order ? __ldg(p.g.row_order + base + grp) : row0 + base + grp) : 0;
+        const int64_t lrow = row - p.local_row_base;
         const int u0 = live ? __ldg(p.g.rowptr + row) : 0;
         const int u1 = live ? __ldg(p.g.rowptr + row + 1) : 0;
         int max_deg = u1 - u0;
@@ -369,11 +373,10 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
         for (int i = 0; i < CPL; ++i) {
             const int ch = 4 * (gl + LPR * i);
             const bool okc = live && ch < d_out;
-            acc1[i] = (okc && p.r1) ? __ldg(reinterpret_cast<const float4*>(p.r1 + (int64_t)row * p.ld_r + ch))
+            acc1[i] = (okc && p.r1) ? __ldg(reinterpret_cast<const float4*>(p.r1 + lrow * p.ld_r + ch))
                                     : make_float4(0, 0, 0, 0);
-            acc2[i] = (MODE == kBi && okc && p.r2)
-                          ? __ldg(reinterpret_cast<const float4*>(p.r2 + (int64_t)row * p.ld_r + ch))
-                          : make_float4(0, 0, 0, 0);
+            acc2[i] = (MODE == kBi && okc && p.r2) ? __ldg(reinterpret_cast<const float4*>(p.r2 + lrow * p.ld_r + ch))
+                                                   : make_float4(0, 0, 0, 0);
         }
 #pragma unroll 2
         for (int sl = 0; sl < LPR; ++sl) {
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
                 x.z = (emb[i].z - mean) * rstd * lw.z + lb.z;
                 x.w = (emb[i].w - mean) * rstd * lw.w + lb.w;
                 if (p.mask && live) {
-                    const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)row * d_out + ch));
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask + lrow * d_out + ch));
                     x.x *= mk.x; x.y *= mk.y; x.z *= mk.z; x.w *= mk.w;
                 }
                 if (live) *reinterpret_cast<float4*>(p.x_out + (int64_t)row * p.ld_x + ch) = x;
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
                 const int ch = 4 * (gl + LPR * i);
                 if (ch < d_out && live) {
                     const float4 xn = make_float4(emb[i].x * inv, emb[i].y * inv, emb[i].z * inv, emb[i].w * inv);
-                    if (p.xn_out) *reinterpret_cast<float4*>(p.xn_out + (int64_t)row * p.ld_xn + ch) = xn;
+                    if (p.xn_out) *reinterpret_cast<float4*>(p.xn_out + lrow * p.ld_xn + ch) = xn;
                     if (p.xn_planes) {
                         const float v[4] = {xn.x * pscale, xn.y * pscale, xn.z * pscale, xn.w * pscale};
                         __align__(8) __half h[4], l[4];
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
                             h[c] = __float2half_rn(v[c]);
                             l[c] = __float2half_rn(v[c] - __half2float(h[c]));
                         }
-                        __half* hp = p.xn_planes + (int64_t)row * p.ld_planes + ch;
+                        __half* hp = p.xn_planes + lrow * p.ld_planes + ch;
                         *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<const uint2*>(h);
                         *reinterpret_cast<uint2*>(hp + p.plane_stride) = *reinterpret_cast<const uint2*>(l);
                     }
@@ -546,7 +549,8 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
                                  const float* r1, const float* r2, int64_t ld_r, const float* ln_weight,
                                  const float* ln_bias, const float* drop_mask, float* x_out, int64_t ld_x,
                                  float* xn_out, int64_t ld_xn, uint16_t* xn_planes, int64_t ld_planes,
-                                 int64_t plane_stride, const float* xn_rec, void* workspace, void* stream_) {
+                                 int64_t plane_stride, const float* xn_rec, int64_t local_row_base, void* workspace,
+                                 void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(g && ego && pb && ln_weight && ln_bias && x_out && workspace, "null argument");
     LKG_REQUIRE(g->nnz == 0 || a_values != nullptr, "a_values is null");
@@ -598,6 +602,7 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     p.xn_rec = xn_rec;
     p.ld_planes = ld_planes;
     p.plane_stride = plane_stride;
+    p.local_row_base = local_row_base;
     p.counter = static_cast<int*>(workspace);
     // lane c reads sp[d * ps + c]: any stride is conflict free for 32 consecutive channels; pad to a
     // multiple of 4 floats to keep rows 16-byte aligned

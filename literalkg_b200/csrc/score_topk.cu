@@ -47,6 +47,10 @@ struct FilterParams {
     int* cnt;                // [n_heads] candidates seen
     int* cand;               // [n_heads, cap] candidate columns (positions in the tail list)
     int cap;
+    // sampling mode (tilemax != NULL): visit tiles 0, tile_stride, 2 tile_stride, ... (n_tiles of them) and store
+    // every head's largest approximate score of each visited tile instead of filtering
+    float* tilemax;          // [n_heads, n_tiles]
+    int tile_stride;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_constant__ FilterParams p) {
@@ -105,7 +109,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
                 for (int kc = 0; kc < p.n_chunks; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], kChunkBytes);
-                    tma_load_2d(&p.b_map, &full[stage], smem_b + stage * kChunkBytes, kc * kBK, tile * kBN);
+                    tma_load_2d(&p.b_map, &full[stage], smem_b + stage * kChunkBytes, kc * kBK,
+                                tile * p.tile_stride * kBN);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             row[b] = row_base + b * kBM + warp * 32 + lane;
-            thr[b] = row[b] < p.n_heads ? __ldg(p.thr + row[b]) : INFINITY;
+            thr[b] = (row[b] < p.n_heads && !p.tilemax) ? __ldg(p.thr + row[b]) : INFINITY;
         }
         int it = 0;
         for (int tile = stream; tile < p.n_tiles; tile += n_streams, ++it) {
@@ -164,16 +169,29 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
             for (int b = 0; b < 2; ++b) {
                 if (b >= n_blk) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * kBN + b * kBN;
+                const int tile_col0 = tile * p.tile_stride * kBN;
+                float tmax = -INFINITY;
 #pragma unroll
                 for (int c0 = 0; c0 < kBN; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32_nowait(taddr + c0, r);
                     tc_ld_wait();
+                    const int col0 = tile_col0 + c0;
+                    if (p.tilemax) {
+                        if (col0 + 32 <= p.n_tails) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(r[j]));
+                        } else {                                         // last, partial tile: TMA zero-filled the rest
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.n_tails) tmax = fmaxf(tmax, __uint_as_float(r[j]));
+                        }
+                        continue;
+                    }
                     float m = __uint_as_float(r[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
                     if (m >= thr[b]) {                                   // rare: this row has a candidate among the 32
-                        const int col0 = tile * kBN + c0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (__uint_as_float(r[j]) >= thr[b] && col0 + j < p.n_tails) {
@@ -183,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
                         }
                     }
                 }
+                if (p.tilemax && row[b] < p.n_heads) p.tilemax[(int64_t)row[b] * p.n_tiles + tile] = tmax;
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
@@ -254,18 +273,57 @@ __global__ void score_index_kernel(const float* __restrict__ emb, int64_t ld, co
     if (lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<uint32_t*>(max_norm), __float_as_uint(wmax));
 }
 
-// thr (accumulator units) = theta * scale^2 - E,  E = kErrCoef |h| max|t| + absolute slack of fp16 subnormals
+// E (accumulator units): bound of |single-product fp16 score - exact score| for one head against any tail
+__device__ __forceinline__ float score_err(float nh, float nt, int dim) {
+    return kErrCoef * nh * nt + 4.8e-7f /*2^-21*/ * (nh + nt) * sqrtf((float)dim) + 1.f;
+}
+
+// thr = theta * scale^2 - E with theta a lower bound of the head's k-th best EXACT score (caller supplied)
 __global__ void score_threshold_kernel(const float* __restrict__ theta, int64_t theta_stride, int n_heads,
                                        const float* __restrict__ head_norms, const float* __restrict__ tail_max_norm,
                                        const float* __restrict__ rec, int dim, float* __restrict__ thr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_heads) return;
     const float s2 = rec[1] * rec[1];
-    const float nh = head_norms[i], nt = *tail_max_norm;
-    const float err = kErrCoef * nh * nt + 4.8e-7f /*2^-21*/ * (nh + nt) * sqrtf((float)dim) + 1.f;
+    const float err = score_err(head_norms[i], *tail_max_norm, dim);
     const float th = theta ? theta[(int64_t)i * theta_stride] : -INFINITY;
-    // theta == -inf (fewer than k sampled tails): every tail is a candidate
+    // theta == -inf (no bound known): every tail is a candidate
     thr[i] = th == -INFINITY ? -INFINITY : th * s2 - err - fabsf(th * s2) * 1e-6f;
+}
+
+// thr = (k-th largest tile maximum of the sampled tiles) - 2E.  The tile maxima are k distinct tails whose
+// APPROXIMATE scores reach m_k, so their exact scores reach m_k - E, so the exact k-th best is >= m_k - E and every
+// member of the true top-k has an approximate score >= m_k - 2E.  One CTA per head, bitonic sort in shared memory.
+__global__ void __launch_bounds__(256) score_sample_threshold_kernel(const float* __restrict__ tilemax, int n_st, int k,
+                                                                     const float* __restrict__ head_norms,
+                                                                     const float* __restrict__ tail_max_norm, int dim,
+                                                                     float* __restrict__ thr) {
+    extern __shared__ float sv[];
+    const int head = blockIdx.x;
+    int p2 = 1;
+    while (p2 < n_st) p2 <<= 1;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) sv[i] = i < n_st ? tilemax[(int64_t)head * n_st + i] : -INFINITY;
+    __syncthreads();
+    for (int size = 2; size <= p2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const float a = sv[i], b = sv[j];
+                    if ((a < b) == desc) {
+                        sv[i] = b;
+                        sv[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        const float mk = k <= n_st ? sv[k - 1] : -INFINITY;
+        thr[head] = mk == -INFINITY ? -INFINITY : mk - 2.f * score_err(head_norms[head], *tail_max_norm, dim) - fabsf(mk) * 1e-6f;
+    }
 }
 
 // ---- finalize ----------------------------------------------------------------------------------------------------
@@ -277,17 +335,33 @@ __device__ __forceinline__ float dec(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// exact score of one (head, tail): fp32 products are exact in fp64, one rounding to fp32 at the end
-template <int NV>   // dim <= 32 * NV
-__device__ __forceinline__ float exact_dot(const float (&h)[NV], const float* __restrict__ trow, int dim, int lane) {
+// Exact score of one (head, tail): fp32 products are exact in fp64, summed in fp64, one rounding to fp32 at the end.
+// Eight lanes share a tail row (lane q of the group takes float4 q, q + 8, ...), so a warp scores four candidates
+// at once with all its row loads in flight together; the head row is read from shared memory.
+__device__ __forceinline__ float exact_dot8(const float* __restrict__ s_head, const float* __restrict__ trow, int dim,
+                                            int q, bool live) {
     double acc = 0.0;
+    const int nv = dim >> 2;                                   // dim % 4 == 0 is checked on the host side
+    float4 t[8];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int d = lane + 32 * i;
-        if (d < dim) acc = fma((double)h[i], (double)__ldg(trow + d), acc);
+    for (int i = 0; i < 8; ++i) {
+        const int v = q + 8 * i;
+        t[i] = (live && v < nv) ? __ldg(reinterpret_cast<const float4*>(trow) + v) : make_float4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    for (int i = 0; i < 8; ++i) {
+        const int v = q + 8 * i;
+        if (v < nv) {
+            const float4 h = *reinterpret_cast<const float4*>(s_head + 4 * v);
+            acc = fma((double)h.x, (double)t[i].x, acc);
+            acc = fma((double)h.y, (double)t[i].y, acc);
+            acc = fma((double)h.z, (double)t[i].z, acc);
+            acc = fma((double)h.w, (double)t[i].w, acc);
+        }
+    }
+    acc += __shfl_xor_sync(kFull, acc, 4);
+    acc += __shfl_xor_sync(kFull, acc, 2);
+    acc += __shfl_xor_sync(kFull, acc, 1);
     return (float)acc;
 }
 
@@ -311,8 +385,10 @@ __device__ void bitonic_desc(unsigned long long* keys, int n_pow2) {
 }
 
 struct FinalParams {
-    const float* emb;
+    const float* emb;           // tails' matrix
     int64_t ld_emb;
+    const float* head_emb;      // heads' matrix (may be the same)
+    int64_t ld_head_emb;
     const int64_t* head_rows;   // nullable: head i = row i
     const int64_t* tail_rows;   // nullable: tail j = row j
     int n_heads, n_tails, dim, k, cap;
@@ -329,34 +405,39 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
     __shared__ int s_kept;
     const int head = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kFinalThreads / 32;
+    const int grp = lane >> 3, q = lane & 7;                    // 4 candidates per warp, 8 lanes each
     const int kk = min(p.k, p.n_tails);
-    const float* hrow = p.emb + (p.head_rows ? p.head_rows[head] : head) * p.ld_emb;
-    float h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = lane + 32 * i < p.dim ? __ldg(hrow + lane + 32 * i) : 0.f;
+    __shared__ __align__(16) float s_head[kMaxChunks * kBK];
+    const float* hrow = p.head_emb + (p.head_rows ? p.head_rows[head] : head) * p.ld_head_emb;
+    for (int i = threadIdx.x; i < kMaxChunks * kBK; i += blockDim.x) s_head[i] = i < p.dim ? __ldg(hrow + i) : 0.f;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
     const int seen = p.cnt[head];
     int n = 0;
+    auto tail_row = [&](int col) { return p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb; };
     if (seen <= p.cap) {
         n = seen;
-        for (int c = warp; c < n; c += nwarps) {
-            const int col = p.cand[(int64_t)head * p.cap + c];
-            const float s = exact_dot<8>(h, p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb, p.dim, lane);
-            if (lane == 0) keys[c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
+        for (int c0 = 4 * warp; c0 < n; c0 += 4 * nwarps) {
+            const int c = c0 + grp;
+            const bool live = c < n;
+            const int col = live ? p.cand[(int64_t)head * p.cap + c] : 0;
+            const float s = exact_dot8(s_head, tail_row(col), p.dim, q, live);
+            if (live && q == 0) keys[c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
         }
     } else {
         // Overflow fallback (the candidate band held more than `cap` tails, e.g. a plateau of near-identical
         // scores): exact scan of every tail, keeping the best `cap / 2` keys seen so far: when the buffer fills up
         // it is sorted and its lower half dropped (cap / 2 >= k is checked on the host side).
-        if (threadIdx.x == 0) s_kept = 0;
-        __syncthreads();
         const int half = p.cap / 2;
         for (int base = 0; base < p.n_tails; base += half) {
             const int chunk = min(half, p.n_tails - base);
             const int kept = s_kept;
-            for (int c = warp; c < chunk; c += nwarps) {
-                const int col = base + c;
-                const float s = exact_dot<8>(h, p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb, p.dim, lane);
-                if (lane == 0) keys[kept + c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
+            for (int c0 = 4 * warp; c0 < chunk; c0 += 4 * nwarps) {
+                const int c = c0 + grp;
+                const bool live = c < chunk;
+                const int col = live ? base + c : 0;
+                const float s = exact_dot8(s_head, tail_row(col), p.dim, q, live);
+                if (live && q == 0) keys[kept + c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
             }
             __syncthreads();
             const int tot = kept + chunk;
@@ -408,22 +489,27 @@ extern "C" int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows
     return LKG_OK;
 }
 
-extern "C" int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, size_t* bytes) {
+extern "C" int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, int32_t sample_tiles, size_t* bytes) {
     LKG_REQUIRE(bytes && n_heads >= 0 && cap >= 2 && (cap & (cap - 1)) == 0, "cap must be a power of two");
-    *bytes = align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4);
+    LKG_REQUIRE(sample_tiles >= 0 && sample_tiles <= 4096, "sample_tiles must be in [0, 4096]");
+    *bytes = align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4) +
+             align_up((size_t)n_heads * sample_tiles * 4);
     return LKG_OK;
 }
 
 extern "C" int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, const float* head_norms, int64_t n_heads,
                               const uint16_t* tails_hi, int64_t ld_tails_hi, const float* tail_max_norm,
                               int64_t n_tails, int32_t dim, const float* rec, const float* theta,
-                              int64_t theta_stride, const float* emb, int64_t ld_emb, const int64_t* head_rows,
-                              const int64_t* tail_rows, int32_t k, int32_t cap, float* top_values,
-                              int64_t* top_cols, void* workspace, void* stream_) {
+                              int64_t theta_stride, int32_t sample_tiles, const float* emb, int64_t ld_emb,
+                              const float* head_emb, int64_t ld_head_emb, const int64_t* head_rows,
+                              const int64_t* tail_rows, int32_t k, int32_t cap,
+                              float* top_values, int64_t* top_cols, void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(n_heads >= 0 && n_tails >= 1 && n_tails < (1ll << 31) - kBN, "bad shape");
-    LKG_REQUIRE(dim >= 1 && dim <= kMaxChunks * kBK, "the fused scoring path supports dim <= %d (got %d)",
-                kMaxChunks * kBK, dim);
+    LKG_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= kMaxChunks * kBK,
+                "the fused scoring path supports dim %% 4 == 0, dim <= %d (got %d)", kMaxChunks * kBK, dim);
+    LKG_REQUIRE(ld_emb % 4 == 0 && aligned16(emb) && (!head_emb || (ld_head_emb % 4 == 0 && aligned16(head_emb))),
+                "embedding rows must be 16-byte aligned");
     LKG_REQUIRE(k >= 1 && cap >= 2 * k && (cap & (cap - 1)) == 0 && cap <= 16384,
                 "cap must be a power of two in [2k, 16384]");
     if (n_heads == 0) return LKG_OK;
@@ -433,38 +519,63 @@ extern "C" int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, con
     int* cnt = reinterpret_cast<int*>(ws);
     float* thr = reinterpret_cast<float*>(ws + align_up((size_t)n_heads * 4));
     int* cand = reinterpret_cast<int*>(ws + 2 * align_up((size_t)n_heads * 4));
+    float* tilemax = reinterpret_cast<float*>(ws + 2 * align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4));
     LKG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_heads * 4, stream));
-    score_threshold_kernel<<<(int)((n_heads + 255) / 256), 256, 0, stream>>>(theta, theta_stride, (int)n_heads, head_norms,
-                                                                            tail_max_norm, rec, dim, thr);
-    LKG_LAUNCH_CHECK("score_threshold_kernel");
+    if (theta || sample_tiles <= 0) {
+        score_threshold_kernel<<<(int)((n_heads + 255) / 256), 256, 0, stream>>>(theta, theta_stride, (int)n_heads,
+                                                                                head_norms, tail_max_norm, rec, dim, thr);
+        LKG_LAUNCH_CHECK("score_threshold_kernel");
+    }
+    const int n_tiles_all = (int)((n_tails + kBN - 1) / kBN);
+    int n_st = 0, st_stride = 1;
+    if (!theta && sample_tiles > 0) {
+        LKG_REQUIRE(sample_tiles <= 4096, "sample_tiles must be <= 4096");
+        st_stride = n_tiles_all / sample_tiles > 0 ? n_tiles_all / sample_tiles : 1;
+        n_st = (n_tiles_all + st_stride - 1) / st_stride;
+        if (n_st > sample_tiles) n_st = sample_tiles;
+    }
 
     const int sms = sm_count();
     const int max_pairs = sms;                      // heads per launch <= 256 * SMs
     auto kern = score_filter_kernel;
     LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem));
-    for (int64_t h0 = 0; h0 < n_heads; h0 += (int64_t)max_pairs * 2 * kBM) {
-        const int nh = (int)((n_heads - h0) < (int64_t)max_pairs * 2 * kBM ? (n_heads - h0) : (int64_t)max_pairs * 2 * kBM);
-        FilterParams p{};
-        if (int rc = make_map_2d(&p.a_map, heads_hi + h0 * ld_heads_hi, nh, dim, ld_heads_hi)) return rc;
-        if (int rc = make_map_2d(&p.b_map, tails_hi, n_tails, dim, ld_tails_hi)) return rc;
-        p.n_heads = nh;
-        p.n_tails = (int)n_tails;
-        p.n_chunks = (dim + kBK - 1) / kBK;
-        p.n_pairs = (nh + 2 * kBM - 1) / (2 * kBM);
-        p.n_tiles = (int)((n_tails + kBN - 1) / kBN);
-        p.thr = thr + h0;
-        p.cnt = cnt + h0;
-        p.cand = cand + h0 * cap;
-        p.cap = cap;
-        int streams = sms / p.n_pairs;
-        if (streams > p.n_tiles) streams = p.n_tiles;
-        kern<<<p.n_pairs * streams, kThreads, kFilterSmem, stream>>>(p);
-        LKG_LAUNCH_CHECK("score_filter_kernel");
+    // pass 0 (optional): tile maxima over the sampled tiles -> thresholds; pass 1: filter over all tiles
+    for (int pass = (n_st > 0 ? 0 : 1); pass < 2; ++pass) {
+        for (int64_t h0 = 0; h0 < n_heads; h0 += (int64_t)max_pairs * 2 * kBM) {
+            const int nh = (int)((n_heads - h0) < (int64_t)max_pairs * 2 * kBM ? (n_heads - h0) : (int64_t)max_pairs * 2 * kBM);
+            FilterParams p{};
+            if (int rc = make_map_2d(&p.a_map, heads_hi + h0 * ld_heads_hi, nh, dim, ld_heads_hi)) return rc;
+            if (int rc = make_map_2d(&p.b_map, tails_hi, n_tails, dim, ld_tails_hi)) return rc;
+            p.n_heads = nh;
+            p.n_tails = (int)n_tails;
+            p.n_chunks = (dim + kBK - 1) / kBK;
+            p.n_pairs = (nh + 2 * kBM - 1) / (2 * kBM);
+            p.n_tiles = pass == 0 ? n_st : n_tiles_all;
+            p.tile_stride = pass == 0 ? st_stride : 1;
+            p.tilemax = pass == 0 ? tilemax + h0 * n_st : nullptr;
+            p.thr = thr + h0;
+            p.cnt = cnt + h0;
+            p.cand = cand + h0 * cap;
+            p.cap = cap;
+            int streams = sms / p.n_pairs;
+            if (streams > p.n_tiles) streams = p.n_tiles;
+            kern<<<p.n_pairs * streams, kThreads, kFilterSmem, stream>>>(p);
+            LKG_LAUNCH_CHECK("score_filter_kernel");
+        }
+        if (pass == 0) {
+            int p2 = 1;
+            while (p2 < n_st) p2 <<= 1;
+            score_sample_threshold_kernel<<<(unsigned)n_heads, 256, p2 * sizeof(float), stream>>>(
+                tilemax, n_st, k, head_norms, tail_max_norm, dim, thr);
+            LKG_LAUNCH_CHECK("score_sample_threshold_kernel");
+        }
     }
 
     FinalParams f{};
     f.emb = emb;
     f.ld_emb = ld_emb;
+    f.head_emb = head_emb ? head_emb : emb;
+    f.ld_head_emb = head_emb ? ld_head_emb : ld_emb;
     f.head_rows = head_rows;
     f.tail_rows = tail_rows;
     f.n_heads = (int)n_heads;

@@ -38,8 +38,11 @@ class GateMul(nn.Module):
         self.gate_bias = nn.Parameter(torch.zeros(emb_size))
 
     def packed(self):
-        return _pair(self.g.weight, (self.gate_ent.weight, self.gate_num_lit.weight, self.gate_txt_lit.weight),
-                     self.g.bias, self.gate_bias)
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_packed", None) is None or self._packed[0] != key:      # parameter derived: cached per version
+            self._packed = (key, _pair(self.g.weight, (self.gate_ent.weight, self.gate_num_lit.weight,
+                                                       self.gate_txt_lit.weight), self.g.bias, self.gate_bias))
+        return self._packed[1]
 
     def forward(self, x_ent, x_lit_num, x_lit_txt, out=None, **planes):
         from .autograd import gate_apply
@@ -61,7 +64,11 @@ class Gate(nn.Module):
         self.gate_bias = nn.Parameter(torch.zeros(emb_size))
 
     def packed(self):
-        return _pair(self.g.weight, (self.gate_ent.weight, self.gate_lit.weight), self.g.bias, self.gate_bias)
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_packed", None) is None or self._packed[0] != key:
+            self._packed = (key, _pair(self.g.weight, (self.gate_ent.weight, self.gate_lit.weight), self.g.bias,
+                                       self.gate_bias))
+        return self._packed[1]
 
     def forward(self, x_ent, x_lit, out=None, **planes):
         from .autograd import gate_apply

@@ -27,6 +27,12 @@ from .gate import Gate, GateMul
 from .graph import GraphPlan
 
 
+def _param_key(module: nn.Module):
+    """Identity + in-place version of every parameter: cache key for tensors derived from the parameters only
+    (folded matrices, stacked gate weights).  Optimizer steps and load_state_dict bump the versions."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
 def _L2_loss_mean(x):
     return torch.mean(torch.sum(torch.pow(x, 2), dim=1, keepdim=False) / 2.)
 
@@ -68,6 +74,7 @@ class Aggregator(nn.Module):
             # 'gin' exists in the reference but is outside the accelerated path
             raise NotImplementedError(aggregator_type)
         self._plan_cache: Optional[Tuple[int, int, GraphPlan, torch.Tensor]] = None
+        self._fold_cache = None
 
     def reset_parameters(self):
         stdv = 1. / math.sqrt(self.out_dim)
@@ -79,6 +86,9 @@ class Aggregator(nn.Module):
         (model.py:90-99): P = (1-a) M W_lin^T, Q = a W_h0^T M W_lin^T, c = a b_h0 M W_lin^T + b_lin.
         Formed in float64 from the live parameters, returned in fp32.  Keys: pa, pb, p2 ([d_in, d_out]),
         q1, q2 ([embed_dim, d_out] or None), c1, c2 ([d_out])."""
+        key = (float(lamda), float(alpha), int(l), _param_key(self))
+        if self._fold_cache is not None and self._fold_cache[0] == key:
+            return self._fold_cache[1]
         dd = torch.float64
         t = self.aggregator_type
         d = self.in_dim
@@ -119,6 +129,7 @@ class Aggregator(nn.Module):
             res[k] = None if v is None else v.float().contiguous()
         if res["pa"] is not None and out["pa"] is out["pb"]:
             res["pa"] = res["pb"]                                      # keep identity: "sum" mode of the kernel
+        self._fold_cache = (key, res)       # derived from the parameters only: reused until one of them changes
         return res
 
     def _drop_mask(self, n: int, device) -> Optional[torch.Tensor]:
@@ -129,11 +140,14 @@ class Aggregator(nn.Module):
 
     def run(self, plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, f: Dict[str, Optional[torch.Tensor]],
             r1: Optional[torch.Tensor], r2: Optional[torch.Tensor], x_out: torch.Tensor,
-            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None) -> torch.Tensor:
+            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None, rows=None) -> torch.Tensor:
+        """``rows`` = (begin, end): the head rows this rank owns; r1 / r2 / xn_out / xn_planes then hold those rows
+        only, ``ego`` and ``x_out`` stay indexed by the global row."""
         pa = None if fold_ego else f["pa"]
+        rb, re = (0, ego.shape[0]) if rows is None else rows
         return ops.aggregate(plan, a_values, ego, self.out_dim, pa, f["pb"], f["p2"], r1, r2,
                              self.layer_normalize.weight, self.layer_normalize.bias,
-                             self._drop_mask(ego.shape[0], ego.device), x_out, xn_out, xn_planes)
+                             self._drop_mask(re - rb, ego.device), x_out, xn_out, xn_planes, local_row_base=rb)
 
     def forward(self, ego_embeddings, A_in, all_layers, lamda, alpha, l):
         """Reference signature (model.py:101): ``A_in`` is a sparse COO tensor, ``all_layers[0]`` the gate
@@ -226,6 +240,9 @@ class LiteralKG(nn.Module):
         self._att_key = None
         self._lit_planes = None                           # fp16 hi/lo planes of the (constant) literal tables
         self._unit_rec = None                             # scale record of planes bounded by 1 (normalised rows)
+        self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
+        self._part = None                                 # parallel.RowPartition when the path is row partitioned
+        self.sync_attention = True                        # partitioned update_att: all-reduce the A_in values
         self._lit_key = None
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -263,27 +280,37 @@ class LiteralKG(nn.Module):
         return plan, values
 
     # ---- gate ------------------------------------------------------------------------------------
-    def _literal_planes(self, tables):
-        """The literal tables are constants (plain attributes in the reference): their bf16 hi/lo planes for
+    def _literal_planes(self, tables, rows=None):
+        """The literal tables are constants (plain attributes in the reference): their fp16 hi/lo planes for
         the gate GEMM are built once and reused, like the reference caches the ``.to(device)`` copy."""
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tables)
+        key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tables), rows)
         if self._lit_key != key:
-            src = tables[0] if len(tables) == 1 else torch.cat(tables, dim=1)
+            if rows is not None:
+                tables = [t[rows[0]:rows[1]] for t in tables]
+            src = tables[0] if len(tables) == 1 else torch.cat(list(tables), dim=1)
             self._lit_planes = ops.split_planes(src)
             self._lit_key = key
         return self._lit_planes
+
+    def set_partition(self, part) -> None:
+        """Row-partition the path over the ranks of ``part`` (``parallel.RowPartition``); None = single GPU."""
+        self._part = part
+        self._lit_key = None
 
     def _unit_record(self, dev) -> torch.Tensor:
         if self._unit_rec is None or self._unit_rec.device != dev:
             self._unit_rec = ops.scale_from_bound(1.0, dev)
         return self._unit_rec
 
-    def gate_embeddings(self, out: Optional[torch.Tensor] = None, planes_window=None):
+    def gate_embeddings(self, out: Optional[torch.Tensor] = None, planes_window=None, rows=None):
         """model.py:265-279.  ``planes_window``: optional (Planes, col, k) column window that receives the scaled
-        fp16 hi/lo copy of the result (A operand of the GEMMs that follow)."""
+        fp16 hi/lo copy of the result (A operand of the GEMMs that follow).  ``rows`` = (begin, end): only these
+        entity rows (the gate is row local; used by the row partition)."""
         ent = self.entity_embed.weight
         dev = self._param_device()
+        sl = slice(None) if rows is None else slice(rows[0], rows[1])
         with torch.no_grad():
+            ent_rows = ent.detach()[sl]
             gate_mod, tables = None, ()
             if self.args.use_num_lit and self.args.use_txt_lit:
                 gate_mod = self.emb_mul_lit
@@ -293,59 +320,83 @@ class LiteralKG(nn.Module):
             elif self.args.use_txt_lit:
                 gate_mod, tables = self.emb_txt_lit, (self._literal("text_literals_embed"),)
             if gate_mod is not None:
-                ent_planes = ops.split_planes(ent.detach())
+                ent_planes = ops.split_planes(ent_rows)
                 out_planes = None
                 if planes_window is not None:
                     # |gate output| <= max(1, max|entity|): convex mix of the entity row and a tanh
                     base, col, k = planes_window
                     out_planes = base.view(col, k, rec=ops.scale_from_bound(1.0, dev, other=ent_planes.rec))
-                res = gate_mod(ent, *tables, out=out, out_planes=out_planes, ent_planes=ent_planes,
-                               lit_planes=self._literal_planes(tables))
+                res = gate_mod(ent_rows, *[t[sl] for t in tables], out=out, out_planes=out_planes,
+                               ent_planes=ent_planes, lit_planes=self._literal_planes(tables, rows))
                 return (res, out_planes) if planes_window is not None else res
             if out is not None:
-                out.copy_(ent.detach())
+                out.copy_(ent_rows)
                 if planes_window is not None:
                     base, col, k = planes_window
                     view = base.view(col, k, rec=torch.empty(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=dev))
-                    ops.split_planes(ent.detach(), out=view)
+                    ops.split_planes(ent_rows, out=view)
                     return out, view
                 return out
-        return ent
+        return ent if rows is None else ent[sl]
 
     # ---- full-graph embedding pass -------------------------------------------------------------
-    def gat_embeddings(self):
-        """model.py:298-314."""
+    def gat_embeddings(self, gather: bool = True):
+        """model.py:298-314.  Row partitioned: ``gather=False`` returns this rank's rows only (what the sharded
+        scoring consumes); the default all-gathers the [N, G] result like the reference returns it."""
         with torch.no_grad():
-            return self._gat_embeddings_native()
+            out = self._gat_embeddings_native()
+            part = self._part
+            if part is None or part.world == 1 or not gather:
+                return out
+            full = torch.empty((part.padded, out.shape[1]), dtype=torch.float32, device=out.device)
+            full[part.begin:part.end] = out
+            return part.all_gather_rows(full)[:self.n_entities]
 
     def _gat_embeddings_native(self, keep: Optional[dict] = None) -> torch.Tensor:
         dev = self._param_device()
         plan, a_values = self._current_plan()
         n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
-        cat = torch.empty((n, total), dtype=torch.float32, device=dev)
-        h0 = cat[:, :d]                                   # gate output lives in the concat buffer
+        part = self._part if (self._part is not None and self._part.world > 1) else None
+        rb, re = (0, n) if part is None else (part.begin, part.end)
+        rows = None if part is None else (rb, re)
+        n_own, n_tab = re - rb, (n if part is None else part.padded)
+        plan.set_row_range(rb, re)
+        cat = torch.empty((n_own, total), dtype=torch.float32, device=dev)   # concat buffer, this rank's rows
+        if part is None:
+            h0_tab = h0 = cat[:, :d]                      # gate output lives in the concat buffer
+        else:
+            h0_tab = torch.empty((n_tab, d), dtype=torch.float32, device=dev)   # row index == entity id
+            h0 = h0_tab[rb:re]
         # scaled fp16 hi/lo planes of the concat buffer: A operand of the h0 @ Q and linear_gat tensor-core GEMMs.
         # Two K segments with their own scale records: the gate output and the L2-normalised layer outputs
         # (|x| <= 1); the second window starts on a 16-byte boundary.
         xcol = (d + 7) // 8 * 8
-        cat_planes = _lib.Planes(n, xcol + (total - d), dev)
-        _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d))
+        cat_planes = _lib.Planes(n_own, xcol + (total - d), dev)
+        _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows)
         xn_all = cat_planes.view(xcol, total - d, rec=self._unit_record(dev))
+        if part is not None:
+            part.all_gather_rows(h0_tab)                  # layer 1 gathers arbitrary neighbour rows of h0
+            if self.scale_gat_dim is None:
+                cat[:, :d] = h0
 
         folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
         h0q = None
         offsets: List[int] = []
         if self.use_residual and self.n_layers > 0:
-            qs, cs, off = [], [], 0
-            for k, f in enumerate(folds):
-                q1 = f["q1"] + f["pa"] if k == 0 else f["q1"]      # layer 0: ego == h0, fold ego @ Pa into h0 @ Q
-                offsets.append(off)
-                qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
-                if f["q2"] is not None:
-                    qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
-            h0q = ops.linear([h0_planes], torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs))
+            qkey = tuple(id(f) for f in folds)                     # the fold dicts are cached per parameter version
+            if self._h0q_cache is None or self._h0q_cache[0] != qkey:
+                qs, cs, off = [], [], 0
+                for k, f in enumerate(folds):
+                    q1 = f["q1"] + f["pa"] if k == 0 else f["q1"]  # layer 0: ego == h0, fold ego @ Pa into h0 @ Q
+                    offsets.append(off)
+                    qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
+                    if f["q2"] is not None:
+                        qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
+                self._h0q_cache = (qkey, torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, folds)
+            _, wq, cq, offsets, _ = self._h0q_cache
+            h0q = ops.linear([h0_planes], wq, cq)                  # this rank's rows
 
-        x = h0
+        x = h0_tab
         col = d
         for k, (layer, f) in enumerate(zip(self.aggregator_layers, folds)):
             c = layer.out_dim
@@ -354,11 +405,14 @@ class LiteralKG(nn.Module):
                 r2 = h0q[:, offsets[k] + c:offsets[k] + 2 * c] if f["q2"] is not None else None
             else:
                 r1, r2 = f["c1"], f["c2"]
-            x_out = torch.empty((n, c), dtype=torch.float32, device=dev)
+            x_out = torch.empty((n_tab, c), dtype=torch.float32, device=dev)
             layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
-                      xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec))
+                      xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows)
+            if part is not None and k + 1 < self.n_layers:
+                part.all_gather_rows(x_out)               # the next layer reads every row of this one
             x = x_out
             col += c
+        plan.set_row_range(0, n)
         if keep is not None:
             keep["cat"] = cat
         if self.scale_gat_dim is not None:
@@ -407,8 +461,17 @@ class LiteralKG(nn.Module):
             self._att_plan = GraphPlan(h, t, r, self.n_entities, self.n_relations, relations)
             self._att_key = key
         plan = self._att_plan
+        part = self._part if (self._part is not None and self._part.world > 1) else None
         with torch.no_grad():
-            values = ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach())
+            if part is None:
+                values = ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach())
+            else:   # rows are independent: every rank fills the values of its own head rows
+                plan.set_row_range(part.begin, part.end)
+                values = torch.zeros(max(plan.nnz, 1), dtype=torch.float32, device=dev)[:plan.nnz]
+                ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach(), out=values)
+                plan.set_row_range(0, self.n_entities)
+                if self.sync_attention:       # complete A_in on every rank (state dict); the layers only need own rows
+                    part.all_reduce(values)
         self._agg_plan, self._agg_values = plan, values
         self.A_in.data = plan.sparse(values)
 
@@ -430,13 +493,49 @@ class LiteralKG(nn.Module):
         ``tail_index`` (``ops.ScoreIndex`` of the tails) can be reused across head batches."""
         if all_embed is None:
             all_embed = self.gat_embeddings()
-        fused = (target_tails is None and all_embed.shape[1] <= ops.FUSED_TOPK_MAX_DIM
-                 and (tail_index is not None or len(tail_ids) >= ops.FUSED_TOPK_MIN_TAILS))
+        n_tails = tail_index.m if tail_index is not None else len(tail_ids)
+        fused = target_tails is None and ops.fused_topk_applicable(n_tails, all_embed.shape[1], k)
         if fused:
             vals, pos = ops.score_topk(all_embed, head_ids, tail_ids, k, tail_index=tail_index)
             return vals, pos, None
         scores = ops.score(all_embed, head_ids, tail_ids)
         return ops.topk_rows(scores, k, target_tails)
+
+    def topk_sharded(self, head_ids, k, local_embed, tail_index=None):
+        """Row-partitioned all-entity top-k: every rank scores the heads against the entities it owns
+        (``local_embed`` = ``gat_embeddings(gather=False)``) and the per-rank survivors are merged.  Returns
+        (values, entity ids) [B, k], identical on every rank."""
+        part = self._part
+        assert part is not None, "topk_sharded needs set_partition()"
+        dev = local_embed.device
+        head_ids = head_ids.to(device=dev, dtype=torch.int64)
+        # head rows from their owners: a zero-padded [B, G] block summed over the ranks (x + 0 is exact)
+        mine = (head_ids >= part.begin) & (head_ids < part.end)
+        hmat = torch.zeros((head_ids.numel(), local_embed.shape[1]), dtype=torch.float32, device=dev)
+        hmat[mine] = local_embed[head_ids[mine] - part.begin]
+        part.all_reduce(hmat)
+        if tail_index is None:
+            tail_index = self.sharded_index(local_embed)
+        if ops.fused_topk_applicable(tail_index.m, local_embed.shape[1], k):
+            vals, pos = ops.score_topk(local_embed, None, None, k, tail_index=tail_index, head_emb=hmat)
+        else:
+            both = torch.cat([local_embed, hmat])
+            scores = ops.score(both, torch.arange(hmat.shape[0], device=dev) + local_embed.shape[0],
+                               torch.arange(local_embed.shape[0], device=dev), rec=tail_index.rec)
+            vals, pos, _ = ops.topk_rows(scores, k)
+        ids = torch.where(pos >= 0, pos + part.begin, pos)
+        from .parallel import merge_topk
+        return merge_topk(part.all_gather_stack(vals), part.all_gather_stack(ids), k,
+                          lambda sc, kk: ops.topk_rows(sc, kk)[:2])
+
+    def sharded_index(self, local_embed):
+        """Tail index of this rank's rows with a scale record that bounds EVERY rank's embeddings (the head rows
+        come from other ranks): the absmax is all-reduced before the power-of-two scale is derived."""
+        part = self._part
+        rec = ops.scale_from_data(local_embed)
+        part.all_reduce(rec[0:1], op=torch.distributed.ReduceOp.MAX)
+        rec = ops.scale_from_bound(0.0, local_embed.device, other=rec)
+        return ops.ScoreIndex(local_embed, None, rec=rec)
 
     def get_final_embeddings(self, entity_ids):
         """model.py:493-497."""

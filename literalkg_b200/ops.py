@@ -178,8 +178,10 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
               pa: Optional[torch.Tensor], pb: torch.Tensor, p2: Optional[torch.Tensor],
               r1: Optional[torch.Tensor], r2: Optional[torch.Tensor],
               ln_weight: torch.Tensor, ln_bias: torch.Tensor, drop_mask: Optional[torch.Tensor],
-              x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None) -> torch.Tensor:
-    """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases."""
+              x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None, local_row_base: int = 0
+              ) -> torch.Tensor:
+    """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases.
+    With a row partition, r1 / r2 / drop_mask / xn_out / xn_planes hold the rows from ``local_row_base`` on."""
     assert ego.dtype == torch.float32 and ego.stride(1) == 1
     d_in = ego.shape[1]
     ld_r = 0
@@ -199,7 +201,7 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
             _lib.ptr(pa_c), pb_c.data_ptr(), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
             _lib.f32c(ln_weight).data_ptr(), _lib.f32c(ln_bias).data_ptr(), _lib.ptr(drop_mask),
             x_out.data_ptr(), x_out.stride(0), _lib.ptr(xn_out), 0 if xn_out is None else xn_out.stride(0),
-            *_planes_out(xn_planes), plan.scratch(), _lib.stream()))
+            *_planes_out(xn_planes), int(local_row_base), plan.scratch(), _lib.stream()))
     return x_out
 
 
@@ -257,7 +259,7 @@ def topk_rows(scores: torch.Tensor, k: int, target_cols: Optional[torch.Tensor] 
 # ---- fused all-entity scoring + top-k ---------------------------------------------------------------------
 FUSED_TOPK_MIN_TAILS = 16384      # below this the score matrix is small: score() + topk_rows()
 FUSED_TOPK_MAX_DIM = 256
-FUSED_TOPK_CAP = 8192             # candidate slots per head
+FUSED_TOPK_CAP = 4096             # candidate slots per head (a head that overflows is re-scanned exactly)
 
 
 class ScoreIndex:
@@ -280,16 +282,28 @@ class ScoreIndex:
                                                    self.norms.data_ptr(), self.max_norm.data_ptr(), _lib.stream()))
 
 
+def fused_topk_applicable(n_tails: int, dim: int, k: int) -> bool:
+    """The fused path needs enough 128-tail tiles to bound the k-th best score from tile maxima."""
+    return (dim <= FUSED_TOPK_MAX_DIM and dim % 4 == 0 and n_tails >= max(FUSED_TOPK_MIN_TAILS, 512 * k)
+            and k <= 1024)
+
+
 def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Tensor], k: int,
-               tail_index: Optional[ScoreIndex] = None, cap: int = FUSED_TOPK_CAP, sample: Optional[int] = None
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+               tail_index: Optional[ScoreIndex] = None, cap: int = FUSED_TOPK_CAP,
+               sample_tiles: Optional[int] = None, theta: Optional[torch.Tensor] = None,
+               head_emb: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per head the k best of ``tails`` (None = every row of emb) without materialising the score matrix.
-    Returns (values [B, k] fp32, positions [B, k] int64 into the tail list)."""
+    Returns (values [B, k] fp32, positions [B, k] int64 into the tail list).  ``theta`` (optional, [B] fp32): a known
+    lower bound of every head's k-th best exact score; by default the kernels derive one from a strided sample.
+    ``head_emb``: matrix the ``heads`` rows index (default ``emb``); its values must be bounded by the tail index's
+    scale record (row partition: the record is built from the all-reduced absmax)."""
     assert emb.dtype == torch.float32 and emb.stride(1) == 1 and emb.shape[1] <= FUSED_TOPK_MAX_DIM
     if tail_index is None:
         tail_index = ScoreIndex(emb, tails)
     ti = tail_index
-    hi = ScoreIndex(emb, heads, rec=ti.rec)
+    hsrc = emb if head_emb is None else head_emb
+    assert hsrc.dtype == torch.float32 and hsrc.stride(1) == 1 and hsrc.shape[1] == emb.shape[1]
+    hi = ScoreIndex(hsrc, heads, rec=ti.rec)          # heads=None: every row of head_emb
     nh, nt = hi.m, ti.m
     vals = torch.empty((nh, k), dtype=torch.float32, device=emb.device)
     pos = torch.empty((nh, k), dtype=torch.int64, device=emb.device)
@@ -297,21 +311,20 @@ def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Ten
         return vals, pos
     while cap < 2 * k:
         cap *= 2
-    # threshold: exact k-th best score of every head over an evenly strided sample of the tails
-    m_s = int(min(nt, sample if sample is not None else max(4096, k * nt // 512)))
-    theta_ptr, theta_stride = None, 0
-    if m_s >= k:
-        spos = (torch.arange(m_s, device=emb.device, dtype=torch.int64) * nt) // m_s
-        srows = spos if ti.rows is None else ti.rows[spos]
-        sv, _, _ = topk_rows(score(emb, hi.rows, srows, rec=ti.rec), k)
-        theta_ptr, theta_stride = sv.data_ptr() + 4 * (k - 1), k
+    n_tiles = (nt + 127) // 128
+    if sample_tiles is None:       # expected candidates per head ~ k * n_tiles / sample_tiles ~ 500
+        sample_tiles = min(n_tiles, 4096, max(2 * k, 64, k * n_tiles // 500))
+    if theta is not None:
+        theta = _lib.f32c(theta)
+        sample_tiles = 0
     nbytes = C.c_size_t(0)
-    _lib.check(_lib.load().lkg_score_topk_workspace_bytes(nh, cap, C.byref(nbytes)))
+    _lib.check(_lib.load().lkg_score_topk_workspace_bytes(nh, cap, sample_tiles, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=emb.device)
-    with _dev_guard(emb, "score_topk", 4):
+    with _dev_guard(emb, "score_topk", 5):
         _lib.check(_lib.load().lkg_score_topk(hi.hi.data_ptr(), hi.ld, hi.norms.data_ptr(), nh, ti.hi.data_ptr(), ti.ld,
-                                              ti.max_norm.data_ptr(), nt, emb.shape[1], ti.rec.data_ptr(), theta_ptr,
-                                              theta_stride, emb.data_ptr(), emb.stride(0), _lib.ptr(hi.rows),
-                                              _lib.ptr(ti.rows), k, cap, vals.data_ptr(), pos.data_ptr(), ws.data_ptr(),
-                                              _lib.stream()))
+                                              ti.max_norm.data_ptr(), nt, emb.shape[1], ti.rec.data_ptr(),
+                                              _lib.ptr(theta), 1, sample_tiles, emb.data_ptr(), emb.stride(0),
+                                              hsrc.data_ptr(), hsrc.stride(0),
+                                              _lib.ptr(hi.rows), _lib.ptr(ti.rows), k, cap, vals.data_ptr(),
+                                              pos.data_ptr(), ws.data_ptr(), _lib.stream()))
     return vals, pos

@@ -1,0 +1,99 @@
+"""Row partition of the path over the GPUs of one box: one process per GPU, NCCL over NVLink.
+
+The reference has no working multi-GPU code (a dead ``nn.DataParallel``, main.py:82-84); this is the B200
+analogue of the scaling axis it lacks.  Head rows are split into equal contiguous ranges; every rank keeps the
+full CSR plan (0.4 GB at 20 M triples) and the raw parameter tables, and owns its rows of every activation:
+
+    update_att       rows independent, no collective (optional all-reduce to complete the ``A_in`` values)
+    gate, h0 @ Q     row local
+    layer k          reads the whole ego table -> one all-gather of the (N/P x d_k) row blocks per layer, written in
+                     place into a [P * chunk, d_k] buffer whose row index is the global entity id
+    linear_gat       row local; the final embeddings stay sharded -- each rank scores its own candidate tails
+    scoring / top-k  head rows are summed from their owners (all-reduce of a zero-padded [B, G] block), local fused
+                     top-k over the local tails, all-gather of the P x [B, k] survivors, k-way merge on every rank
+
+The collectives go through ``torch.distributed`` (NCCL on the GPU box).  With the ``gloo`` backend (CPU tests, or two
+processes sharing one GPU in the test-suite) CUDA tensors are staged through host memory.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class RowPartition:
+    """Rank p owns head rows [p * chunk, min(N, (p + 1) * chunk)), chunk = ceil(N / world)."""
+
+    def __init__(self, n_entities: int, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        self.n = int(n_entities)
+        self.chunk = (self.n + self.world - 1) // self.world
+        self.begin = min(self.n, self.rank * self.chunk)
+        self.end = min(self.n, self.begin + self.chunk)
+        self.padded = self.chunk * self.world          # rows of an all-gather buffer (row index == entity id)
+
+    @property
+    def n_own(self) -> int:
+        return self.end - self.begin
+
+    def owner_of(self, rows: torch.Tensor) -> torch.Tensor:
+        return torch.div(rows, self.chunk, rounding_mode="floor")
+
+    def _backend(self) -> str:
+        return dist.get_backend(self.group) if dist.is_initialized() else "none"
+
+    # ---- collectives -------------------------------------------------------------------------------------
+    def all_gather_rows(self, buf: torch.Tensor) -> torch.Tensor:
+        """``buf`` [padded, d] contiguous with this rank's rows already written: fetches every other rank's
+        row block in place."""
+        assert buf.is_contiguous() and buf.shape[0] == self.padded
+        if self.world == 1:
+            return buf
+        own = buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+        if buf.is_cuda and self._backend() != "nccl":          # gloo has no CUDA all-gather: stage through the host
+            full = torch.empty(buf.numel(), dtype=buf.dtype)
+            dist.all_gather_into_tensor(full, own.cpu().reshape(-1), group=self.group)
+            buf.copy_(full.view(buf.shape))
+        else:
+            dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=self.group)
+        return buf
+
+    def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        if self.world == 1:
+            return t
+        if t.is_cuda and self._backend() != "nccl":
+            c = t.cpu()
+            dist.all_reduce(c, op=op, group=self.group)
+            t.copy_(c)
+        else:
+            dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+    def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
+        """[...] on every rank -> [world, ...]."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        staged = t.is_cuda and self._backend() != "nccl"
+        src = t.cpu() if staged else t
+        out = torch.empty(self.world * src.numel(), dtype=src.dtype, device=src.device)
+        dist.all_gather_into_tensor(out, src.reshape(-1), group=self.group)     # flat: accepted by every backend
+        return out.view(self.world, *t.shape).to(t.device)
+
+
+def merge_topk(vals: torch.Tensor, ids: torch.Tensor, k: int, topk_fn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k-way merge of per-rank results.  ``vals`` / ``ids`` [world, B, k] (ids = global tail positions, -1 pads with
+    value -inf).  Ranks own ascending, disjoint position ranges and each list is ordered (score desc, position asc),
+    so "ties -> lower column" on the rank-major concatenation equals "ties -> lower global position".
+    ``topk_fn(scores [B, world * k], k) -> (values, columns)`` is the row-wise top-k (``ops.topk_rows`` on the GPU)."""
+    world, b, kk = vals.shape
+    flat_v = vals.permute(1, 0, 2).reshape(b, world * kk).contiguous()
+    flat_i = ids.permute(1, 0, 2).reshape(b, world * kk).contiguous()
+    top_v, cols = topk_fn(flat_v, k)
+    top_i = torch.gather(flat_i, 1, cols.clamp_min(0))
+    top_i = torch.where(cols < 0, torch.full_like(top_i, -1), top_i)
+    return top_v, top_i

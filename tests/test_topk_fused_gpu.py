@@ -37,6 +37,20 @@ def test_fused_topk_matches_float64_ranking(n, dim, nh, k):
     assert torch.equal(p2, rp2) and torch.equal(v2, rv2)
 
 
+def test_fused_topk_external_bound_and_sampling_knobs():
+    """A caller-supplied lower bound of the k-th best score (theta) and any sampling density give the same result:
+    the bound only decides how many candidates are re-scored."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, dim, k = 60_000, 128, 7
+    emb = torch.randn(n, dim, generator=g, device="cuda") * 2.0
+    heads = torch.randint(0, n, (70,), generator=g, device="cuda")
+    rv, rp = ref_topk(emb, heads, torch.arange(n, device="cuda"), k)
+    for kw in (dict(sample_tiles=16), dict(sample_tiles=469), dict(theta=rv[:, -1] - 0.5), dict(theta=rv[:, -1].clone())):
+        v, p_ = ops.score_topk(emb, heads, None, k, **kw)
+        assert torch.equal(p_, rp) and torch.equal(v, rv), kw
+
+
 def test_fused_topk_plateau_overflow_and_ties():
     """20 000 identical best tails: the candidate band overflows every head's list; the exact fallback must return
     the lowest positions of the plateau, in order."""
