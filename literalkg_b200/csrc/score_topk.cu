@@ -22,7 +22,11 @@
 //     and hit in L2 by the other head blocks;
 //   * accumulators: 2 buffers x 2 head blocks x 128 TMEM columns (all 512), epilogue of tile i overlaps MMAs of i+1;
 //   * epilogue: 4 warps, thread = head row, tcgen05.ld 32 columns at a time, max-reduce, ONE compare against the
-//     row's threshold (pre-multiplied by the operand scales), rare slow path appends (atomicAdd on the row counter).
+//     row's threshold (pre-multiplied by the operand scales).  Candidates go to a list private to this (head row,
+//     CTA stream): exactly one thread of one CTA writes it, so the counter lives in a register and there is no
+//     atomic.  They are staged in shared memory, 16 per row, and flushed to the global list when the stage fills
+//     up: a global store (let alone an atomicAdd round trip) in front of the releasing mbarrier.arrive that hands
+//     the accumulator back made the epilogue wait for the store to land on most tiles (measured 3.6 ms vs 1.1 ms).
 #include "tc.cuh"
 
 namespace lkg {
@@ -35,6 +39,7 @@ constexpr int kStages = 5;
 constexpr int kThreads = 192;            // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
 constexpr int kMaxChunks = 4;            // K <= 256
 constexpr uint32_t kChunkBytes = kBM * kBK * 2;     // 16 KB: 128 rows x 64 fp16 (A block chunk and B stage alike)
+constexpr int kStageCand = 16;                      // candidates staged in shared memory per (thread, head block)
 constexpr float kErrCoef = 1.15f / 1024.f;          // |s~ - s| <= kErrCoef |h| |t|: two fp16 roundings (2 * 2^-11),
                                                     // fp32 accumulation over K <= 256 (2^-16), theta's own 2^-21
 constexpr int kFinalThreads = 256;
@@ -44,9 +49,9 @@ struct FilterParams {
     CUtensorMap b_map;       // tails hi plane [n_tails, K] fp16
     int n_heads, n_tails, n_chunks, n_pairs, n_tiles;
     const float* thr;        // [n_heads] threshold in accumulator (scaled) units
-    int* cnt;                // [n_heads] candidates seen
-    int* cand;               // [n_heads, cap] candidate columns (positions in the tail list)
-    int cap;
+    int* cnt;                // [n_heads, n_streams] candidates seen by each CTA stream
+    int* cand;               // [n_heads, n_streams, cap_s] candidate columns (positions in the tail list)
+    int cap_s;               // slots per (head, stream) sublist
     // sampling mode (tilemax != NULL): visit tiles 0, tile_stride, 2 tile_stride, ... (n_tiles of them) and store
     // every head's largest approximate score of each visited tile instead of filtering
     float* tilemax;          // [n_heads, n_tiles]
@@ -58,7 +63,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                           // [2 blocks][n_chunks] x 16 KB
     uint8_t* smem_b = smem + 2 * kMaxChunks * kChunkBytes;            // [kStages] x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * kChunkBytes);
+    int* smem_cand = reinterpret_cast<int*>(smem_b + kStages * kChunkBytes);        // [2][kStageCand][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_cand + 2 * kStageCand * 128);
     uint64_t* full = bars;                    // [kStages]
     uint64_t* empty = bars + kStages;         // [kStages]
     uint64_t* acc_full = bars + 2 * kStages;  // [2]
@@ -153,50 +159,64 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
         }
     } else {
         // ===== epilogue warps 0-3: TMEM lane = head row of the block =====
+        // The candidate path is rare per thread but hit by some lane of the warp on most tiles, so it is kept small
+        // (a bit mask + a compact loop, no unrolled copies): a 32-way unrolled version made the kernel 600 KB of
+        // SASS and every entry into it an instruction-cache miss (3.6 ms instead of 1.1 ms).
+        int row[2], seen[2] = {0, 0}, staged[2] = {0, 0};
         float thr[2];
-        int row[2];
+        int* my_cand[2];
+        int* my_stage = smem_cand + threadIdx.x;        // slot i of block b: my_stage[(b * kStageCand + i) * 128]
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             row[b] = row_base + b * kBM + warp * 32 + lane;
             thr[b] = (row[b] < p.n_heads && !p.tilemax) ? __ldg(p.thr + row[b]) : INFINITY;
+            my_cand[b] = p.cand + ((int64_t)row[b] * n_streams + stream) * p.cap_s;
         }
         int it = 0;
         for (int tile = stream; tile < p.n_tiles; tile += n_streams, ++it) {
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
+            const int tile_col0 = tile * p.tile_stride * kBN;
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 if (b >= n_blk) break;
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * kBN + b * kBN;
-                const int tile_col0 = tile * p.tile_stride * kBN;
                 float tmax = -INFINITY;
-#pragma unroll
+#pragma unroll 1
                 for (int c0 = 0; c0 < kBN; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32_nowait(taddr + c0, r);
                     tc_ld_wait();
                     const int col0 = tile_col0 + c0;
-                    if (p.tilemax) {
-                        if (col0 + 32 <= p.n_tails) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(r[j]));
-                        } else {                                         // last, partial tile: TMA zero-filled the rest
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.n_tails) tmax = fmaxf(tmax, __uint_as_float(r[j]));
-                        }
-                        continue;
-                    }
+                    const int valid = p.n_tails - col0;                  // columns of this group inside the tail list
                     float m = __uint_as_float(r[0]);
 #pragma unroll
                     for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-                    if (m >= thr[b]) {                                   // rare: this row has a candidate among the 32
+                    if (p.tilemax) {
+                        if (valid < 32) {                                // last, partial tile: TMA zero-filled the rest
+                            m = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (__uint_as_float(r[j]) >= thr[b] && col0 + j < p.n_tails) {
-                                const int pos = atomicAdd(p.cnt + row[b], 1);
-                                if (pos < p.cap) p.cand[(int64_t)row[b] * p.cap + pos] = col0 + j;
+                            for (int j = 0; j < 32; ++j)
+                                if (j < valid) m = fmaxf(m, __uint_as_float(r[j]));
+                        }
+                        tmax = fmaxf(tmax, m);
+                    } else if (m >= thr[b]) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= thr[b] ? 1u : 0u) << j;
+                        if (valid < 32) mask &= valid <= 0 ? 0u : (1u << valid) - 1u;
+#pragma unroll 1
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            my_stage[(b * kStageCand + staged[b]) * 128] = col0 + j;
+                            if (++staged[b] == kStageCand) {             // stage full: flush to the global list
+#pragma unroll 1
+                                for (int i = 0; i < kStageCand; ++i)
+                                    if (seen[b] + i < p.cap_s) my_cand[b][seen[b] + i] = my_stage[(b * kStageCand + i) * 128];
+                                seen[b] += kStageCand;
+                                staged[b] = 0;
                             }
                         }
                     }
@@ -205,6 +225,16 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
+        }
+        if (!p.tilemax) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll 1
+                for (int i = 0; i < staged[b]; ++i)
+                    if (seen[b] + i < p.cap_s) my_cand[b][seen[b] + i] = my_stage[(b * kStageCand + i) * 128];
+                seen[b] += staged[b];
+                if (row[b] < p.n_heads) p.cnt[(int64_t)row[b] * n_streams + stream] = seen[b];
+            }
         }
     }
 
@@ -216,7 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_filter_kernel(const __grid_
     }
 }
 
-constexpr uint32_t kFilterSmem = (2 * kMaxChunks + kStages) * kChunkBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kFilterSmem = (2 * kMaxChunks + kStages) * kChunkBytes + 2 * kStageCand * 128 * 4 /*candidates*/ +
+                                 1024 /*align*/ + 256 /*barriers*/;
+static_assert(kFilterSmem <= 227 * 1024, "filter kernel shared memory");
 
 int make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
@@ -389,9 +421,11 @@ struct FinalParams {
     int64_t ld_emb;
     const float* head_emb;      // heads' matrix (may be the same)
     int64_t ld_head_emb;
-    const int64_t* head_rows;   // nullable: head i = row i
+    const int64_t* head_rows;   // nullable: head i = row head_row_base + i
+    int64_t head_row_base;
     const int64_t* tail_rows;   // nullable: tail j = row j
     int n_heads, n_tails, dim, k, cap;
+    int n_streams, cap_s;       // candidate sublists per head and their capacity (n_streams * cap_s <= cap)
     const int* cnt;
     const int* cand;
     float* top_val;
@@ -408,19 +442,43 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
     const int grp = lane >> 3, q = lane & 7;                    // 4 candidates per warp, 8 lanes each
     const int kk = min(p.k, p.n_tails);
     __shared__ __align__(16) float s_head[kMaxChunks * kBK];
-    const float* hrow = p.head_emb + (p.head_rows ? p.head_rows[head] : head) * p.ld_head_emb;
+    const float* hrow = p.head_emb + (p.head_rows ? p.head_rows[head] : p.head_row_base + head) * p.ld_head_emb;
     for (int i = threadIdx.x; i < kMaxChunks * kBK; i += blockDim.x) s_head[i] = i < p.dim ? __ldg(hrow + i) : 0.f;
     if (threadIdx.x == 0) s_kept = 0;
+    // gather the head's sublists (one per CTA stream of the filter kernel) into one column list
+    int* cols = reinterpret_cast<int*>(keys + p.cap);
+    __shared__ int s_off[161], s_n, s_over;
+    for (int sidx = threadIdx.x; sidx < p.n_streams; sidx += blockDim.x)
+        s_off[sidx] = p.cnt[(int64_t)head * p.n_streams + sidx];
     __syncthreads();
-    const int seen = p.cnt[head];
+    if (threadIdx.x == 0) {
+        int tot = 0, over = 0;
+        for (int sidx = 0; sidx < p.n_streams; ++sidx) {
+            const int c = s_off[sidx];
+            over |= c > p.cap_s;
+            s_off[sidx] = tot;
+            tot += min(c, p.cap_s);
+        }
+        s_off[p.n_streams] = tot;
+        s_n = tot;
+        s_over = over;
+    }
+    __syncthreads();
+    const bool overflow = s_over != 0;
     int n = 0;
     auto tail_row = [&](int col) { return p.emb + (p.tail_rows ? p.tail_rows[col] : col) * p.ld_emb; };
-    if (seen <= p.cap) {
-        n = seen;
+    if (!overflow) {
+        n = s_n;
+        for (int sidx = warp; sidx < p.n_streams; sidx += nwarps) {
+            const int o = s_off[sidx], c = s_off[sidx + 1] - o;
+            const int* src = p.cand + ((int64_t)head * p.n_streams + sidx) * p.cap_s;
+            for (int i = lane; i < c; i += 32) cols[o + i] = src[i];
+        }
+        __syncthreads();
         for (int c0 = 4 * warp; c0 < n; c0 += 4 * nwarps) {
             const int c = c0 + grp;
             const bool live = c < n;
-            const int col = live ? p.cand[(int64_t)head * p.cap + c] : 0;
+            const int col = live ? cols[c] : 0;
             const float s = exact_dot8(s_head, tail_row(col), p.dim, q, live);
             if (live && q == 0) keys[c] = ((unsigned long long)enc(s) << 32) | (uint32_t)(~(uint32_t)col);
         }
@@ -452,7 +510,7 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
         n = s_kept;
     }
     __syncthreads();
-    if (seen <= p.cap) {
+    if (!overflow) {
         int p2 = 1;
         while (p2 < n) p2 <<= 1;
         for (int i = n + threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
@@ -492,7 +550,8 @@ extern "C" int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows
 extern "C" int lkg_score_topk_workspace_bytes(int64_t n_heads, int32_t cap, int32_t sample_tiles, size_t* bytes) {
     LKG_REQUIRE(bytes && n_heads >= 0 && cap >= 2 && (cap & (cap - 1)) == 0, "cap must be a power of two");
     LKG_REQUIRE(sample_tiles >= 0 && sample_tiles <= 4096, "sample_tiles must be in [0, 4096]");
-    *bytes = align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4) +
+    // counters [n_heads, <= 160 streams], thresholds, candidate sublists (n_streams * cap_s <= cap), tile maxima
+    *bytes = align_up((size_t)n_heads * 160 * 4) + align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4) +
              align_up((size_t)n_heads * sample_tiles * 4);
     return LKG_OK;
 }
@@ -517,10 +576,10 @@ extern "C" int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, con
                 "null argument");
     char* ws = static_cast<char*>(workspace);
     int* cnt = reinterpret_cast<int*>(ws);
-    float* thr = reinterpret_cast<float*>(ws + align_up((size_t)n_heads * 4));
-    int* cand = reinterpret_cast<int*>(ws + 2 * align_up((size_t)n_heads * 4));
-    float* tilemax = reinterpret_cast<float*>(ws + 2 * align_up((size_t)n_heads * 4) + align_up((size_t)n_heads * cap * 4));
-    LKG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_heads * 4, stream));
+    float* thr = reinterpret_cast<float*>(ws + align_up((size_t)n_heads * 160 * 4));
+    int* cand = reinterpret_cast<int*>(ws + align_up((size_t)n_heads * 160 * 4) + align_up((size_t)n_heads * 4));
+    float* tilemax = reinterpret_cast<float*>(ws + align_up((size_t)n_heads * 160 * 4) + align_up((size_t)n_heads * 4) +
+                                              align_up((size_t)n_heads * cap * 4));
     if (theta || sample_tiles <= 0) {
         score_threshold_kernel<<<(int)((n_heads + 255) / 256), 256, 0, stream>>>(theta, theta_stride, (int)n_heads,
                                                                                 head_norms, tail_max_norm, rec, dim, thr);
@@ -535,61 +594,65 @@ extern "C" int lkg_score_topk(const uint16_t* heads_hi, int64_t ld_heads_hi, con
         if (n_st > sample_tiles) n_st = sample_tiles;
     }
 
-    const int sms = sm_count();
+    const int sms = sm_count() < 160 ? sm_count() : 160;
     const int max_pairs = sms;                      // heads per launch <= 256 * SMs
     auto kern = score_filter_kernel;
     LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmem));
-    // pass 0 (optional): tile maxima over the sampled tiles -> thresholds; pass 1: filter over all tiles
-    for (int pass = (n_st > 0 ? 0 : 1); pass < 2; ++pass) {
-        for (int64_t h0 = 0; h0 < n_heads; h0 += (int64_t)max_pairs * 2 * kBM) {
-            const int nh = (int)((n_heads - h0) < (int64_t)max_pairs * 2 * kBM ? (n_heads - h0) : (int64_t)max_pairs * 2 * kBM);
-            FilterParams p{};
-            if (int rc = make_map_2d(&p.a_map, heads_hi + h0 * ld_heads_hi, nh, dim, ld_heads_hi)) return rc;
-            if (int rc = make_map_2d(&p.b_map, tails_hi, n_tails, dim, ld_tails_hi)) return rc;
-            p.n_heads = nh;
-            p.n_tails = (int)n_tails;
-            p.n_chunks = (dim + kBK - 1) / kBK;
-            p.n_pairs = (nh + 2 * kBM - 1) / (2 * kBM);
+    const size_t fsmem = (size_t)cap * (sizeof(unsigned long long) + sizeof(int));
+    LKG_CUDA(cudaFuncSetAttribute(score_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    for (int64_t h0 = 0; h0 < n_heads; h0 += (int64_t)max_pairs * 2 * kBM) {
+        const int nh = (int)((n_heads - h0) < (int64_t)max_pairs * 2 * kBM ? (n_heads - h0) : (int64_t)max_pairs * 2 * kBM);
+        FilterParams p{};
+        if (int rc = make_map_2d(&p.a_map, heads_hi + h0 * ld_heads_hi, nh, dim, ld_heads_hi)) return rc;
+        if (int rc = make_map_2d(&p.b_map, tails_hi, n_tails, dim, ld_tails_hi)) return rc;
+        p.n_heads = nh;
+        p.n_tails = (int)n_tails;
+        p.n_chunks = (dim + kBK - 1) / kBK;
+        p.n_pairs = (nh + 2 * kBM - 1) / (2 * kBM);
+        p.thr = thr + h0;
+        // pass 0 (optional): tile maxima over the sampled tiles -> thresholds; pass 1: filter over all tiles
+        int streams = 1;
+        for (int pass = (n_st > 0 ? 0 : 1); pass < 2; ++pass) {
             p.n_tiles = pass == 0 ? n_st : n_tiles_all;
             p.tile_stride = pass == 0 ? st_stride : 1;
             p.tilemax = pass == 0 ? tilemax + h0 * n_st : nullptr;
-            p.thr = thr + h0;
-            p.cnt = cnt + h0;
-            p.cand = cand + h0 * cap;
-            p.cap = cap;
-            int streams = sms / p.n_pairs;
+            streams = sms / p.n_pairs;
             if (streams > p.n_tiles) streams = p.n_tiles;
+            p.cnt = cnt + h0 * 160;
+            p.cand = cand + h0 * cap;
+            p.cap_s = cap / streams;
             kern<<<p.n_pairs * streams, kThreads, kFilterSmem, stream>>>(p);
             LKG_LAUNCH_CHECK("score_filter_kernel");
+            if (pass == 0) {
+                int p2 = 1;
+                while (p2 < n_st) p2 <<= 1;
+                score_sample_threshold_kernel<<<(unsigned)nh, 256, p2 * sizeof(float), stream>>>(
+                    p.tilemax, n_st, k, head_norms + h0, tail_max_norm, dim, thr + h0);
+                LKG_LAUNCH_CHECK("score_sample_threshold_kernel");
+            }
         }
-        if (pass == 0) {
-            int p2 = 1;
-            while (p2 < n_st) p2 <<= 1;
-            score_sample_threshold_kernel<<<(unsigned)n_heads, 256, p2 * sizeof(float), stream>>>(
-                tilemax, n_st, k, head_norms, tail_max_norm, dim, thr);
-            LKG_LAUNCH_CHECK("score_sample_threshold_kernel");
-        }
-    }
 
-    FinalParams f{};
-    f.emb = emb;
-    f.ld_emb = ld_emb;
-    f.head_emb = head_emb ? head_emb : emb;
-    f.ld_head_emb = head_emb ? ld_head_emb : ld_emb;
-    f.head_rows = head_rows;
-    f.tail_rows = tail_rows;
-    f.n_heads = (int)n_heads;
-    f.n_tails = (int)n_tails;
-    f.dim = dim;
-    f.k = k;
-    f.cap = cap;
-    f.cnt = cnt;
-    f.cand = cand;
-    f.top_val = top_values;
-    f.top_col = top_cols;
-    const size_t fsmem = (size_t)cap * sizeof(unsigned long long);
-    LKG_CUDA(cudaFuncSetAttribute(score_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    score_finalize_kernel<<<(unsigned)n_heads, kFinalThreads, fsmem, stream>>>(f);
-    LKG_LAUNCH_CHECK("score_finalize_kernel");
+        FinalParams f{};
+        f.emb = emb;
+        f.ld_emb = ld_emb;
+        f.head_emb = head_emb ? head_emb : emb;
+        f.ld_head_emb = head_emb ? ld_head_emb : ld_emb;
+        f.head_rows = head_rows ? head_rows + h0 : nullptr;
+        f.head_row_base = head_rows ? 0 : h0;
+        f.tail_rows = tail_rows;
+        f.n_heads = nh;
+        f.n_tails = (int)n_tails;
+        f.dim = dim;
+        f.k = k;
+        f.cap = cap;
+        f.n_streams = streams;
+        f.cap_s = cap / streams;
+        f.cnt = cnt + h0 * 160;
+        f.cand = cand + h0 * cap;
+        f.top_val = top_values + h0 * k;
+        f.top_col = top_cols + h0 * k;
+        score_finalize_kernel<<<(unsigned)nh, kFinalThreads, fsmem, stream>>>(f);
+        LKG_LAUNCH_CHECK("score_finalize_kernel");
+    }
     return LKG_OK;
 }

@@ -289,9 +289,10 @@ def fused_topk_applicable(n_tails: int, dim: int, k: int) -> bool:
 
 
 def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Tensor], k: int,
-               tail_index: Optional[ScoreIndex] = None, cap: int = FUSED_TOPK_CAP,
+               tail_index: Optional[ScoreIndex] = None, cap: Optional[int] = None,
                sample_tiles: Optional[int] = None, theta: Optional[torch.Tensor] = None,
-               head_emb: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+               head_emb: Optional[torch.Tensor] = None, stats: Optional[dict] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per head the k best of ``tails`` (None = every row of emb) without materialising the score matrix.
     Returns (values [B, k] fp32, positions [B, k] int64 into the tail list).  ``theta`` (optional, [B] fp32): a known
     lower bound of every head's k-th best exact score; by default the kernels derive one from a strided sample.
@@ -309,11 +310,13 @@ def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Ten
     pos = torch.empty((nh, k), dtype=torch.int64, device=emb.device)
     if nh == 0:
         return vals, pos
+    if cap is None:
+        cap = FUSED_TOPK_CAP if k < 64 else 2 * FUSED_TOPK_CAP
     while cap < 2 * k:
         cap *= 2
     n_tiles = (nt + 127) // 128
-    if sample_tiles is None:       # expected candidates per head ~ k * n_tiles / sample_tiles ~ 500
-        sample_tiles = min(n_tiles, 4096, max(2 * k, 64, k * n_tiles // 500))
+    if sample_tiles is None:       # expected candidates per head ~ k * n_tiles / sample_tiles ~ max(250, 10 k)
+        sample_tiles = min(n_tiles, 4096, max(2 * k, 64, k * n_tiles // max(250, 10 * k)))
     if theta is not None:
         theta = _lib.f32c(theta)
         sample_tiles = 0
@@ -327,4 +330,8 @@ def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Ten
                                               hsrc.data_ptr(), hsrc.stride(0),
                                               _lib.ptr(hi.rows), _lib.ptr(ti.rows), k, cap, vals.data_ptr(),
                                               pos.data_ptr(), ws.data_ptr(), _lib.stream()))
+    if stats is not None and nh <= 256 * 148:   # diagnostics: candidates per head (counters [nh, streams] lead the ws)
+        streams = min(148 // ((nh + 255) // 256), n_tiles)
+        stats["candidates"] = ws[:4 * nh * streams].view(torch.int32).view(nh, streams).sum(1)
+        stats["cap"], stats["cap_per_stream"], stats["sample_tiles"] = cap, cap // streams, sample_tiles
     return vals, pos
