@@ -360,6 +360,19 @@ def run_ours(a):
 
 def main():
     a = parse()
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write to fd 1 too, so the
+    # process-level stdout is pointed at stderr for the whole run and the line goes to a private copy of the real one.
+    global print
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    builtin_print = print
+
+    def print(*args, **kw):            # noqa: A001 -- the two run_* functions print exactly one line each
+        kw["file"] = real_stdout
+        builtin_print(*args, **kw)
+        real_stdout.flush()
+
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -55,12 +55,15 @@ typedef struct {
     const int32_t* att_rowptr;  /* [N+1] */
     const int32_t* att_tail;    /* [E]   */
     const int32_t* att_rel;     /* [E]   */
-    const int32_t* att_seg;     /* [E]   index into the agg arrays                          */
+    const int32_t* att_seg;     /* [E]   bits 0-30: index into the agg arrays; bit 31: the pair has several triples */
     const int32_t* rowptr;      /* [N+1] */
     const int32_t* col;         /* [nnz] */
     const int32_t* row_order;   /* [row_end - row_begin] the rows of the partition, most triples first: the
                                    kernels take rows in this order so that the heaviest rows of a power-law
                                    graph start first (nullable: natural order) */
+    const int32_t* row_sched;   /* [row_end - row_begin][8] the same order as 32-byte records {row, att_rowptr[row],
+                                   att_rowptr[row+1], rowptr[row], rowptr[row+1], 0, 0, 0} (required by
+                                   lkg_attn_update; 16-byte aligned) */
 } lkg_graph;
 
 /* fp16 "planes" operand of the tensor-core GEMMs.  A value x is stored as hi = fp16(s*x) and
@@ -98,7 +101,7 @@ int lkg_device_check(int device);
  *      model.py:462-470) ------------------------------------------------------------------------ */
 int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, size_t* bytes /*host out*/);
 /* h,t,r: int64 [n_edges] in file order.  row_order (nullable) int32 [n_entities]: all rows by decreasing
- * triple count (stable).  rel_keep: optional uint8 [n_relations]; triples whose
+ * triple count (stable); row_sched (nullable) int32 [n_entities][8]: the schedule records of lkg_graph.  rel_keep: optional uint8 [n_relations]; triples whose
  * relation has rel_keep == 0 are dropped (a `relations` list that omits ids, model.py:451).
  * Outputs are caller-allocated: att_* and col sized for n_edges, rowptrs for n_entities+1,
  * coo_rows/coo_cols (nullable) int64 [n_edges] receive the coalesced COO indices, file_seg
@@ -107,7 +110,8 @@ int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, size_t* bytes 
 int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
                    int64_t n_entities, int32_t n_relations, const uint8_t* rel_keep,
                    int32_t* att_rowptr, int32_t* att_tail, int32_t* att_rel, int32_t* att_seg,
-                   int32_t* rowptr, int32_t* col, int32_t* row_order, int64_t* coo_rows, int64_t* coo_cols,
+                   int32_t* rowptr, int32_t* col, int32_t* row_order, int32_t* row_sched, int64_t* coo_rows,
+                   int64_t* coo_cols,
                    int32_t* file_seg, int64_t* counts_dev, void* workspace, size_t workspace_bytes,
                    void* stream);
 /* values_out[file_seg[i]] += values_in[i]: imports an un-coalesced COO value list (e.g. an A_in taken

@@ -22,7 +22,7 @@ i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 class LkgGraph(C.Structure):
     _fields_ = [("n_entities", i64), ("n_edges", i64), ("nnz", i64), ("n_relations", i32),
                 ("row_begin", i64), ("row_end", i64), ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
-                ("rowptr", vp), ("col", vp), ("row_order", vp)]
+                ("rowptr", vp), ("col", vp), ("row_order", vp), ("row_sched", vp)]
 
 
 class LkgPlanes(C.Structure):
@@ -37,7 +37,7 @@ SIGNATURES = {
     "lkg_last_error": (C.c_char_p, []),
     "lkg_device_check": (C.c_int, [C.c_int]),
     "lkg_plan_workspace_bytes": (C.c_int, [i64, i64, C.POINTER(C.c_size_t)]),
-    "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+    "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  C.c_size_t, vp]),
     "lkg_segment_scatter_add": (C.c_int, [vp, vp, i64, vp, i64, vp]),
     "lkg_edge_fingerprint": (C.c_int, [vp, vp, vp, i64, vp, vp]),

@@ -12,7 +12,11 @@
 //     ~25-instruction tanh -- with R = 64 uniform relations almost every triple starts a new run and
 //     the old per-run tanh made the kernel issue bound (ncu: 52 % issue slots at 22 % occupancy);
 //   * triples are visited in (h, r, t) order, so the weight vector is still shared by a whole run;
-//   * each tail row e_t is fetched exactly once with 128-bit streaming loads, kUnroll tails in flight;
+//   * each tail row e_t is fetched exactly once: a row's (tail, relation, pair) indices are loaded 32 at a time in one
+//     coalesced step and the 1 200-byte tail rows stream through a per-warp shared-memory ring filled by
+//     cp.async.bulk (one TMA-unit copy per row, completion on an mbarrier), kRing rows in flight per warp without
+//     holding registers -- the register-staged version kept 4 rows in flight behind a dependent index -> gather
+//     chain and sat at 71 % of the HBM peak with long_scoreboard as the top stall;
 //   * the logit is accumulated into its (h,t) pair slot (att_seg), which sums duplicates -- in shared
 //     memory for rows of up to kSegCap pairs, in the output array itself for longer rows;
 //   * the softmax over the row's pair slots runs in the same warp;
@@ -20,12 +24,13 @@
 //     power-law graph start first instead of forming the kernel's tail.
 // Envelope: exact formula for |e| <= 40 (beyond that exp(2e) is clamped; tanh is saturated anyway).
 // HBM bound: algorithmic bytes = E*(4 tail + 4 rel + 4 seg + 4D) + N*(4D + 8 + 4 order) + nnz*4.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lkg {
 namespace {
 
-constexpr int kUnroll = 4;
 constexpr int kWarps = 8;
 constexpr int kSegCap = 128;                     // pair slots per warp kept in shared memory
 constexpr float kTwoLog2e = 2.8853900817779268f; // exp(2x) = exp2(x * 2 log2 e)
@@ -48,26 +53,87 @@ __device__ __forceinline__ float tanh_from_exp(float p) {
     return fmaf(-2.f, r, 1.f);
 }
 
-template <int S>  // S = float4 slots per lane: dim <= 128 * S
-__global__ void __launch_bounds__(kWarps * 32)
+// ---- per-warp ring of gathered rows: one cp.async.bulk (TMA unit, 1-D) per row, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+}
+__device__ __forceinline__ void ring_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// S = float4 slots per lane (dim <= 128 * S); kRing = tail rows in flight per warp (bulk copies into shared memory)
+template <int S, int kRing, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
                    const float* __restrict__ rel_exp /* [R, 4 * nvec] */, int nvec /* dim/4 */,
                    float* __restrict__ val, int* __restrict__ row_counter) {
-    __shared__ float s_logit[kWarps][kSegCap];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int row0 = (int)g.row_begin, n_rows = (int)(g.row_end - g.row_begin);
+    const uint32_t row_bytes = (uint32_t)nvec * 16u;
+    // per warp: kRing row slots, kRing mbarriers, kSegCap logit slots
+    uint8_t* ring = smem_raw + (size_t)warp * kRing * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kRing * row_bytes) + warp * kRing;
+    float* s_logit = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * kRing * row_bytes + kWarps * kRing * 8) +
+                     warp * kSegCap;
+    if (lane < kRing) ring_bar_init(&bars[lane]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int n_rows = (int)(g.row_end - g.row_begin);
+    uint32_t issued = 0, consumed = 0;              // running counts over the kernel: slot = count % kRing,
+                                                    // parity of a slot's use = (count / kRing) & 1
+    // Rows come from a shared counter (dynamic balance: the heaviest rows are first in the schedule).  The counter
+    // fetch and the schedule record of the NEXT row are issued while the current row streams, so a row starts with
+    // everything it needs in registers instead of an atomic -> row_order -> rowptr chain of dependent round trips.
+    const int4* sched = reinterpret_cast<const int4*>(g.row_sched);
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(row_counter, 1);
+    idx = __shfl_sync(kFull, idx, 0);
+    int4 rec = make_int4(0, 0, 0, 0);
+    int rec_u1 = 0;
+    if (idx < n_rows) {
+        rec = __ldg(sched + 2 * idx);
+        rec_u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * idx + 1));
+    }
 
-    for (;;) {
-        int idx = 0;
-        if (lane == 0) idx = atomicAdd(row_counter, 1);
-        idx = __shfl_sync(kFull, idx, 0);
-        if (idx >= n_rows) break;
-        const int row = g.row_order ? __ldg(g.row_order + idx) : row0 + idx;
-        const int e0 = g.att_rowptr[row], e1 = g.att_rowptr[row + 1];
-        if (e0 == e1) continue;
-        const int u0 = g.rowptr[row], nu = g.rowptr[row + 1] - u0;
-        float* logit = nu <= kSegCap ? s_logit[warp] : val + u0;      // slot of pair u: logit[u - u0]
+    while (idx < n_rows) {
+        int next_idx = 0;
+        if (lane == 0) next_idx = atomicAdd(row_counter, 1);          // consumed after the first chunk's prologue
+        const int row = rec.x, e0 = rec.y, e1 = rec.z, u0 = rec.w, nu = rec_u1 - rec.w;
+        bool next_loaded = false;
+        int4 nrec = make_int4(0, 0, 0, 0);
+        int nrec_u1 = 0;
+        auto load_next = [&]() {
+            next_idx = __shfl_sync(kFull, next_idx, 0);
+            if (next_idx < n_rows) {
+                nrec = __ldg(sched + 2 * next_idx);
+                nrec_u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * next_idx + 1));
+            }
+            next_loaded = true;
+        };
+        if (e0 == e1) {
+            load_next();
+            idx = next_idx; rec = nrec; rec_u1 = nrec_u1;
+            continue;
+        }
+        const bool in_smem = nu <= kSegCap;
+        float* logit = in_smem ? s_logit : val + u0;                   // slot of pair u: logit[u - u0]
         for (int i = lane; i < nu; i += 32) logit[i] = 0.f;
 
         float4 eh[S], w[S];
@@ -75,87 +141,115 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int v = lane + 32 * s;
+            // raw e_h for now: exp(2 e_h) is taken after the first chunk's indices and bulk copies are on their way
             eh[s] = v < nvec ? __ldg(reinterpret_cast<const float4*>(hrow) + v) : make_float4(0, 0, 0, 0);
-            eh[s].x = exp2x(eh[s].x);
-            eh[s].y = exp2x(eh[s].y);
-            eh[s].z = exp2x(eh[s].z);
-            eh[s].w = exp2x(eh[s].w);
             w[s] = make_float4(0, 0, 0, 0);
         }
         __syncwarp();   // zeroing of the slots visible before lane 0 accumulates
 
         int cur_rel = -1;
-        for (int e = e0; e < e1; e += kUnroll) {
-            int tl[kUnroll], rl[kUnroll], sg[kUnroll];
-            float4 et[kUnroll][S];
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                const bool live = e + j < e1;
-                tl[j] = live ? __ldg(g.att_tail + e + j) : 0;
-                rl[j] = live ? __ldg(g.att_rel + e + j) : -1;
-                sg[j] = live ? __ldg(g.att_seg + e + j) : 0;
+        // the row's triples in chunks of 32: one coalesced load of (tail, relation, pair) per chunk, then the tail rows
+        // stream through the ring, kRing bulk copies in flight
+        for (int c0 = e0; c0 < e1; c0 += 32) {
+            const int cn = min(32, e1 - c0);
+            const int my_tail = lane < cn ? __ldg(g.att_tail + c0 + lane) : 0;
+            const int my_rel = lane < cn ? __ldg(g.att_rel + c0 + lane) : -1;
+            const int my_seg = lane < cn ? __ldg(g.att_seg + c0 + lane) : 0;
+            // prologue: fill the ring
+            const int first = min(cn, kRing);
+            if (lane < first) {
+                const uint32_t slot = (issued + lane) % kRing;
+                ring_issue(ring + slot * row_bytes, ent + (int64_t)my_tail * ld_ent, row_bytes, &bars[slot]);
             }
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                const float* trow = ent + (int64_t)tl[j] * ld_ent;
+            issued += first;
+            if (!next_loaded) load_next();
+            if (c0 == e0) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    const int v = lane + 32 * s;
-                    et[j][s] = (rl[j] >= 0 && v < nvec) ? ldg_stream4(trow + 4 * v) : make_float4(0, 0, 0, 0);
+                    eh[s].x = exp2x(eh[s].x);
+                    eh[s].y = exp2x(eh[s].y);
+                    eh[s].z = exp2x(eh[s].z);
+                    eh[s].w = exp2x(eh[s].w);
                 }
             }
-            float part[kUnroll];
+            for (int j0 = 0; j0 < cn; j0 += 4) {
+                float part[4];
 #pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                if (rl[j] >= 0 && rl[j] != cur_rel) {   // warp-uniform
-                    cur_rel = rl[j];
-                    const float4* rrow = reinterpret_cast<const float4*>(rel_exp) + (int64_t)cur_rel * nvec;
+                for (int j = 0; j < 4; ++j) {
+                    const int e = j0 + j;
+                    const int rl = __shfl_sync(kFull, my_rel, e & 31);
+                    float p = 0.f;
+                    if (e < cn) {                               // warp-uniform
+                        if (rl != cur_rel) {
+                            cur_rel = rl;
+                            const float4* rrow = reinterpret_cast<const float4*>(rel_exp) + (int64_t)cur_rel * nvec;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const int v = lane + 32 * s;
-                        if (v < nvec) {
-                            const float4 er = __ldg(rrow + v);
-                            w[s].x = tanh_from_exp(eh[s].x * er.x);
-                            w[s].y = tanh_from_exp(eh[s].y * er.y);
-                            w[s].z = tanh_from_exp(eh[s].z * er.z);
-                            w[s].w = tanh_from_exp(eh[s].w * er.w);
+                            for (int s = 0; s < S; ++s) {
+                                const int v = lane + 32 * s;
+                                if (v < nvec) {
+                                    const float4 er = __ldg(rrow + v);
+                                    w[s].x = tanh_from_exp(eh[s].x * er.x);
+                                    w[s].y = tanh_from_exp(eh[s].y * er.y);
+                                    w[s].z = tanh_from_exp(eh[s].z * er.z);
+                                    w[s].w = tanh_from_exp(eh[s].w * er.w);
+                                }
+                            }
+                        }
+                        const uint32_t slot = consumed % kRing;
+                        ring_wait(&bars[slot], (consumed / kRing) & 1);
+                        const float4* trow = reinterpret_cast<const float4*>(ring + slot * row_bytes);
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const int v = lane + 32 * s;
+                            if (v < nvec) {
+                                const float4 et = trow[v];
+                                p = fmaf(et.x, w[s].x, p);
+                                p = fmaf(et.y, w[s].y, p);
+                                p = fmaf(et.z, w[s].z, p);
+                                p = fmaf(et.w, w[s].w, p);
+                            }
+                        }
+                        ++consumed;
+                        __syncwarp();                            // every lane has read the slot before it is refilled
+                        const int nxt = e + kRing;               // keep kRing copies in flight
+                        if (nxt < cn) {
+                            if (lane == (nxt & 31))
+                                ring_issue(ring + slot * row_bytes, ent + (int64_t)my_tail * ld_ent, row_bytes, &bars[slot]);
+                            ++issued;
                         }
                     }
+                    part[j] = p;
                 }
-                float p = 0.f;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    p = fmaf(et[j][s].x, w[s].x, p);
-                    p = fmaf(et[j][s].y, w[s].y, p);
-                    p = fmaf(et[j][s].z, w[s].z, p);
-                    p = fmaf(et[j][s].w, w[s].w, p);
+                // four warp sums in 6 shuffles: halve the number of live values on the first two steps
+                const bool up16 = lane & 16, up8 = lane & 8;
+                float k0 = (up16 ? part[2] : part[0]) + __shfl_xor_sync(kFull, up16 ? part[0] : part[2], 16);
+                float k1 = (up16 ? part[3] : part[1]) + __shfl_xor_sync(kFull, up16 ? part[1] : part[3], 16);
+                float k = (up8 ? k1 : k0) + __shfl_xor_sync(kFull, up8 ? k0 : k1, 8);
+                k += __shfl_xor_sync(kFull, k, 4);
+                k += __shfl_xor_sync(kFull, k, 2);
+                k += __shfl_xor_sync(kFull, k, 1);     // lanes with (lane >> 3) == j hold the logit of triple j0 + j
+                // lane 8 j owns triple j0 + j: a triple that is alone in its (h,t) pair stores its logit; the rare
+                // triples of multi-relation pairs (bit 31 of att_seg) are added (the slots start at zero).  A lane-0
+                // load + add + store per triple was a dependent chain that cost 19 % of the stall samples.
+                const int mine = j0 + (lane >> 3);
+                const int sg = __shfl_sync(kFull, my_seg, mine & 31);
+                if ((lane & 7) == 0 && mine < cn) {
+                    float* slot = logit + ((sg & 0x7fffffff) - u0);
+                    if (sg >= 0) *slot = k;
+                    else atomicAdd(slot, k);
                 }
-                part[j] = p;
-            }
-            // four warp sums in 6 shuffles: halve the number of live values on the first two steps
-            static_assert(kUnroll == 4, "the folded reduction below is written for 4 values");
-            const bool up16 = lane & 16, up8 = lane & 8;
-            float k0 = (up16 ? part[2] : part[0]) + __shfl_xor_sync(kFull, up16 ? part[0] : part[2], 16);
-            float k1 = (up16 ? part[3] : part[1]) + __shfl_xor_sync(kFull, up16 ? part[1] : part[3], 16);
-            float k = (up8 ? k1 : k0) + __shfl_xor_sync(kFull, up8 ? k0 : k1, 8);
-            k += __shfl_xor_sync(kFull, k, 4);
-            k += __shfl_xor_sync(kFull, k, 2);
-            k += __shfl_xor_sync(kFull, k, 1);     // lanes with (lane >> 3) == j hold the logit of triple j
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                const float v = __shfl_sync(kFull, k, 8 * j);
-                if (lane == 0 && rl[j] >= 0) logit[sg[j] - u0] += v;   // sequential: duplicates of a pair add up in order
             }
         }
+        if (!in_smem) __threadfence();          // the long-row reductions are performed before other lanes read them
         __syncwarp();
 
-        // softmax over the row's unique pairs
+        // softmax over the row's unique pairs (__ldcg: the long-row logits were reduced in L2, bypass L1)
         float m = -INFINITY;
-        for (int i = lane; i < nu; i += 32) m = fmaxf(m, logit[i]);
+        for (int i = lane; i < nu; i += 32) m = fmaxf(m, in_smem ? logit[i] : __ldcg(logit + i));
         m = warp_max(m);
         float sum = 0.f;
         for (int i = lane; i < nu; i += 32) {
-            const float ex = __expf(logit[i] - m);
+            const float ex = __expf((in_smem ? logit[i] : __ldcg(logit + i)) - m);
             logit[i] = ex;
             sum += ex;
         }
@@ -163,7 +257,12 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         const float inv = 1.f / sum;
         for (int i = lane; i < nu; i += 32) val[u0 + i] = logit[i] * inv;
         __syncwarp();   // the shared slots are reused by the next row
+        idx = next_idx; rec = nrec; rec_u1 = nrec_u1;
     }
+}
+
+inline size_t attn_smem_bytes(int nvec, int ring) {
+    return (size_t)kWarps * ring * nvec * 16 + kWarps * ring * 8 + kWarps * kSegCap * 4;
 }
 
 constexpr size_t kCounterBytes = 256;
@@ -189,6 +288,7 @@ extern "C" int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t 
     LKG_REQUIRE(dim > 0 && dim % 4 == 0, "dim must be a positive multiple of 4 (got %d)", dim);
     LKG_REQUIRE(ld_entity % 4 == 0 && aligned16(entity) && aligned16(workspace),
                 "entity rows and the workspace must be 16-byte aligned");
+    LKG_REQUIRE(g->row_sched != nullptr && aligned16(g->row_sched), "the plan has no row schedule (lkg_plan_build row_sched)");
     if (dim > 512) LKG_FAIL(LKG_ERR_UNSUPPORTED, "attention dim %d > 512", dim);
     if (g->n_edges == 0) return LKG_OK;
     int* counter = static_cast<int*>(workspace);
@@ -200,13 +300,25 @@ extern "C" int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t 
     const int nvec = dim / 4;
     const int slots = (nvec + 31) / 32;
     const int block = kWarps * 32;
-    const int grid = sm_count() * 8;
+    static const int ring_env = getenv("LKG_ATTN_RING") ? atoi(getenv("LKG_ATTN_RING")) : 0;
+    const int ring = ring_env == 4 ? 4 : 8;
+    const size_t smem = attn_smem_bytes(nvec, ring);
+    auto launch = [&](auto kern) -> int {
+        LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        LKG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+        if (per_sm < 1) LKG_FAIL(LKG_ERR_UNSUPPORTED, "attention kernel does not fit (smem %zu)", smem);
+        kern<<<sm_count() * per_sm, block, smem, stream>>>(*g, entity, ld_entity, rel_exp, nvec, values, counter);
+        return LKG_OK;
+    };
+    int rc;
     switch (slots) {
-        case 1: attn_update_kernel<1><<<grid, block, 0, stream>>>(*g, entity, ld_entity, rel_exp, nvec, values, counter); break;
-        case 2: attn_update_kernel<2><<<grid, block, 0, stream>>>(*g, entity, ld_entity, rel_exp, nvec, values, counter); break;
-        case 3: attn_update_kernel<3><<<grid, block, 0, stream>>>(*g, entity, ld_entity, rel_exp, nvec, values, counter); break;
-        default: attn_update_kernel<4><<<grid, block, 0, stream>>>(*g, entity, ld_entity, rel_exp, nvec, values, counter); break;
+        case 1: rc = launch(attn_update_kernel<1, 8, 2>); break;
+        case 2: rc = launch(attn_update_kernel<2, 8, 2>); break;
+        case 3: rc = ring == 4 ? launch(attn_update_kernel<3, 4, 4>) : launch(attn_update_kernel<3, 8, 2>); break;
+        default: rc = launch(attn_update_kernel<4, 8, 1>); break;
     }
+    if (rc) return rc;
     LKG_LAUNCH_CHECK("attn_update_kernel");
     return LKG_OK;
 }

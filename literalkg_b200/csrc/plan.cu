@@ -161,15 +161,31 @@ __global__ void gather_att(const uint64_t* __restrict__ key_hr_sorted, const int
     const int64_t e = counts[0];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t p = pos_sorted[i];
-        att_tail[i] = (int32_t)(key_ht[p] & 0xffffffffu);
+        const uint64_t k = key_ht[p];
+        att_tail[i] = (int32_t)(k & 0xffffffffu);
         att_rel[i] = (int32_t)(key_hr_sorted[i] & 0xffffffffu);
-        att_seg[i] = seg_ht[p];
+        // bit 31 flags a triple whose (h,t) pair has other triples (another relation): its logit must be ADDED to the
+        // pair slot; every other triple owns its slot and is simply stored
+        const bool dup = (p > 0 && key_ht[p - 1] == k) || (p + 1 < e && key_ht[p + 1] == k);
+        att_seg[i] = seg_ht[p] | (dup ? (int32_t)0x80000000 : 0);
     }
 }
 
 __global__ void iota_kernel(int32_t* __restrict__ out, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)i;
+}
+
+// schedule record of the i-th heaviest row: {row, att_begin, att_end, agg_begin, agg_end, 0, 0, 0} -- one 32-byte
+// sector tells a warp everything about its next row (instead of a row_order -> rowptr -> rowptr chain of loads)
+__global__ void make_sched_kernel(const int32_t* __restrict__ row_order, const int32_t* __restrict__ att_rowptr,
+                                  const int32_t* __restrict__ rowptr, int64_t n, int32_t* __restrict__ sched) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t row = row_order[i];
+        int4* out = reinterpret_cast<int4*>(sched + 8 * i);
+        out[0] = make_int4(row, att_rowptr[row], att_rowptr[row + 1], rowptr[row]);
+        out[1] = make_int4(rowptr[row + 1], 0, 0, 0);
+    }
 }
 
 inline int grid_for(int64_t n, int block = 256) {
@@ -181,6 +197,8 @@ inline int grid_for(int64_t n, int block = 256) {
 }
 
 // ---- Laplacian -------------------------------------------------------------------------------
+constexpr int32_t kSegMask = 0x7fffffff;   // att_seg: bit 31 = "pair has several triples"
+
 // one thread per head row; walks the row's (h,r) runs in att order.  deg_r(h) = run length.
 // random-walk: each triple contributes 1/deg_r(h); symmetric: deg_r(h)^-1/2 * deg_r(t)^-1/2 where
 // deg_r(t) is the OUT-degree of t under r (row sums on both sides, dataloader.py:464-470), 0 -> 0.
@@ -219,7 +237,7 @@ __global__ void laplacian_kernel(lkg_graph g, int symmetric, double* __restrict_
                     const int32_t dt = run_length(g, g.att_tail[k], rel);
                     v = dt > 0 ? dh * (1.0 / sqrt((double)dt)) : 0.0;
                 }
-                acc[g.att_seg[k]] += v;   // all triples of one pair live in this row: no race
+                acc[g.att_seg[k] & kSegMask] += v;   // all triples of one pair live in this row: no race
             }
             i = j;
         }
@@ -247,7 +265,7 @@ extern "C" int lkg_plan_workspace_bytes(int64_t n_edges, int64_t n_entities, siz
 extern "C" int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t* r, int64_t n_edges,
                               int64_t n_entities, int32_t n_relations, const uint8_t* rel_keep,
                               int32_t* att_rowptr, int32_t* att_tail, int32_t* att_rel, int32_t* att_seg,
-                              int32_t* rowptr, int32_t* col, int32_t* row_order, int64_t* coo_rows,
+                              int32_t* rowptr, int32_t* col, int32_t* row_order, int32_t* row_sched, int64_t* coo_rows,
                               int64_t* coo_cols, int32_t* file_seg, int64_t* counts_dev, void* workspace,
                               size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -303,6 +321,11 @@ extern "C" int lkg_plan_build(const int64_t* h, const int64_t* t, const int64_t*
     LKG_CUDA(cub::DeviceScan::ExclusiveSum(s.cub, tb, s.deg_e, att_rowptr, (int)n1, stream));
     tb = s.cub_bytes;
     LKG_CUDA(cub::DeviceScan::ExclusiveSum(s.cub, tb, s.deg_u, rowptr, (int)n1, stream));
+    if (row_sched) {
+        LKG_REQUIRE(row_order != nullptr && aligned16(row_sched), "row_sched needs row_order and 16-byte alignment");
+        make_sched_kernel<<<grid_for(n_entities), 256, 0, stream>>>(row_order, att_rowptr, rowptr, n_entities, row_sched);
+        LKG_LAUNCH_CHECK("make_sched_kernel");
+    }
     return LKG_OK;
 }
 

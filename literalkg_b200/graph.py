@@ -44,6 +44,7 @@ class GraphPlan:
         self.att_seg = torch.empty(max(e, 1), **i32)
         self.col = torch.empty(max(e, 1), **i32)
         self.row_order = torch.empty(n_entities, **i32)     # rows by decreasing triple count (LPT schedule)
+        self.row_sched = torch.empty((n_entities, 8), **i32)   # the same order as {row, att range, agg range} records
         coo = torch.empty((2, max(e, 1)), dtype=torch.int64, device=dev)
         self.file_seg = torch.empty(max(e, 1), **i32)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
@@ -54,8 +55,8 @@ class GraphPlan:
             _lib.check(lib.lkg_plan_build(h.data_ptr(), t.data_ptr(), r.data_ptr(), e, n_entities, n_relations,
                                           _lib.ptr(keep), self.att_rowptr.data_ptr(), self.att_tail.data_ptr(),
                                           self.att_rel.data_ptr(), self.att_seg.data_ptr(), self.rowptr.data_ptr(),
-                                          self.col.data_ptr(), self.row_order.data_ptr(), coo[0].data_ptr(),
-                                          coo[1].data_ptr(),
+                                          self.col.data_ptr(), self.row_order.data_ptr(), self.row_sched.data_ptr(),
+                                          coo[0].data_ptr(), coo[1].data_ptr(),
                                           self.file_seg.data_ptr(), counts.data_ptr(), ws.data_ptr(), nbytes.value,
                                           _lib.stream()))
         kept, nnz, bad = counts.tolist()          # one host sync per plan build
@@ -72,8 +73,8 @@ class GraphPlan:
         self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations, 0, self.n_entities,
                                self.att_rowptr.data_ptr(), self.att_tail.data_ptr(), self.att_rel.data_ptr(),
                                self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr(),
-                               self.row_order.data_ptr())
-        self._part_order = None
+                               self.row_order.data_ptr(), self.row_sched.data_ptr())
+        self._part_order = self._part_sched = self._part_range = None
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
         self._attn_ws = None
 
@@ -95,12 +96,16 @@ class GraphPlan:
             raise ValueError("bad row range")
         self.c.row_begin, self.c.row_end = int(begin), int(end)
         if begin == 0 and end == self.n_entities:
-            self._part_order = None
             self.c.row_order = self.row_order.data_ptr()
-        else:   # the partition's rows, still heaviest first
+            self.c.row_sched = self.row_sched.data_ptr()
+            return
+        if self._part_order is None or self._part_range != (begin, end):   # the partition's rows, heaviest first
             keep = (self.row_order >= begin) & (self.row_order < end)
             self._part_order = self.row_order[keep].contiguous()
-            self.c.row_order = self._part_order.data_ptr()
+            self._part_sched = self.row_sched[keep].contiguous()
+            self._part_range = (begin, end)
+        self.c.row_order = self._part_order.data_ptr()
+        self.c.row_sched = self._part_sched.data_ptr()
 
     @staticmethod
     def fingerprint(h: torch.Tensor, t: torch.Tensor, r: torch.Tensor):
