@@ -78,6 +78,12 @@ __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // S = float4 slots per lane (dim <= 128 * S); kRing = tail rows in flight per warp (bulk copies into shared memory)
+//
+// Software pipeline across rows (every load below is a global round trip of 1-2 us under load, and a warp spends
+// only ~5 us streaming an average row, so a chain of them per row would dominate):
+//   during row i     the counter fetch for row i+2, then the schedule record of row i+2;
+//                    the first index chunk and the head row e_h of row i+1 (its record arrived during row i-1)
+//   at row i start   everything is in registers: the ring copies of the first chunk are issued immediately
 template <int S, int kRing, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
@@ -98,63 +104,77 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
     const int n_rows = (int)(g.row_end - g.row_begin);
     uint32_t issued = 0, consumed = 0;              // running counts over the kernel: slot = count % kRing,
                                                     // parity of a slot's use = (count / kRing) & 1
-    // Rows come from a shared counter (dynamic balance: the heaviest rows are first in the schedule).  The counter
-    // fetch and the schedule record of the NEXT row are issued while the current row streams, so a row starts with
-    // everything it needs in registers instead of an atomic -> row_order -> rowptr chain of dependent round trips.
     const int4* sched = reinterpret_cast<const int4*>(g.row_sched);
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(row_counter, 1);
-    idx = __shfl_sync(kFull, idx, 0);
-    int4 rec = make_int4(0, 0, 0, 0);
-    int rec_u1 = 0;
-    if (idx < n_rows) {
-        rec = __ldg(sched + 2 * idx);
-        rec_u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * idx + 1));
-    }
 
-    while (idx < n_rows) {
-        int next_idx = 0;
-        if (lane == 0) next_idx = atomicAdd(row_counter, 1);          // consumed after the first chunk's prologue
-        const int row = rec.x, e0 = rec.y, e1 = rec.z, u0 = rec.w, nu = rec_u1 - rec.w;
-        bool next_loaded = false;
-        int4 nrec = make_int4(0, 0, 0, 0);
-        int nrec_u1 = 0;
-        auto load_next = [&]() {
-            next_idx = __shfl_sync(kFull, next_idx, 0);
-            if (next_idx < n_rows) {
-                nrec = __ldg(sched + 2 * next_idx);
-                nrec_u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * next_idx + 1));
-            }
-            next_loaded = true;
-        };
-        if (e0 == e1) {
-            load_next();
-            idx = next_idx; rec = nrec; rec_u1 = nrec_u1;
-            continue;
+    struct Rec { int row, e0, e1, u0, u1; };
+    auto fetch_idx = [&]() {                         // dynamic balance: the heaviest rows are first in the schedule
+        int i = 0;
+        if (lane == 0) i = atomicAdd(row_counter, 1);
+        return i;                                    // valid in lane 0 until broadcast
+    };
+    auto load_rec = [&](int i) {
+        Rec r{0, 0, 0, 0, 0};
+        if (i < n_rows) {
+            const int4 a = __ldg(sched + 2 * i);
+            r.row = a.x; r.e0 = a.y; r.e1 = a.z; r.u0 = a.w;
+            r.u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * i + 1));
         }
-        const bool in_smem = nu <= kSegCap;
-        float* logit = in_smem ? s_logit : val + u0;                   // slot of pair u: logit[u - u0]
-        for (int i = lane; i < nu; i += 32) logit[i] = 0.f;
-
-        float4 eh[S], w[S];
-        const float* hrow = ent + (int64_t)row * ld_ent;
+        return r;
+    };
+    // first chunk of a row: this lane's (tail, relation, pair) and the raw head row
+    struct Head { int tail, rel, seg; float4 eh[S]; };
+    auto load_head = [&](const Rec& r) {
+        Head h;
+        const int cn = min(32, r.e1 - r.e0);
+        h.tail = lane < cn ? __ldg(g.att_tail + r.e0 + lane) : 0;
+        h.rel = lane < cn ? __ldg(g.att_rel + r.e0 + lane) : -1;
+        h.seg = lane < cn ? __ldg(g.att_seg + r.e0 + lane) : 0;
+        const float* hrow = ent + (int64_t)r.row * ld_ent;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int v = lane + 32 * s;
-            // raw e_h for now: exp(2 e_h) is taken after the first chunk's indices and bulk copies are on their way
-            eh[s] = v < nvec ? __ldg(reinterpret_cast<const float4*>(hrow) + v) : make_float4(0, 0, 0, 0);
+            h.eh[s] = (v < nvec && r.e1 > r.e0) ? __ldg(reinterpret_cast<const float4*>(hrow) + v) : make_float4(0, 0, 0, 0);
+        }
+        return h;
+    };
+
+    // pipeline fill: rows 0 and 1 of this warp
+    int idx = __shfl_sync(kFull, fetch_idx(), 0);
+    Rec rec = load_rec(idx);
+    int idx1 = __shfl_sync(kFull, fetch_idx(), 0);
+    Rec rec1 = load_rec(idx1);
+    Head head = load_head(rec);
+
+    while (idx < n_rows && rec.e1 > rec.e0) {        // the schedule is sorted by triple count: an empty row ends it
+        int idx2 = fetch_idx();                      // row i+2: broadcast and record load after the ring is filled
+        const int row = rec.row, e0 = rec.e0, e1 = rec.e1, u0 = rec.u0, nu = rec.u1 - rec.u0;
+        (void)row;
+        const bool in_smem = nu <= kSegCap;
+        float* logit = in_smem ? s_logit : val + u0;                   // slot of pair u: logit[u - u0]
+        for (int i = lane; i < nu; i += 32) logit[i] = 0.f;
+        float4 eh[S], w[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            eh[s] = head.eh[s];
             w[s] = make_float4(0, 0, 0, 0);
         }
-        __syncwarp();   // zeroing of the slots visible before lane 0 accumulates
+        __syncwarp();   // zeroing of the slots visible before the logits are written
 
+        Rec rec2{0, 0, 0, 0, 0};
+        Head head1;
         int cur_rel = -1;
         // the row's triples in chunks of 32: one coalesced load of (tail, relation, pair) per chunk, then the tail rows
         // stream through the ring, kRing bulk copies in flight
         for (int c0 = e0; c0 < e1; c0 += 32) {
             const int cn = min(32, e1 - c0);
-            const int my_tail = lane < cn ? __ldg(g.att_tail + c0 + lane) : 0;
-            const int my_rel = lane < cn ? __ldg(g.att_rel + c0 + lane) : -1;
-            const int my_seg = lane < cn ? __ldg(g.att_seg + c0 + lane) : 0;
+            int my_tail, my_rel, my_seg;
+            if (c0 == e0) {
+                my_tail = head.tail; my_rel = head.rel; my_seg = head.seg;
+            } else {
+                my_tail = lane < cn ? __ldg(g.att_tail + c0 + lane) : 0;
+                my_rel = lane < cn ? __ldg(g.att_rel + c0 + lane) : -1;
+                my_seg = lane < cn ? __ldg(g.att_seg + c0 + lane) : 0;
+            }
             // prologue: fill the ring
             const int first = min(cn, kRing);
             if (lane < first) {
@@ -162,8 +182,11 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
                 ring_issue(ring + slot * row_bytes, ent + (int64_t)my_tail * ld_ent, row_bytes, &bars[slot]);
             }
             issued += first;
-            if (!next_loaded) load_next();
             if (c0 == e0) {
+                // with this row's copies in flight: the loads of the rows to come, then exp(2 e_h)
+                idx2 = __shfl_sync(kFull, idx2, 0);
+                rec2 = load_rec(idx2);
+                head1 = load_head(rec1);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     eh[s].x = exp2x(eh[s].x);
@@ -257,7 +280,8 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         const float inv = 1.f / sum;
         for (int i = lane; i < nu; i += 32) val[u0 + i] = logit[i] * inv;
         __syncwarp();   // the shared slots are reused by the next row
-        idx = next_idx; rec = nrec; rec_u1 = nrec_u1;
+        idx = idx1; rec = rec1; head = head1;
+        idx1 = idx2; rec1 = rec2;
     }
 }
 
