@@ -196,6 +196,10 @@ int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* eg
                       int64_t local_row_base /*r1, r2, drop_mask, xn_out, xn_planes hold rows [local_row_base, ...):
                                                the row partition's local buffers (0 on one GPU); ego and x_out
                                                are indexed by the global row*/,
+                      const float* z /*nullable*/, int64_t ld_z /*pre-projected sum term of the bi-interaction
+                                               layer: z = ego @ Pb [N, d_out], e.g. extra columns of the h0 @ Q GEMM;
+                                               then o1 = r1[row] + sum_j A[row,j] z[col_j], pa = pb = NULL, and
+                                               only P2 is combined in the kernel (wide rows only)*/,
                       void* workspace, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */

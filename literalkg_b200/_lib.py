@@ -55,7 +55,7 @@ SIGNATURES = {
                                i64, vp, vp]),
     "lkg_aggregate_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
     "lkg_aggregate_fwd": (C.c_int, [C.POINTER(LkgGraph), vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp,
-                                    vp, vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, vp]),
+                                    vp, vp, i64, vp, i64, vp, i64, i64, vp, i64, vp, i64, vp, vp]),
     "lkg_score": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i64, vp, i64, vp, vp]),
     "lkg_minmax_reset": (C.c_int, [vp, vp]),
     "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),

@@ -19,7 +19,7 @@ namespace {
 
 constexpr int kRows = 2;  // head rows per warp per step (P is read from shared memory once per kRows rows)
 
-enum Mode { kOneTerm = 0, kTwoTerms = 1, kBi = 2 };
+enum Mode { kOneTerm = 0, kTwoTerms = 1, kBi = 2, kBiZ = 3 /* bi-interaction with a pre-projected sum term */ };
 
 struct AggParams {
     lkg_graph g;
@@ -45,6 +45,8 @@ struct AggParams {
     const float* xn_rec;        // its scale record (|xn| <= 1)
     int* counter;
     int p_stride;      // padded row stride (floats) of P in shared memory
+    const float* z;    // kBiZ: pre-projected neighbour term, z = ego @ Pb ([N, d_out], row stride ld_z): the sum path
+    int64_t ld_z;      //       o1 = r1 + sum_j A[row, j] z[col_j] needs no combine matrix in the kernel
     int64_t local_row_base;   // r1 / r2 / mask / xn_out / xn_planes are indexed by (row - local_row_base): the
                               // row partition's local buffers; ego and x_out are indexed by the global row
 };
@@ -511,6 +513,345 @@ int dispatch_narrow(int mode, const AggParams& p, cudaStream_t stream) {
     }
 }
 
+// ---- wide rows (layer 1, d_in = 300): gathered rows stream through a per-warp shared-memory ring --------------------
+// Same streaming structure as the attention update (attn.cu): the neighbour list is loaded 32 entries at a time in
+// one coalesced step, the 1 200-byte neighbour rows arrive by cp.async.bulk (one TMA-unit copy per row, kRing in
+// flight per warp, no registers held), and the schedule record, first index chunk and own ego row of the NEXT row
+// are prefetched while the current row streams.  The register-staged kernel above keeps 4 rows in flight behind a
+// rowptr -> col -> gather chain of dependent round trips (ncu r01: 66 % of the HBM peak, long_scoreboard on top).
+// The folded combine reads the u-vectors (side | ego+side | ego*side) from a per-warp staging buffer and P from
+// shared memory in [d/4][channel][4] order: one 16-byte load per matrix feeds four FMAs.
+constexpr int kStreamWarps = 16;
+// neighbour rows in flight per warp: what fits next to the P tiles (kBiZ keeps one matrix instead of two)
+__host__ __device__ constexpr int stream_ring(int mode) { return mode == kBiZ ? 6 : 4; }
+
+template <int S, int NC, int MODE>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(AggParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr bool Z = MODE == kBiZ;                            // sum term pre-projected: only the product term is combined
+    constexpr int NT = (MODE == kOneTerm || Z) ? 1 : 2;
+    constexpr int kRing = stream_ring(MODE);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int d_in = p.d_in, d_out = p.d_out, nvec = p.nvec;
+    const int cpad = 32 * NC;                                   // padded channel count of the P tiles
+    const uint32_t row_bytes = (uint32_t)nvec * 16u;
+    const uint32_t z_bytes = Z ? (uint32_t)d_out * 4u : 0u;      // a ring slot = neighbour row (+ its z row)
+    const uint32_t slot_bytes = row_bytes + z_bytes;
+    // layout: P0 [nvec][cpad][4] | P1 | per warp { ring kRing x slot_bytes | stage NT x row_bytes } | barriers
+    float4* sp0 = reinterpret_cast<float4*>(smem_raw);
+    float4* sp1 = sp0 + (size_t)nvec * cpad;
+    const size_t warp_bytes = (size_t)kRing * slot_bytes + (size_t)NT * row_bytes;
+    uint8_t* warp_base = smem_raw + (size_t)NT * nvec * cpad * 16 + (size_t)warp * warp_bytes;
+    uint8_t* ring = warp_base;
+    float4* stage = reinterpret_cast<float4*>(warp_base + (size_t)kRing * slot_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NT * nvec * cpad * 16 +
+                                                 (size_t)kStreamWarps * warp_bytes) + warp * kRing;
+    auto issue = [&](uint32_t slot, int col) {                   // one elected lane: row copy (+ z copy), one barrier
+        uint8_t* dst = ring + slot * slot_bytes;
+        if (Z) {
+            ring_expect(&bars[slot], slot_bytes);
+            ring_copy(dst, p.ego + (int64_t)col * p.ld_ego, row_bytes, &bars[slot]);
+            ring_copy(dst + row_bytes, p.z + (int64_t)col * p.ld_z, z_bytes, &bars[slot]);
+        } else {
+            ring_issue(dst, p.ego + (int64_t)col * p.ld_ego, row_bytes, &bars[slot]);
+        }
+    };
+    for (int i = threadIdx.x; i < nvec * cpad; i += blockDim.x) {
+        const int d4 = i / cpad, c = i - d4 * cpad;
+        float w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+        if (c < d_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w0[k] = p.p0[(4 * d4 + k) * d_out + c];
+                if (NT == 2) w1[k] = p.p1[(4 * d4 + k) * d_out + c];
+            }
+        }
+        sp0[i] = make_float4(w0[0], w0[1], w0[2], w0[3]);
+        if (NT == 2) sp1[i] = make_float4(w1[0], w1[1], w1[2], w1[3]);
+    }
+    if (lane < kRing) ring_bar_init(&bars[lane]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int n_rows = (int)(p.g.row_end - p.g.row_begin);
+    const int4* sched = reinterpret_cast<const int4*>(p.g.row_sched);
+    uint32_t issued = 0, consumed = 0;
+    const bool need_ego = MODE != kOneTerm || p.sum_ego;
+    const int zvec = d_out >> 2;                                 // float4 per z row
+
+    struct Rec { int row, u0, u1; };
+    auto fetch_idx = [&]() {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(p.counter, 1);
+        return i;
+    };
+    auto load_rec = [&](int i) {
+        Rec r{0, 0, 0};
+        if (i < n_rows) {
+            const int4 a = __ldg(sched + 2 * i);
+            r.row = a.x; r.u0 = a.w;
+            r.u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * i + 1));
+        }
+        return r;
+    };
+    struct Head { int col; float val; float4 eg[S]; bool live; };
+    auto load_head = [&](const Rec& r, bool live) {
+        Head h;
+        h.live = live;
+        const int cn = min(32, r.u1 - r.u0);
+        h.col = (live && lane < cn) ? __ldg(p.g.col + r.u0 + lane) : 0;
+        h.val = (live && lane < cn) ? __ldg(p.a_val + r.u0 + lane) : 0.f;
+        const float4* erow = reinterpret_cast<const float4*>(p.ego + (int64_t)r.row * p.ld_ego);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int v = lane + 32 * s;
+            h.eg[s] = (live && need_ego && v < nvec) ? __ldg(erow + v) : make_float4(0, 0, 0, 0);
+        }
+        return h;
+    };
+
+    int idx = __shfl_sync(kFull, fetch_idx(), 0);
+    Rec rec = load_rec(idx);
+    int idx1 = __shfl_sync(kFull, fetch_idx(), 0);
+    Rec rec1 = load_rec(idx1);
+    Head head = load_head(rec, idx < n_rows);
+    int pre_issued = 0;                              // copies of this row's first chunk issued during the previous row
+
+    while (idx < n_rows) {
+        int idx2 = fetch_idx();
+        const int row = rec.row, u0 = rec.u0, u1 = rec.u1;
+        const int64_t lrow = row - p.local_row_base;
+        Rec rec2{0, 0, 0};
+        Head head1;
+        bool fetched = false;
+        auto prefetch_rows = [&]() {                 // with this row's copies in flight: loads of the rows to come
+            idx2 = __shfl_sync(kFull, idx2, 0);
+            rec2 = load_rec(idx2);
+            head1 = load_head(rec1, idx1 < n_rows);
+            fetched = true;
+        };
+
+        // ---- phase 1: side = sum_j A[row, j] * ego[col_j] ---------------------------------------------------
+        float4 side[S];
+        float4 zside = make_float4(0, 0, 0, 0);                  // kBiZ: lane q < zvec holds channels [4q, 4q + 4)
+#pragma unroll
+        for (int s = 0; s < S; ++s) side[s] = make_float4(0, 0, 0, 0);
+        for (int c0 = u0; c0 < u1; c0 += 32) {
+            const int cn = min(32, u1 - c0);
+            int my_col;
+            float my_val;
+            if (c0 == u0) {
+                my_col = head.col; my_val = head.val;
+            } else {
+                my_col = lane < cn ? __ldg(p.g.col + c0 + lane) : 0;
+                my_val = lane < cn ? __ldg(p.a_val + c0 + lane) : 0.f;
+            }
+            const int first = min(cn, kRing);
+            const int done = c0 == u0 ? pre_issued : 0;          // the first chunk's copies may already be in flight
+            if (lane >= done && lane < first) {
+                issue((issued + lane - done) % kRing, my_col);
+            }
+            issued += first - done;
+            if (!fetched) prefetch_rows();
+            for (int e = 0; e < cn; ++e) {
+                const float a = __shfl_sync(kFull, my_val, e);
+                const uint32_t slot = consumed % kRing;
+                ring_wait(&bars[slot], (consumed / kRing) & 1);
+                const float4* nrow = reinterpret_cast<const float4*>(ring + slot * slot_bytes);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const int v = lane + 32 * s;
+                    if (v < nvec) {
+                        const float4 x = nrow[v];
+                        side[s].x = fmaf(a, x.x, side[s].x);
+                        side[s].y = fmaf(a, x.y, side[s].y);
+                        side[s].z = fmaf(a, x.z, side[s].z);
+                        side[s].w = fmaf(a, x.w, side[s].w);
+                    }
+                }
+                if (Z && lane < zvec) {
+                    const float4 x = nrow[nvec + lane];
+                    zside.x = fmaf(a, x.x, zside.x);
+                    zside.y = fmaf(a, x.y, zside.y);
+                    zside.z = fmaf(a, x.z, zside.z);
+                    zside.w = fmaf(a, x.w, zside.w);
+                }
+                ++consumed;
+                __syncwarp();                                    // every lane has read the slot before it is refilled
+                const int nxt = e + kRing;
+                if (nxt < cn) {
+                    if (lane == nxt) issue(slot, my_col);
+                    ++issued;
+                }
+            }
+        }
+        if (!fetched) prefetch_rows();                           // row without neighbours
+        // the ring is empty: start the next row's first copies now, they land while this row is combined
+        pre_issued = 0;
+        if (idx1 < n_rows) {
+            pre_issued = min(kRing, min(32, rec1.u1 - rec1.u0));
+            if (lane < pre_issued) issue((issued + lane) % kRing, head1.col);
+            issued += pre_issued;
+        }
+
+        // ---- phase 2: u-vectors to the staging buffer, folded combine with lane = output channel -------------
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int v = lane + 32 * s;
+            if (v < nvec) {
+                const float4 sd = side[s], eg = head.eg[s];
+                float4 t0, t1;
+                if (Z) {
+                    t0 = make_float4(eg.x * sd.x, eg.y * sd.y, eg.z * sd.z, eg.w * sd.w);
+                    t1 = t0;
+                } else if (MODE == kTwoTerms) {
+                    t0 = eg;
+                    t1 = sd;
+                } else {
+                    t0 = p.sum_ego ? make_float4(eg.x + sd.x, eg.y + sd.y, eg.z + sd.z, eg.w + sd.w) : sd;
+                    t1 = make_float4(eg.x * sd.x, eg.y * sd.y, eg.z * sd.z, eg.w * sd.w);
+                }
+                stage[v] = t0;
+                if (NT == 2) stage[nvec + v] = t1;
+            }
+        }
+        __syncwarp();
+        float acc1[NC], acc2[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int ch = lane + 32 * c;
+            // kBiZ: acc1 accumulates the product path (r2 + (ego * side) @ P2); the sum path is r1 + zside
+            const float* rp = Z ? p.r2 : p.r1;
+            acc1[c] = (ch < d_out && rp) ? __ldg(rp + lrow * p.ld_r + ch) : 0.f;
+            acc2[c] = (MODE == kBi && ch < d_out && p.r2) ? __ldg(p.r2 + lrow * p.ld_r + ch) : 0.f;
+            if (Z) {
+                const int src = (ch >> 2) & 31;
+                const float zx = __shfl_sync(kFull, zside.x, src), zy = __shfl_sync(kFull, zside.y, src);
+                const float zz = __shfl_sync(kFull, zside.z, src), zw = __shfl_sync(kFull, zside.w, src);
+                const int comp = ch & 3;
+                const float zv = comp == 0 ? zx : (comp == 1 ? zy : (comp == 2 ? zz : zw));
+                acc2[c] = ((ch < d_out && p.r1) ? __ldg(p.r1 + lrow * p.ld_r + ch) : 0.f) + zv;
+            }
+        }
+#pragma unroll 5
+        for (int d4 = 0; d4 < nvec; ++d4) {
+            const float4 ua = stage[d4];
+            float4 ub = make_float4(0, 0, 0, 0);
+            if (NT == 2) ub = stage[nvec + d4];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float4 w0 = sp0[d4 * cpad + lane + 32 * c];
+                float x = acc1[c];
+                x = fmaf(ua.x, w0.x, x);
+                x = fmaf(ua.y, w0.y, x);
+                x = fmaf(ua.z, w0.z, x);
+                x = fmaf(ua.w, w0.w, x);
+                if (NT == 2) {
+                    const float4 w1 = sp1[d4 * cpad + lane + 32 * c];
+                    if (MODE == kTwoTerms) {
+                        x = fmaf(ub.x, w1.x, x);
+                        x = fmaf(ub.y, w1.y, x);
+                        x = fmaf(ub.z, w1.z, x);
+                        x = fmaf(ub.w, w1.w, x);
+                    } else {
+                        float y = acc2[c];
+                        y = fmaf(ub.x, w1.x, y);
+                        y = fmaf(ub.y, w1.y, y);
+                        y = fmaf(ub.z, w1.z, y);
+                        y = fmaf(ub.w, w1.w, y);
+                        acc2[c] = y;
+                    }
+                }
+                acc1[c] = x;
+            }
+        }
+        __syncwarp();   // the staging buffer is reused by the next row
+
+        // ---- phase 3: activation, LayerNorm, mask, L2 normalise ------------------------------------------------
+        {
+            float emb[NC];
+            float s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                float e = leaky(acc1[c]);
+                if (MODE == kBi || Z) e += leaky(acc2[c]);
+                emb[c] = ch < d_out ? e : 0.f;
+                s1 += emb[c];
+            }
+            const float mean = warp_sum(s1) / (float)d_out;
+            float s2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                const float dlt = ch < d_out ? emb[c] - mean : 0.f;
+                s2 = fmaf(dlt, dlt, s2);
+            }
+            const float rstd = rsqrtf(warp_sum(s2) / (float)d_out + 1e-5f);
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ch = lane + 32 * c;
+                float x = 0.f;
+                if (ch < d_out) {
+                    x = (emb[c] - mean) * rstd * __ldg(p.ln_w + ch) + __ldg(p.ln_b + ch);
+                    if (p.mask) x *= __ldg(p.mask + lrow * d_out + ch);
+                    p.x_out[(int64_t)row * p.ld_x + ch] = x;
+                }
+                emb[c] = x;
+                sq = fmaf(x, x, sq);
+            }
+            if (p.xn_out || p.xn_planes) {
+                const float inv = 1.f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+                const float pscale = p.xn_planes ? __ldg(p.xn_rec + 1) : 1.f;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int ch = lane + 32 * c;
+                    if (ch < d_out) {
+                        const float xn = emb[c] * inv;
+                        if (p.xn_out) p.xn_out[lrow * p.ld_xn + ch] = xn;
+                        if (p.xn_planes) {
+                            const float xs = xn * pscale;
+                            const __half h = __float2half_rn(xs);
+                            const __half l = __float2half_rn(xs - __half2float(h));
+                            p.xn_planes[lrow * p.ld_planes + ch] = h;
+                            p.xn_planes[p.plane_stride + lrow * p.ld_planes + ch] = l;
+                        }
+                    }
+                }
+            }
+        }
+        idx = idx1; rec = rec1; head = head1;
+        idx1 = idx2; rec1 = rec2;
+    }
+}
+
+template <int S, int NC, int MODE>
+int launch_stream(const AggParams& p, cudaStream_t stream) {
+    auto kern = aggregate_stream_kernel<S, NC, MODE>;
+    constexpr int NT = (MODE == kOneTerm || MODE == kBiZ) ? 1 : 2;
+    const size_t z_bytes = MODE == kBiZ ? (size_t)p.d_out * 4 : 0;
+    const size_t smem = (size_t)NT * p.nvec * 32 * NC * 16 +
+                        (size_t)kStreamWarps * (stream_ring(MODE) * (p.nvec * 16 + z_bytes) + (size_t)NT * p.nvec * 16) +
+                        kStreamWarps * stream_ring(MODE) * 8;
+    if (smem > 227 * 1024) return 1;                             // does not fit: the caller falls back
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sm_count(), kStreamWarps * 32, smem, stream>>>(p);
+    LKG_LAUNCH_CHECK("aggregate_stream_kernel");
+    return LKG_OK;
+}
+
+template <int S, int NC>
+int dispatch_stream(int mode, const AggParams& p, cudaStream_t stream) {
+    switch (mode) {
+        case kOneTerm: return launch_stream<S, NC, kOneTerm>(p, stream);
+        case kTwoTerms: return launch_stream<S, NC, kTwoTerms>(p, stream);
+        case kBiZ: return launch_stream<S, NC, kBiZ>(p, stream);
+        default: return launch_stream<S, NC, kBi>(p, stream);
+    }
+}
+
 template <int S, int NC, int MODE>
 int launch(const AggParams& p, int threads, size_t smem, cudaStream_t stream) {
     auto kern = aggregate_kernel<S, NC, MODE>;
@@ -549,10 +890,13 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
                                  const float* r1, const float* r2, int64_t ld_r, const float* ln_weight,
                                  const float* ln_bias, const float* drop_mask, float* x_out, int64_t ld_x,
                                  float* xn_out, int64_t ld_xn, uint16_t* xn_planes, int64_t ld_planes,
-                                 int64_t plane_stride, const float* xn_rec, int64_t local_row_base, void* workspace,
-                                 void* stream_) {
+                                 int64_t plane_stride, const float* xn_rec, int64_t local_row_base, const float* z,
+                                 int64_t ld_z, void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    LKG_REQUIRE(g && ego && pb && ln_weight && ln_bias && x_out && workspace, "null argument");
+    LKG_REQUIRE(g && ego && (pb || z) && ln_weight && ln_bias && x_out && workspace, "null argument");
+    LKG_REQUIRE(!z || (p2 && !pa && !pb && d_out % 4 == 0 && ld_z % 4 == 0 && aligned16(z) && d_in >= 128 && g->row_sched),
+                "a pre-projected sum term (z) needs the bi-interaction product matrix p2, no pa / pb, wide rows and a "
+                "plan with a row schedule");
     LKG_REQUIRE(g->nnz == 0 || a_values != nullptr, "a_values is null");
     LKG_REQUIRE(!xn_planes || xn_rec, "xn_planes needs a scale record");
     LKG_REQUIRE(g->row_begin >= 0 && g->row_begin <= g->row_end && g->row_end <= g->n_entities, "bad row range");
@@ -572,7 +916,14 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     p.d_out = d_out;
     p.nvec = d_in / 4;
     int mode;
-    if (p2) {
+    p.z = z;
+    p.ld_z = ld_z;
+    if (z) {
+        mode = kBiZ;
+        p.p0 = p2;
+        p.p1 = nullptr;
+        p.sum_ego = 0;
+    } else if (p2) {
         mode = kBi;
         p.p0 = pb;
         p.p1 = p2;
@@ -626,6 +977,18 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
 #undef LKG_NARROW_CASE
         }
     }
+
+    // wide rows with a schedule: the shared-memory ring kernel (returns 1 when the shapes do not fit its smem)
+    if (d_in >= 128 && g->row_sched && aligned16(g->row_sched)) {
+        const int slots_w = (p.nvec + 31) / 32, nc_w = (d_out + 31) / 32;
+        int rc = 1;
+        if (slots_w == 2 && nc_w == 1) rc = dispatch_stream<2, 1>(mode, p, stream);
+        if (slots_w == 3 && nc_w == 1) rc = dispatch_stream<3, 1>(mode, p, stream);
+        if (slots_w == 3 && nc_w == 2) rc = dispatch_stream<3, 2>(mode, p, stream);
+        if (slots_w == 4 && nc_w == 1) rc = dispatch_stream<4, 1>(mode, p, stream);
+        if (rc <= 0) return rc;
+    }
+    if (z) LKG_FAIL(LKG_ERR_UNSUPPORTED, "aggregate with a pre-projected sum term: d_in %d d_out %d not supported", d_in, d_out);
 
     const int nt = mode == kOneTerm ? 1 : 2;
     const size_t p_bytes = (size_t)nt * d_in * p.p_stride * sizeof(float);

@@ -53,30 +53,6 @@ __device__ __forceinline__ float tanh_from_exp(float p) {
     return fmaf(-2.f, r, 1.f);
 }
 
-// ---- per-warp ring of gathered rows: one cp.async.bulk (TMA unit, 1-D) per row, completion on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ring_bar_init(uint64_t* bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
-}
-__device__ __forceinline__ void ring_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-
 // S = float4 slots per lane (dim <= 128 * S); kRing = tail rows in flight per warp (bulk copies into shared memory)
 //
 // Software pipeline across rows (every load below is a global round trip of 1-2 us under load, and a warp spends
@@ -144,6 +120,7 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
     int idx1 = __shfl_sync(kFull, fetch_idx(), 0);
     Rec rec1 = load_rec(idx1);
     Head head = load_head(rec);
+    int pre_issued = 0;                              // copies of this row's first chunk issued during the previous row
 
     while (idx < n_rows && rec.e1 > rec.e0) {        // the schedule is sorted by triple count: an empty row ends it
         int idx2 = fetch_idx();                      // row i+2: broadcast and record load after the ring is filled
@@ -177,11 +154,12 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
             }
             // prologue: fill the ring
             const int first = min(cn, kRing);
-            if (lane < first) {
-                const uint32_t slot = (issued + lane) % kRing;
+            const int done = c0 == e0 ? pre_issued : 0;          // the first chunk's copies may already be in flight
+            if (lane >= done && lane < first) {
+                const uint32_t slot = (issued + lane - done) % kRing;
                 ring_issue(ring + slot * row_bytes, ent + (int64_t)my_tail * ld_ent, row_bytes, &bars[slot]);
             }
-            issued += first;
+            issued += first - done;
             if (c0 == e0) {
                 // with this row's copies in flight: the loads of the rows to come, then exp(2 e_h)
                 idx2 = __shfl_sync(kFull, idx2, 0);
@@ -262,6 +240,16 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
                     else atomicAdd(slot, k);
                 }
             }
+        }
+        // the ring is empty: start the next row's first copies now, they land during the softmax and the row switch
+        pre_issued = 0;
+        if (idx1 < n_rows && rec1.e1 > rec1.e0) {
+            pre_issued = min(kRing, min(32, rec1.e1 - rec1.e0));
+            if (lane < pre_issued) {
+                const uint32_t slot = (issued + lane) % kRing;
+                ring_issue(ring + slot * row_bytes, ent + (int64_t)head1.tail * ld_ent, row_bytes, &bars[slot]);
+            }
+            issued += pre_issued;
         }
         if (!in_smem) __threadfence();          // the long-row reductions are performed before other lanes read them
         __syncwarp();

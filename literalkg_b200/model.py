@@ -33,6 +33,16 @@ def _param_key(module: nn.Module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
+_EYE = {}
+
+
+def _identity(n: int, device) -> torch.Tensor:
+    key = (n, str(device))
+    if key not in _EYE:
+        _EYE[key] = torch.eye(n, dtype=torch.float32, device=device)
+    return _EYE[key]
+
+
 def _L2_loss_mean(x):
     return torch.mean(torch.sum(torch.pow(x, 2), dim=1, keepdim=False) / 2.)
 
@@ -140,14 +150,25 @@ class Aggregator(nn.Module):
 
     def run(self, plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, f: Dict[str, Optional[torch.Tensor]],
             r1: Optional[torch.Tensor], r2: Optional[torch.Tensor], x_out: torch.Tensor,
-            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None, rows=None) -> torch.Tensor:
+            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None, rows=None, z=None
+            ) -> torch.Tensor:
         """``rows`` = (begin, end): the head rows this rank owns; r1 / r2 / xn_out / xn_planes then hold those rows
         only, ``ego`` and ``x_out`` stay indexed by the global row."""
         pa = None if fold_ego else f["pa"]
         rb, re = (0, ego.shape[0]) if rows is None else rows
-        return ops.aggregate(plan, a_values, ego, self.out_dim, pa, f["pb"], f["p2"], r1, r2,
+        pb, p2 = f["pb"], f["p2"]
+        if z is not None:
+            # the neighbour sum term arrives pre-projected (z = ego @ Pb, DESIGN.md section 4):
+            #   bi-interaction: the wide kernel gathers z next to the ego rows and only combines the product term;
+            #   gcn / graphsage: nothing but z is gathered -- the layer runs on the d_out-wide z table
+            assert pa is None
+            if p2 is None:
+                ego, z, pb = z, None, _identity(self.out_dim, ego.device)
+            else:
+                pb = None
+        return ops.aggregate(plan, a_values, ego, self.out_dim, pa, pb, p2, r1, r2,
                              self.layer_normalize.weight, self.layer_normalize.bias,
-                             self._drop_mask(re - rb, ego.device), x_out, xn_out, xn_planes, local_row_base=rb)
+                             self._drop_mask(re - rb, ego.device), x_out, xn_out, xn_planes, local_row_base=rb, z=z)
 
     def forward(self, ego_embeddings, A_in, all_layers, lamda, alpha, l):
         """Reference signature (model.py:101): ``A_in`` is a sparse COO tensor, ``all_layers[0]`` the gate
@@ -374,14 +395,10 @@ class LiteralKG(nn.Module):
         cat_planes = _lib.Planes(n_own, xcol + (total - d), dev)
         _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows)
         xn_all = cat_planes.view(xcol, total - d, rec=self._unit_record(dev))
-        if part is not None:
-            part.all_gather_rows(h0_tab)                  # layer 1 gathers arbitrary neighbour rows of h0
-            if self.scale_gat_dim is None:
-                cat[:, :d] = h0
-
         folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
         h0q = None
         offsets: List[int] = []
+        zoff = -1                                         # column of the pre-projected layer-1 sum term in h0q
         if self.use_residual and self.n_layers > 0:
             qkey = tuple(id(f) for f in folds)                     # the fold dicts are cached per parameter version
             if self._h0q_cache is None or self._h0q_cache[0] != qkey:
@@ -392,9 +409,31 @@ class LiteralKG(nn.Module):
                     qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
                     if f["q2"] is not None:
                         qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
-                self._h0q_cache = (qkey, torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, folds)
-            _, wq, cq, offsets, _ = self._h0q_cache
+                # layer 0 again: z = h0 @ Pb, the neighbour sum term projected BEFORE the aggregation
+                # ((A h0) Pb == A (h0 Pb)): 32 more GEMM columns replace a 300 x 32 combine per row, and for
+                # gcn / graphsage the 1 200-byte neighbour gather of layer 1 altogether
+                zcol = off if d >= 128 and folds[0]["pb"].shape[1] % 4 == 0 else -1
+                if zcol >= 0:
+                    qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
+                self._h0q_cache = (qkey, torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, folds, zcol)
+            _, wq, cq, offsets, _, zoff = self._h0q_cache
             h0q = ops.linear([h0_planes], wq, cq)                  # this rank's rows
+
+        c0 = self.aggregator_layers[0].out_dim if self.n_layers > 0 else 0
+        z_tab = None
+        if zoff >= 0:
+            if part is None:
+                z_tab = h0q[:, zoff:zoff + c0]                     # [N, C] view, row index == entity id
+            else:
+                z_tab = torch.empty((n_tab, c0), dtype=torch.float32, device=dev)
+                z_tab[rb:re] = h0q[:, zoff:zoff + c0]
+                part.all_gather_rows(z_tab)
+        needs_h0_rows = self.n_layers > 0 and (z_tab is None or self.aggregation_type == 'bi-interaction')
+        if part is not None:
+            if needs_h0_rows:
+                part.all_gather_rows(h0_tab)              # layer 1 gathers arbitrary neighbour rows of h0
+            if self.scale_gat_dim is None:
+                cat[:, :d] = h0
 
         x = h0_tab
         col = d
@@ -407,7 +446,8 @@ class LiteralKG(nn.Module):
                 r1, r2 = f["c1"], f["c2"]
             x_out = torch.empty((n_tab, c), dtype=torch.float32, device=dev)
             layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
-                      xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows)
+                      xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows,
+                      z=z_tab if k == 0 else None)
             if part is not None and k + 1 < self.n_layers:
                 part.all_gather_rows(x_out)               # the next layer reads every row of this one
             x = x_out

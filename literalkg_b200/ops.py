@@ -178,10 +178,11 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
               pa: Optional[torch.Tensor], pb: torch.Tensor, p2: Optional[torch.Tensor],
               r1: Optional[torch.Tensor], r2: Optional[torch.Tensor],
               ln_weight: torch.Tensor, ln_bias: torch.Tensor, drop_mask: Optional[torch.Tensor],
-              x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None, local_row_base: int = 0
-              ) -> torch.Tensor:
+              x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None, local_row_base: int = 0,
+              z: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases.
-    With a row partition, r1 / r2 / drop_mask / xn_out / xn_planes hold the rows from ``local_row_base`` on."""
+    With a row partition, r1 / r2 / drop_mask / xn_out / xn_planes hold the rows from ``local_row_base`` on.
+    ``z`` (bi-interaction, wide rows): pre-projected sum term ego @ Pb, [N, d_out] view; then pa = pb = None."""
     assert ego.dtype == torch.float32 and ego.stride(1) == 1
     d_in = ego.shape[1]
     ld_r = 0
@@ -192,16 +193,19 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
     if r1 is not None and r2 is not None:
         assert (r1.dim() == r2.dim()) and (r1.dim() == 1 or r1.stride(0) == r2.stride(0))
     same = pa is not None and pa is pb
-    pb_c = _lib.f32c(pb)
+    pb_c = None if pb is None else _lib.f32c(pb)
     pa_c = pb_c if same else (None if pa is None else _lib.f32c(pa))
+    if z is not None:
+        assert z.dtype == torch.float32 and z.stride(1) == 1 and z.shape[1] == d_out and pa is None and pb is None
     p2_c = None if p2 is None else _lib.f32c(p2)
     with _dev_guard(ego, f"aggregate_d{d_in}"):
         _lib.check(_lib.load().lkg_aggregate_fwd(
             plan.byref(), _lib.ptr(a_values), ego.data_ptr(), ego.stride(0), d_in, d_out,
-            _lib.ptr(pa_c), pb_c.data_ptr(), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
+            _lib.ptr(pa_c), _lib.ptr(pb_c), _lib.ptr(p2_c), _lib.ptr(r1), _lib.ptr(r2), ld_r,
             _lib.f32c(ln_weight).data_ptr(), _lib.f32c(ln_bias).data_ptr(), _lib.ptr(drop_mask),
             x_out.data_ptr(), x_out.stride(0), _lib.ptr(xn_out), 0 if xn_out is None else xn_out.stride(0),
-            *_planes_out(xn_planes), int(local_row_base), plan.scratch(), _lib.stream()))
+            *_planes_out(xn_planes), int(local_row_base), _lib.ptr(z), 0 if z is None else z.stride(0),
+            plan.scratch(), _lib.stream()))
     return x_out
 
 
