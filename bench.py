@@ -171,6 +171,7 @@ def algorithmic_bytes(n, e, nnz, r, d, c, layers, bi=True):
     return {"attn_update": att, f"aggregate_d{d}": l1, f"aggregate_d{c}": lk}
 
 
+@torch.no_grad()
 def run_ours(a):
     import torch.distributed as dist
     import literalkg_b200 as L

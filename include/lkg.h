@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LKG_ABI_VERSION 2
+#define LKG_ABI_VERSION 3
 
 typedef enum {
     LKG_OK = 0,
@@ -87,7 +87,11 @@ typedef struct {
     const float* scale[LKG_MAX_SEGMENTS];   /* scale record of each segment (device) */
 } lkg_planes;
 
-typedef enum { LKG_ACT_NONE = 0, LKG_ACT_LEAKY_RELU = 1 } lkg_activation;
+typedef enum {
+    LKG_ACT_NONE = 0,
+    LKG_ACT_LEAKY_RELU = 1,
+    LKG_ACT_ACCUMULATE = 256 /* flag, OR-ed in: out += act(result) (gradient accumulation of the backward pass) */
+} lkg_activation;
 typedef enum { LKG_AGG_GCN = 0, LKG_AGG_GRAPHSAGE = 1, LKG_AGG_BI_INTERACTION = 2 } lkg_aggregator;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -169,11 +173,12 @@ int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t 
 /* Literal gate (gate.py:22-28 / :45-51).  x = (entity | literals...) planes; w_pair = packed planes of
  * the [2*dim, K] matrix with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of output
  * j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]); x_ent = fp32 entity table for the mix
- * out = (1 - z) * x_ent + z * tanh(g). */
+ * out = (1 - z) * x_ent + z * tanh(g).  gz_out (nullable, training): the activated pairs
+ * (tanh g_j, sigmoid z_j) interleaved like w_pair's rows, [m, 2*dim], saved for lkg_gate_bwd. */
 int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
                  int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
                  uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
-                 void* stream);
+                 float* gz_out, int64_t ld_gz, void* stream);
 
 /* ---- one aggregator layer, forward (model.py:101-164 + F.normalize of model.py:305) ----------
  * side = A_in @ ego fused with the combine, LeakyReLU, LayerNorm, optional dropout mask and the
@@ -200,7 +205,51 @@ int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, const float* eg
                                                layer: z = ego @ Pb [N, d_out], e.g. extra columns of the h0 @ Q GEMM;
                                                then o1 = r1[row] + sum_j A[row,j] z[col_j], pa = pb = NULL, and
                                                only P2 is combined in the kernel (wide rows only)*/,
+                      float* o_out /*nullable, training: pre-activations [o1 | o2] of every local row*/, int64_t ld_o,
+                      float* side_out /*nullable, training: side = A @ ego of every local row*/, int64_t ld_side,
                       void* workspace, void* stream);
+
+/* ---- backward of the embedding pass (what loss.backward() replays through model.py:298-314) -------------
+ * Transposed plan: the nnz (head, tail) pairs sorted by (tail, head) as a COO list; t_perm[i] = position of the
+ * pair in agg order (index of its A_in value).  Stable radix sort: bit-exact, deterministic. */
+int lkg_plan_transpose_workspace_bytes(int64_t nnz, size_t* bytes /*host out*/);
+int lkg_plan_transpose(const lkg_graph* g, int32_t* t_tail, int32_t* t_head, int32_t* t_perm,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* out[seg[i], :] += vals[perm ? perm[i] : i] * x[src[i], :] over a COO list sorted by seg (segmented reduction,
+ * equal nnz per worker).  With (t_tail, t_head, t_perm) this is out += A_in^T @ x: the backward of torch.sparse.mm
+ * (model.py:106).  d % 4 == 0, d <= 512. */
+int lkg_spmm_coo(const int32_t* seg, const int32_t* src, const int32_t* perm /*nullable*/, const float* vals,
+                 int64_t nnz, const float* x, int64_t ldx, int32_t d, float* out, int64_t ldo, void* stream);
+/* Row-local backward of one aggregator layer (model.py:108-130, 161-164 and F.normalize of :305):
+ *   dy = dy_in + d normalize(y)^T dyn;  dropout mask;  LayerNorm backward;  LeakyReLU backward of both paths.
+ * y: the layer output, o: the pre-activations saved by lkg_aggregate_fwd ([o1 | o2], has_o2 for
+ * bi-interaction).  Writes d_o = [do1 | do2] and ACCUMULATES dgamma_dbeta[2*c] (LayerNorm weight / bias). */
+int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const float* y, int64_t ld_y, const float* o,
+                       int64_t ld_o, const float* mask /*nullable [n, c]*/, const float* dy_in /*nullable*/,
+                       int64_t ld_dy, const float* dyn /*nullable*/, int64_t ld_dyn, const float* ln_weight,
+                       float* d_o, int64_t ld_do, float* dgamma_dbeta, void* stream);
+/* Product path of bi-interaction (model.py:127-128): V = do2 @ P2^T;  w_out = V * x (the operand of the
+ * A^T gather);  dx (+)= V * side. */
+int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o2, int64_t ld_do, const float* p2 /*[d, c]*/,
+                    const float* x, int64_t ld_x, const float* side, int64_t ld_side, float* w_out, int64_t ld_w,
+                    float* dx, int64_t ld_dx, int32_t accumulate, void* stream);
+/* Parameter gradients: out[i, j] += sum_rows x[row, i] * (x2 ? x2[row, i] : 1) * y[row, j]; x == NULL with dx == 1
+ * gives the column sums of y (bias gradients).  out [dx, cy] is accumulated into (zero it first). */
+int lkg_xt_y(const float* x /*nullable*/, int64_t ld_x, const float* x2 /*nullable*/, int64_t ld_x2, int32_t dx,
+             const float* y, int64_t ld_y, int32_t cy, int64_t n, float* out, int64_t ld_out, void* stream);
+/* The same reduction on the tensor cores: out[dx, cy] += x^T y with both operands given as fp16 hi/lo planes
+ * ([n_rows, k] row-major, single segment; the planes the forward GEMMs already use).  MN-major tcgen05 operands,
+ * split over row ranges, fp32 atomics into out. */
+int lkg_xt_y_planes(const lkg_planes* x, const lkg_planes* y, int64_t n_rows, float* out, int64_t ld_out, void* stream);
+/* out[j] += sum_rows y[row, j]  (bias gradients). */
+int lkg_colsum(const float* y, int64_t ld_y, int64_t n, int32_t c, float* out, void* stream);
+/* Literal gate backward, elementwise part (gate.py:22-28): from dh = d loss / d out and the saved (g, z) pairs:
+ * d_pre (interleaved like w_pair's rows) and the direct entity term d_ent = dh * (1 - z). */
+int lkg_gate_bwd(const float* dh, int64_t ld_dh, const float* gz, int64_t ld_gz, const float* ent, int64_t ld_ent,
+                 int64_t n, int32_t dim, float* d_pre, int64_t ld_pre, float* d_ent, int64_t ld_de, void* stream);
+/* d_pre = grad * LeakyReLU'(out) from the activated output (model.py:311). */
+int lkg_leaky_bwd(const float* grad, int64_t ld_g, const float* out, int64_t ld_out, int64_t n, int32_t c,
+                  float* d_pre, int64_t ld_d, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
 /* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final

@@ -15,15 +15,15 @@ def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
-def gate_apply(module, inputs, out=None, out_planes=None, ent_planes=None, lit_planes=None):
+def gate_apply(module, inputs, out=None, out_planes=None, ent_planes=None, lit_planes=None, packed=None, gz_out=None):
     """Fused literal gate forward for ``Gate`` / ``GateMul`` (gate.py:22-28, 45-51).  The A operand is the K
     concatenation (entity | literals); ``ent_planes`` / ``lit_planes`` let the caller reuse cached fp16 planes."""
     x_ent = inputs[0]
     with torch.no_grad():
-        w_pair, b_pair = module.packed()
+        w_pair, b_pair = module.packed() if packed is None else packed
         if ent_planes is None:
             ent_planes = ops.split_planes(x_ent.detach())
         if lit_planes is None:
             lits = [x.detach().float() for x in inputs[1:]]
             lit_planes = ops.split_planes(lits[0] if len(lits) == 1 else torch.cat(lits, dim=1))
-        return ops.gate([ent_planes, lit_planes], w_pair, b_pair, x_ent.detach(), out, out_planes)
+        return ops.gate([ent_planes, lit_planes], w_pair, b_pair, x_ent.detach(), out, out_planes, gz_out=gz_out)

@@ -49,6 +49,10 @@ struct AggParams {
     int64_t ld_z;      //       o1 = r1 + sum_j A[row, j] z[col_j] needs no combine matrix in the kernel
     int64_t local_row_base;   // r1 / r2 / mask / xn_out / xn_planes are indexed by (row - local_row_base): the
                               // row partition's local buffers; ego and x_out are indexed by the global row
+    float* o_out;      // training: saved pre-activations [o1 | o2] per local row (nullable), row stride ld_o
+    int64_t ld_o;
+    float* side_out;   // training: saved side = A @ ego per local row (nullable), row stride ld_side
+    int64_t ld_side;
 };
 
 template <int S, int NC, int MODE>
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
                 const int v = lane + 32 * s;
                 if (v < nvec) {
                     const float4 sd = side[s];
+                    if (p.side_out)
+                        reinterpret_cast<float4*>(p.side_out + (row - p.local_row_base) * p.ld_side)[v] = sd;
                     float4 eg = make_float4(0, 0, 0, 0);
                     if (MODE != kOneTerm || p.sum_ego) eg = __ldg(reinterpret_cast<const float4*>(erow) + v);
                     float4 t0, t1;
@@ -213,6 +219,10 @@ __global__ void __launch_bounds__(512, 1) aggregate_kernel(AggParams p) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int ch = lane + 32 * c;
+                if (p.o_out && ch < d_out) {
+                    p.o_out[lrow * p.ld_o + ch] = acc1[rr][c];
+                    if (MODE == kBi) p.o_out[lrow * p.ld_o + d_out + ch] = acc2[rr][c];
+                }
                 float e = leaky(acc1[rr][c]);
                 if (MODE == kBi) e += leaky(acc2[rr][c]);
                 emb[c] = ch < d_out ? e : 0.f;
@@ -362,6 +372,7 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
         float4 eg = make_float4(0, 0, 0, 0);
         if (live && (MODE != kOneTerm || p.sum_ego))
             eg = __ldg(reinterpret_cast<const float4*>(p.ego + (int64_t)row * p.ld_ego) + gl);
+        if (p.side_out && live) reinterpret_cast<float4*>(p.side_out + lrow * p.ld_side)[gl] = side;
         float4 t0, t1;
         if (MODE == kTwoTerms) {
             t0 = eg;
@@ -416,6 +427,10 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int ch = 4 * (gl + LPR * i);
+            if (p.o_out && live && ch < d_out) {
+                *reinterpret_cast<float4*>(p.o_out + lrow * p.ld_o + ch) = acc1[i];
+                if (MODE == kBi) *reinterpret_cast<float4*>(p.o_out + lrow * p.ld_o + d_out + ch) = acc2[i];
+            }
             float4 e = make_float4(leaky(acc1[i].x), leaky(acc1[i].y), leaky(acc1[i].z), leaky(acc1[i].w));
             if (MODE == kBi) {
                 e.x += leaky(acc2[i].x);
@@ -701,6 +716,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
             const int v = lane + 32 * s;
             if (v < nvec) {
                 const float4 sd = side[s], eg = head.eg[s];
+                if (p.side_out) reinterpret_cast<float4*>(p.side_out + lrow * p.ld_side)[v] = sd;
                 float4 t0, t1;
                 if (Z) {
                     t0 = make_float4(eg.x * sd.x, eg.y * sd.y, eg.z * sd.z, eg.w * sd.w);
@@ -775,6 +791,10 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int ch = lane + 32 * c;
+                if (p.o_out && ch < d_out) {     // kBiZ: acc1 is the product path (o2), acc2 the sum path (o1)
+                    p.o_out[lrow * p.ld_o + (Z ? d_out : 0) + ch] = acc1[c];
+                    if (MODE == kBi || Z) p.o_out[lrow * p.ld_o + (Z ? 0 : d_out) + ch] = acc2[c];
+                }
                 float e = leaky(acc1[c]);
                 if (MODE == kBi || Z) e += leaky(acc2[c]);
                 emb[c] = ch < d_out ? e : 0.f;
@@ -891,7 +911,8 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
                                  const float* ln_bias, const float* drop_mask, float* x_out, int64_t ld_x,
                                  float* xn_out, int64_t ld_xn, uint16_t* xn_planes, int64_t ld_planes,
                                  int64_t plane_stride, const float* xn_rec, int64_t local_row_base, const float* z,
-                                 int64_t ld_z, void* workspace, void* stream_) {
+                                 int64_t ld_z, float* o_out, int64_t ld_o, float* side_out, int64_t ld_side,
+                                 void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(g && ego && (pb || z) && ln_weight && ln_bias && x_out && workspace, "null argument");
     LKG_REQUIRE(!z || (p2 && !pa && !pb && d_out % 4 == 0 && ld_z % 4 == 0 && aligned16(z) && d_in >= 128 && g->row_sched),
@@ -954,6 +975,12 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     p.ld_planes = ld_planes;
     p.plane_stride = plane_stride;
     p.local_row_base = local_row_base;
+    LKG_REQUIRE(!o_out || (ld_o % 4 == 0 && aligned16(o_out)), "o_out rows must be 16-byte aligned");
+    LKG_REQUIRE(!side_out || (ld_side % 4 == 0 && aligned16(side_out)), "side_out rows must be 16-byte aligned");
+    p.o_out = o_out;
+    p.ld_o = ld_o;
+    p.side_out = side_out;
+    p.ld_side = ld_side;
     p.counter = static_cast<int*>(workspace);
     // lane c reads sp[d * ps + c]: any stride is conflict free for 32 consecutive channels; pad to a
     // multiple of 4 floats to keep rows 16-byte aligned

@@ -57,6 +57,9 @@ struct TcParams {
     const float* mul_a;                 // scale records whose [2] (= 1/scale) the accumulator is multiplied by:
     const float* mul_b;                 //   mul_b = packed weight (1/S) or tails; mul_a = heads (score only), nullable
     const float* out_rec;               // scale record of out_planes
+    float* gz_out;                      // gate, training: activated (tanh g, sigmoid z) pairs [m, n] (nullable)
+    int64_t ld_gz;
+    int accumulate;                     // linear: out += result
 };
 
 __device__ __forceinline__ uint32_t order_enc(float f) {
@@ -101,11 +104,26 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
 #pragma unroll
             for (int j = 0; j < 16; ++j) b[j] = col0 + j < p.n ? __ldg(p.bias + col0 + j) : 0.f;
         }
+        float gz[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float g = tanh_acc(acc[2 * j] + b[2 * j]);
             const float z = sigmoid_acc(acc[2 * j + 1] + b[2 * j + 1]);
+            gz[2 * j] = g;
+            gz[2 * j + 1] = z;
             o[j] = (1.f - z) * e[j] + z * g;
+        }
+        if (p.gz_out) {
+            float* grow = p.gz_out + row * p.ld_gz + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(grow) & 15u) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(grow + j) = make_float4(gz[j], gz[j + 1], gz[j + 2], gz[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (col0 + j < p.n) grow[j] = gz[j];
+            }
         }
         if (full && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
             reinterpret_cast<float4*>(orow)[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -150,6 +168,11 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
             }
         }
         float* dst = p.out + row * p.ldo + col0;
+        if (EPI == kEpiLinear && p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.n) o[j] += dst[j];
+        }
         if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -680,7 +703,8 @@ extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* 
     if (m == 0) return LKG_OK;
     TcParams p{};
     p.bias = bias;
-    p.act = activation;
+    p.act = activation & 0xff;
+    p.accumulate = (activation & LKG_ACT_ACCUMULATE) != 0;
     p.out = out;
     p.ldo = ldo;
     p.out_planes = (__half*)out_planes;
@@ -693,8 +717,9 @@ extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* 
 extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,
                             int32_t dim, const float* x_ent, int64_t ld_ent, float* out, int64_t ldo,
                             uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
-                            void* stream_) {
+                            float* gz_out, int64_t ld_gz, void* stream_) {
     LKG_REQUIRE(bias_pair && x_ent && out && dim > 0 && ldo >= dim, "bad gate arguments");
+    LKG_REQUIRE(!gz_out || ld_gz >= 2 * dim, "bad gz_out stride");
     LKG_REQUIRE(!out_planes || out_rec, "out_planes needs a scale record");
     if (m == 0) return LKG_OK;
     TcParams p{};
@@ -707,6 +732,8 @@ extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_
     p.out_rec = out_rec;
     p.x_ent = x_ent;
     p.ld_ent = ld_ent;
+    p.gz_out = gz_out;
+    p.ld_gz = ld_gz;
     return launch_tc<kEpiGate>(p, x, m, w_pair, 2 * dim, (cudaStream_t)stream_);
 }
 

@@ -44,6 +44,11 @@ class GateMul(nn.Module):
                                                        self.gate_txt_lit.weight), self.g.bias, self.gate_bias))
         return self._packed[1]
 
+    def pair(self):
+        """The interleaved (g, z) weight and bias built under autograd (training path)."""
+        return _pair(self.g.weight, (self.gate_ent.weight, self.gate_num_lit.weight, self.gate_txt_lit.weight),
+                     self.g.bias, self.gate_bias)
+
     def forward(self, x_ent, x_lit_num, x_lit_txt, out=None, **planes):
         from .autograd import gate_apply
         return gate_apply(self, (x_ent, x_lit_num, x_lit_txt), out, **planes)
@@ -69,6 +74,9 @@ class Gate(nn.Module):
             self._packed = (key, _pair(self.g.weight, (self.gate_ent.weight, self.gate_lit.weight), self.g.bias,
                                        self.gate_bias))
         return self._packed[1]
+
+    def pair(self):
+        return _pair(self.g.weight, (self.gate_ent.weight, self.gate_lit.weight), self.g.bias, self.gate_bias)
 
     def forward(self, x_ent, x_lit, out=None, **planes):
         from .autograd import gate_apply

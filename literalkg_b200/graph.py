@@ -77,6 +77,7 @@ class GraphPlan:
         self._part_order = self._part_sched = self._part_range = None
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
         self._attn_ws = None
+        self._transposed = None
 
     # -- constructors ---------------------------------------------------------------------------
     @classmethod
@@ -119,6 +120,23 @@ class GraphPlan:
 
     def scratch(self) -> int:
         return self._scratch.data_ptr()
+
+    def transposed(self):
+        """(t_tail, t_head, t_perm): the unique (h, t) pairs as a COO list sorted by (tail, head); t_perm = position of
+        the pair in agg order.  What the backward of ``A_in @ x`` gathers over (built on first use, cached)."""
+        if self._transposed is None:
+            lib = _lib.load()
+            i32 = dict(dtype=torch.int32, device=self.device)
+            m = max(self.nnz, 1)
+            t_tail, t_head, t_perm = torch.empty(m, **i32), torch.empty(m, **i32), torch.empty(m, **i32)
+            nbytes = C.c_size_t(0)
+            _lib.check(lib.lkg_plan_transpose_workspace_bytes(self.nnz, C.byref(nbytes)))
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.lkg_plan_transpose(self.byref(), t_tail.data_ptr(), t_head.data_ptr(), t_perm.data_ptr(),
+                                                  ws.data_ptr(), nbytes.value, _lib.stream()))
+            self._transposed = tuple(x[:self.nnz] for x in (t_tail, t_head, t_perm))
+        return self._transposed
 
     def attn_workspace(self, dim: int) -> int:
         """Workspace of lkg_attn_update: row counter + the exp(2 e_r) table."""

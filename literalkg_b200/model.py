@@ -91,13 +91,15 @@ class Aggregator(nn.Module):
         self.weight.data.uniform_(-stdv, stdv)
 
     # ---- parameter folding -------------------------------------------------
-    def folded(self, lamda: float, alpha: float, l: int) -> Dict[str, Optional[torch.Tensor]]:
+    def folded(self, lamda: float, alpha: float, l: int, differentiable: bool = False
+               ) -> Dict[str, Optional[torch.Tensor]]:
         """linear(residual(hi)) == hi @ P + h0 @ Q + c with  M = (1-b) + b*W,  b = ln(lamda/l + 1)
         (model.py:90-99): P = (1-a) M W_lin^T, Q = a W_h0^T M W_lin^T, c = a b_h0 M W_lin^T + b_lin.
         Formed in float64 from the live parameters, returned in fp32.  Keys: pa, pb, p2 ([d_in, d_out]),
-        q1, q2 ([embed_dim, d_out] or None), c1, c2 ([d_out])."""
+        q1, q2 ([embed_dim, d_out] or None), c1, c2 ([d_out]).  ``differentiable``: build the fold under autograd
+        (no cache) so that gradients w.r.t. P / Q / c flow on to the layer's parameters."""
         key = (float(lamda), float(alpha), int(l), _param_key(self))
-        if self._fold_cache is not None and self._fold_cache[0] == key:
+        if not differentiable and self._fold_cache is not None and self._fold_cache[0] == key:
             return self._fold_cache[1]
         dd = torch.float64
         t = self.aggregator_type
@@ -139,7 +141,8 @@ class Aggregator(nn.Module):
             res[k] = None if v is None else v.float().contiguous()
         if res["pa"] is not None and out["pa"] is out["pb"]:
             res["pa"] = res["pb"]                                      # keep identity: "sum" mode of the kernel
-        self._fold_cache = (key, res)       # derived from the parameters only: reused until one of them changes
+        if not differentiable:
+            self._fold_cache = (key, res)   # derived from the parameters only: reused until one of them changes
         return res
 
     def _drop_mask(self, n: int, device) -> Optional[torch.Tensor]:
@@ -150,13 +153,22 @@ class Aggregator(nn.Module):
 
     def run(self, plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, f: Dict[str, Optional[torch.Tensor]],
             r1: Optional[torch.Tensor], r2: Optional[torch.Tensor], x_out: torch.Tensor,
-            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None, rows=None, z=None
-            ) -> torch.Tensor:
+            xn_out: Optional[torch.Tensor], fold_ego: bool = False, xn_planes=None, rows=None, z=None,
+            saved: Optional[dict] = None) -> torch.Tensor:
         """``rows`` = (begin, end): the head rows this rank owns; r1 / r2 / xn_out / xn_planes then hold those rows
-        only, ``ego`` and ``x_out`` stay indexed by the global row."""
+        only, ``ego`` and ``x_out`` stay indexed by the global row.  ``saved`` (training): receives the dropout
+        mask, the pre-activations and (bi-interaction) side = A @ ego for the backward pass."""
         pa = None if fold_ego else f["pa"]
         rb, re = (0, ego.shape[0]) if rows is None else rows
         pb, p2 = f["pb"], f["p2"]
+        mask = self._drop_mask(re - rb, ego.device)
+        o_out = side_out = None
+        if saved is not None:
+            nt = 2 if p2 is not None else 1
+            o_out = torch.empty((re - rb, nt * self.out_dim), dtype=torch.float32, device=ego.device)
+            if p2 is not None:
+                side_out = torch.empty((re - rb, ego.shape[1]), dtype=torch.float32, device=ego.device)
+            saved.update(mask=mask, o=o_out, side=side_out)
         if z is not None:
             # the neighbour sum term arrives pre-projected (z = ego @ Pb, DESIGN.md section 4):
             #   bi-interaction: the wide kernel gathers z next to the ego rows and only combines the product term;
@@ -168,7 +180,7 @@ class Aggregator(nn.Module):
                 pb = None
         return ops.aggregate(plan, a_values, ego, self.out_dim, pa, pb, p2, r1, r2,
                              self.layer_normalize.weight, self.layer_normalize.bias,
-                             self._drop_mask(re - rb, ego.device), x_out, xn_out, xn_planes, local_row_base=rb, z=z)
+                             mask, x_out, xn_out, xn_planes, local_row_base=rb, z=z, o_out=o_out, side_out=side_out)
 
     def forward(self, ego_embeddings, A_in, all_layers, lamda, alpha, l):
         """Reference signature (model.py:101): ``A_in`` is a sparse COO tensor, ``all_layers[0]`` the gate
@@ -195,6 +207,29 @@ class Aggregator(nn.Module):
             plan = GraphPlan.from_coo(A_in._indices(), A_in.shape[0])
             self._plan_cache = (*key, plan, plan.import_values(A_in._values()))
         return self._plan_cache[2], self._plan_cache[3]
+
+
+class _GatEmbeddingsFn(torch.autograd.Function):
+    """Full-graph embedding pass as one autograd node: forward = the inference kernels (+ saved activations),
+    backward = csrc/backward.cu.  ``leaves`` only tie the node into the graph; values travel in ``pre``."""
+
+    @staticmethod
+    def forward(ctx, model, pre, *leaves):
+        keep: dict = {}
+        out = model._gat_embeddings_native(keep=keep, pre=pre)
+        if getattr(model, "debug_keep_activations", False):      # tests: sign pattern of the LeakyReLU inputs
+            model._debug_keep = keep
+        ctx.model, ctx.pre, ctx.keep = model, pre, keep
+        ctx.present = [t is not None for t in leaves]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        with torch.no_grad():
+            grads = ctx.model._gat_backward(ctx.keep, ctx.pre, g_out)
+        ctx.keep = None
+        assert len(grads) == len(ctx.present)
+        return (None, None, *[g if has else None for g, has in zip(grads, ctx.present)])
 
 
 class LiteralKG(nn.Module):
@@ -323,23 +358,28 @@ class LiteralKG(nn.Module):
             self._unit_rec = ops.scale_from_bound(1.0, dev)
         return self._unit_rec
 
-    def gate_embeddings(self, out: Optional[torch.Tensor] = None, planes_window=None, rows=None):
+    def _gate_module(self):
+        """(gate module or None, its literal tables) for the configured literal kinds (model.py:265-279)."""
+        if self.args.use_num_lit and self.args.use_txt_lit:
+            return self.emb_mul_lit, (self._literal("numerical_literals_embed"), self._literal("text_literals_embed"))
+        if self.args.use_num_lit:
+            return self.emb_num_lit, (self._literal("numerical_literals_embed"),)
+        if self.args.use_txt_lit:
+            return self.emb_txt_lit, (self._literal("text_literals_embed"),)
+        return None, ()
+
+    def gate_embeddings(self, out: Optional[torch.Tensor] = None, planes_window=None, rows=None, packed=None,
+                        gz_out=None):
         """model.py:265-279.  ``planes_window``: optional (Planes, col, k) column window that receives the scaled
         fp16 hi/lo copy of the result (A operand of the GEMMs that follow).  ``rows`` = (begin, end): only these
-        entity rows (the gate is row local; used by the row partition)."""
+        entity rows (the gate is row local; used by the row partition).  ``packed`` / ``gz_out``: training path
+        (interleaved weights built under autograd by the caller, saved activations for the backward)."""
         ent = self.entity_embed.weight
         dev = self._param_device()
         sl = slice(None) if rows is None else slice(rows[0], rows[1])
         with torch.no_grad():
             ent_rows = ent.detach()[sl]
-            gate_mod, tables = None, ()
-            if self.args.use_num_lit and self.args.use_txt_lit:
-                gate_mod = self.emb_mul_lit
-                tables = (self._literal("numerical_literals_embed"), self._literal("text_literals_embed"))
-            elif self.args.use_num_lit:
-                gate_mod, tables = self.emb_num_lit, (self._literal("numerical_literals_embed"),)
-            elif self.args.use_txt_lit:
-                gate_mod, tables = self.emb_txt_lit, (self._literal("text_literals_embed"),)
+            gate_mod, tables = self._gate_module()
             if gate_mod is not None:
                 ent_planes = ops.split_planes(ent_rows)
                 out_planes = None
@@ -347,8 +387,11 @@ class LiteralKG(nn.Module):
                     # |gate output| <= max(1, max|entity|): convex mix of the entity row and a tanh
                     base, col, k = planes_window
                     out_planes = base.view(col, k, rec=ops.scale_from_bound(1.0, dev, other=ent_planes.rec))
+                lit_planes = self._literal_planes(tables, rows)
+                if gz_out is not None:
+                    self._gate_operands = (ent_planes, lit_planes)       # reused by the backward pass
                 res = gate_mod(ent_rows, *[t[sl] for t in tables], out=out, out_planes=out_planes,
-                               ent_planes=ent_planes, lit_planes=self._literal_planes(tables, rows))
+                               ent_planes=ent_planes, lit_planes=lit_planes, packed=packed, gz_out=gz_out)
                 return (res, out_planes) if planes_window is not None else res
             if out is not None:
                 out.copy_(ent_rows)
@@ -364,6 +407,8 @@ class LiteralKG(nn.Module):
     def gat_embeddings(self, gather: bool = True):
         """model.py:298-314.  Row partitioned: ``gather=False`` returns this rank's rows only (what the sharded
         scoring consumes); the default all-gathers the [N, G] result like the reference returns it."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._gat_embeddings_autograd()
         with torch.no_grad():
             out = self._gat_embeddings_native()
             part = self._part
@@ -373,7 +418,28 @@ class LiteralKG(nn.Module):
             full[part.begin:part.end] = out
             return part.all_gather_rows(full)[:self.n_entities]
 
-    def _gat_embeddings_native(self, keep: Optional[dict] = None) -> torch.Tensor:
+    def _stack_q(self, folds):
+        """The h0 @ Q GEMM of all layers as ONE stacked weight: rows = [layer 0: q1 + pa | q2 | layer 1: q1 | q2 ...
+        | z columns = layer 0's pb].  Returns (wq [cols, embed_dim], cq [cols], offsets, zcol)."""
+        d = self.embed_dim
+        qs, cs, off, offsets = [], [], 0, []
+        for k, f in enumerate(folds):
+            q1 = f["q1"] + f["pa"] if k == 0 else f["q1"]      # layer 0: ego == h0, fold ego @ Pa into h0 @ Q
+            offsets.append(off)
+            qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
+            if f["q2"] is not None:
+                qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
+        # layer 0 again: z = h0 @ Pb, the neighbour sum term projected BEFORE the aggregation
+        # ((A h0) Pb == A (h0 Pb)): 32 more GEMM columns replace a 300 x 32 combine per row, and for
+        # gcn / graphsage the 1 200-byte neighbour gather of layer 1 altogether
+        zcol = off if d >= 128 and folds[0]["pb"].shape[1] % 4 == 0 else -1
+        if zcol >= 0:
+            qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
+        return torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, zcol
+
+    def _gat_embeddings_native(self, keep: Optional[dict] = None, pre: Optional[dict] = None) -> torch.Tensor:
+        """``pre`` (training): {folds, wq, cq, offsets, zcol, packed} built under autograd by the caller (detached
+        values are used here); ``keep`` then receives what the backward pass needs."""
         dev = self._param_device()
         plan, a_values = self._current_plan()
         n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
@@ -393,31 +459,27 @@ class LiteralKG(nn.Module):
         # (|x| <= 1); the second window starts on a 16-byte boundary.
         xcol = (d + 7) // 8 * 8
         cat_planes = _lib.Planes(n_own, xcol + (total - d), dev)
-        _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows)
+        gz = None
+        if keep is not None and self._gate_module()[0] is not None:
+            gz = torch.empty((n_own, 2 * d), dtype=torch.float32, device=dev)      # activated (g, z) pairs
+        _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows,
+                                            packed=None if pre is None else pre["packed"], gz_out=gz)
         xn_all = cat_planes.view(xcol, total - d, rec=self._unit_record(dev))
-        folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
         h0q = None
         offsets: List[int] = []
         zoff = -1                                         # column of the pre-projected layer-1 sum term in h0q
-        if self.use_residual and self.n_layers > 0:
-            qkey = tuple(id(f) for f in folds)                     # the fold dicts are cached per parameter version
-            if self._h0q_cache is None or self._h0q_cache[0] != qkey:
-                qs, cs, off = [], [], 0
-                for k, f in enumerate(folds):
-                    q1 = f["q1"] + f["pa"] if k == 0 else f["q1"]  # layer 0: ego == h0, fold ego @ Pa into h0 @ Q
-                    offsets.append(off)
-                    qs.append(q1); cs.append(f["c1"]); off += q1.shape[1]
-                    if f["q2"] is not None:
-                        qs.append(f["q2"]); cs.append(f["c2"]); off += f["q2"].shape[1]
-                # layer 0 again: z = h0 @ Pb, the neighbour sum term projected BEFORE the aggregation
-                # ((A h0) Pb == A (h0 Pb)): 32 more GEMM columns replace a 300 x 32 combine per row, and for
-                # gcn / graphsage the 1 200-byte neighbour gather of layer 1 altogether
-                zcol = off if d >= 128 and folds[0]["pb"].shape[1] % 4 == 0 else -1
-                if zcol >= 0:
-                    qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
-                self._h0q_cache = (qkey, torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, folds, zcol)
-            _, wq, cq, offsets, _, zoff = self._h0q_cache
-            h0q = ops.linear([h0_planes], wq, cq)                  # this rank's rows
+        if pre is not None:
+            folds, wq, cq, offsets, zoff = pre["folds"], pre["wq"], pre["cq"], pre["offsets"], pre["zcol"]
+            if wq is not None:
+                h0q = ops.linear([h0_planes], wq, cq)
+        else:
+            folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
+            if self.use_residual and self.n_layers > 0:
+                qkey = tuple(id(f) for f in folds)                 # the fold dicts are cached per parameter version
+                if self._h0q_cache is None or self._h0q_cache[0] != qkey:
+                    self._h0q_cache = (qkey, *self._stack_q(folds), folds)
+                _, wq, cq, offsets, zoff, _ = self._h0q_cache
+                h0q = ops.linear([h0_planes], wq, cq)              # this rank's rows
 
         c0 = self.aggregator_layers[0].out_dim if self.n_layers > 0 else 0
         z_tab = None
@@ -445,20 +507,190 @@ class LiteralKG(nn.Module):
             else:
                 r1, r2 = f["c1"], f["c2"]
             x_out = torch.empty((n_tab, c), dtype=torch.float32, device=dev)
+            saved = None
+            if keep is not None:
+                saved = {}
+                keep.setdefault("layers", []).append(saved)
+                saved.update(x=x, y=x_out)
             layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
                       xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows,
-                      z=z_tab if k == 0 else None)
+                      z=z_tab if k == 0 else None, saved=saved)
             if part is not None and k + 1 < self.n_layers:
                 part.all_gather_rows(x_out)               # the next layer reads every row of this one
             x = x_out
             col += c
         plan.set_row_range(0, n)
         if keep is not None:
-            keep["cat"] = cat
+            keep.update(cat=cat, h0=h0, gz=gz, plan=plan, a_values=a_values, h0_planes=h0_planes, xn_all=xn_all,
+                        gate_operands=getattr(self, "_gate_operands", None))
+            self._gate_operands = None
         if self.scale_gat_dim is not None:
             segs = [h0_planes] + ([xn_all] if total > d else [])
-            return ops.linear(segs, self.linear_gat.weight, self.linear_gat.bias, _lib.ACT_LEAKY_RELU)
+            out = ops.linear(segs, self.linear_gat.weight.detach(), self.linear_gat.bias.detach(), _lib.ACT_LEAKY_RELU)
+            if keep is not None:
+                keep["out"] = out
+            return out
         return cat
+
+    # ---- training path: the same forward kernels + the backward kernels of csrc/backward.cu ---------------------
+    _FOLD_KEYS = ("pa", "pb", "p2", "c1", "c2")
+
+    def _gat_embeddings_autograd(self) -> torch.Tensor:
+        """gat_embeddings with gradient support (what pre_training / fine_tuning differentiate, model.py:298-314).
+        The parameter folds and the interleaved gate weight are built under autograd from the
+        live parameters, so the kernels only produce gradients w.r.t. the folded tensors and torch chains them on
+        to linear / linear_h0 / weight / g / gate_* (tiny d x d matrix products)."""
+        if self._part is not None and self._part.world > 1:
+            raise NotImplementedError("the backward pass is single-GPU in this round: call set_partition(None) to train")
+        folds = [layer.folded(self.lamda, self.alpha, k + 1, differentiable=True)
+                 for k, layer in enumerate(self.aggregator_layers)]
+        wq = cq = None
+        offsets, zcol = [], -1
+        if self.use_residual and self.n_layers > 0:
+            wq, cq, offsets, zcol = self._stack_q(folds)
+        gate_mod, _ = self._gate_module()
+        w_pair = b_pair = None
+        if gate_mod is not None:
+            w_pair, b_pair = gate_mod.pair()
+        leaves: List[Optional[torch.Tensor]] = [self.entity_embed.weight, w_pair, b_pair, wq, cq]
+        for k, (layer, f) in enumerate(zip(self.aggregator_layers, folds)):
+            leaves += [f[key] for key in self._FOLD_KEYS]
+            leaves += [layer.layer_normalize.weight, layer.layer_normalize.bias]
+        if self.scale_gat_dim is not None:
+            leaves += [self.linear_gat.weight, self.linear_gat.bias]
+        det = lambda t: None if t is None else t.detach()
+        pre = dict(folds=[{k_: det(v) for k_, v in f.items()} for f in folds], wq=det(wq), cq=det(cq),
+                   offsets=offsets, zcol=zcol, packed=None if w_pair is None else (det(w_pair), det(b_pair)))
+        for f, fd in zip(folds, pre["folds"]):
+            if f["pa"] is not None and f["pa"] is f["pb"]:
+                fd["pa"] = fd["pb"]                       # keep the identity the kernels dispatch on
+        return _GatEmbeddingsFn.apply(self, pre, *leaves)
+
+    def _gat_backward(self, keep: dict, pre: dict, g_out: torch.Tensor) -> List[Optional[torch.Tensor]]:
+        """Gradients w.r.t. the leaves of ``_gat_embeddings_autograd`` (same order)."""
+        dev = g_out.device
+        n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
+        L = self.n_layers
+        plan, a_values = keep["plan"], keep["a_values"]
+        folds, wq, offsets, zcol = pre["folds"], pre["wq"], pre["offsets"], pre["zcol"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        colsum = ops.colsum
+        h0_planes = keep["h0_planes"]
+        grads: List[Optional[torch.Tensor]] = []
+        g_out = g_out if (g_out.dtype == torch.float32 and g_out.stride(1) == 1) else _lib.f32c(g_out)
+
+        # ---- linear_gat + LeakyReLU (model.py:311) ----
+        g_wg = g_bg = None
+        if self.scale_gat_dim is not None:
+            dpre = ops.leaky_bwd(g_out, keep["out"])
+            dpre_pl = ops.split_planes(dpre)
+            g_wg = torch.zeros_like(self.linear_gat.weight)                     # [G, T] = dpre^T [h0 | xn_1 | ...]
+            ops.xt_y_planes(dpre_pl, h0_planes, out=g_wg[:, :d])
+            if total > d:
+                ops.xt_y_planes(dpre_pl, keep["xn_all"], out=g_wg[:, d:])
+            g_bg = colsum(dpre)
+            dcat = ops.linear([dpre_pl], self.linear_gat.weight.detach().t().contiguous(), None)
+            del dpre, dpre_pl
+        else:
+            dcat = g_out.clone()
+        # accumulates every contribution to d loss / d h0 in place (a strided view when its rows stay 16-byte aligned)
+        dh0 = dcat[:, :d] if dcat.stride(0) % 4 == 0 else dcat[:, :d].contiguous()
+        h0 = keep["h0"]
+
+        # ---- aggregator layers, last to first (model.py:101-164) ----
+        residual = wq is not None
+        dmat = None
+        if residual:
+            dmat = torch.empty((n, wq.shape[0]), **f32)        # [dO of every layer | t1 of layer 0]: d (h0 @ Q)
+        layer_grads = [None] * L
+        dy_in = None
+        col = d + sum(layer.out_dim for layer in self.aggregator_layers)
+        for k in reversed(range(L)):
+            layer, f, sv = self.aggregator_layers[k], folds[k], keep["layers"][k]
+            c, dk = layer.out_dim, layer.in_dim
+            col -= c
+            x_k, y_k = sv["x"], sv["y"]
+            has_o2 = f["p2"] is not None
+            nt = 2 if has_o2 else 1
+            d_o = dmat[:, offsets[k]:offsets[k] + nt * c] if residual else torch.empty((n, nt * c), **f32)
+            dgb = torch.zeros(2 * c, **f32)
+            ops.layer_bwd_rows(y_k, sv["o"], has_o2, sv["mask"], dy_in, dcat[:, col:col + c],
+                               layer.layer_normalize.weight.detach(), d_o, dgb)
+            do1 = d_o[:, :c]
+            do2 = d_o[:, c:] if has_o2 else None
+            fold_ego = residual and k == 0                     # ego @ Pa lives inside h0 @ Q
+            z_path = fold_ego and zcol >= 0                    # ... and so does the projected sum term
+            t1 = dmat[:, zcol:zcol + c] if z_path else torch.empty((n, c), **f32)
+            t1.zero_()
+            ops.spmm_t(plan, a_values, do1, t1)                # A^T do1: (A x) Pb backward without the wide gather
+            g = dict.fromkeys(self._FOLD_KEYS)
+            use_pa = f["pa"] is not None and not fold_ego
+            use_pb = not z_path
+            do1_pl = ops.split_planes(do1) if use_pa else None
+            t1_pl = ops.split_planes(t1) if use_pb else None
+            if use_pa or use_pb:
+                xk_pl = h0_planes if k == 0 else ops.split_planes(x_k)
+            if use_pa:
+                g["pa"] = ops.xt_y_planes(xk_pl, do1_pl)
+            if use_pb:
+                g["pb"] = ops.xt_y_planes(xk_pl, t1_pl)        # (A x)^T do1 == x^T (A^T do1)
+            if has_o2:
+                g["p2"] = ops.xt_y(x_k, do2, x2=sv["side"])
+            if not residual:
+                g["c1"] = colsum(do1)
+                if has_o2:
+                    g["c2"] = colsum(do2)
+            layer_grads[k] = (g, dgb[:c], dgb[c:])
+            # d loss / d x_k = do1 Pa^T + t1 Pb^T + (do2 P2^T) * side + A^T ((do2 P2^T) * x_k)
+            dx = dh0 if k == 0 else torch.empty((n, dk), **f32)
+            acc = _lib.ACT_ACCUMULATE if k == 0 else _lib.ACT_NONE
+            segs, ws = [], []
+            if use_pa:
+                segs.append(do1_pl); ws.append(f["pa"])
+            if use_pb:
+                segs.append(t1_pl); ws.append(f["pb"])
+            if segs:
+                ops.linear(segs, torch.cat(ws, dim=1).contiguous(), None, acc, out=dx)
+            if has_o2:
+                wbuf = torch.empty((n, dk), **f32)
+                ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True)
+                ops.spmm_t(plan, a_values, wbuf, dx)
+                del wbuf
+            dy_in = dx
+        g_wq = g_cq = None
+        if residual:
+            dmat_pl = ops.split_planes(dmat)
+            g_wq = ops.xt_y_planes(dmat_pl, h0_planes)                          # [cols, embed_dim]
+            g_cq = colsum(dmat)
+            ops.linear([dmat_pl], wq.t().contiguous(), None, _lib.ACT_ACCUMULATE, out=dh0)
+            del dmat_pl
+
+        # ---- literal gate (gate.py:22-28) ----
+        gate_mod, tables = self._gate_module()
+        g_wpair = g_bpair = None
+        if gate_mod is not None:
+            ent = self.entity_embed.weight.detach()
+            w_pair = pre["packed"][0]
+            d_pre = torch.empty((n, 2 * d), **f32)
+            g_ent = torch.empty((n, d), **f32)
+            ops.gate_bwd(dh0, keep["gz"], ent, d_pre, g_ent)
+            d_pre_pl = ops.split_planes(d_pre)
+            ops.linear([d_pre_pl], w_pair[:, :d].t().contiguous(), None, _lib.ACT_ACCUMULATE, out=g_ent)
+            g_wpair = torch.zeros_like(w_pair)                  # [2 dim, dim + literals] = d_pre^T [ent | literals]
+            ent_planes, lit_planes = keep["gate_operands"]
+            ops.xt_y_planes(d_pre_pl, ent_planes, out=g_wpair[:, :d])
+            ops.xt_y_planes(d_pre_pl, lit_planes, out=g_wpair[:, d:])
+            g_bpair = colsum(d_pre)
+            del d_pre_pl
+        else:
+            g_ent = dh0.contiguous()
+
+        grads += [g_ent, g_wpair, g_bpair, g_wq, g_cq]
+        for g, g_lw, g_lb in layer_grads:
+            grads += [g[key] for key in self._FOLD_KEYS] + [g_lw, g_lb]
+        if self.scale_gat_dim is not None:
+            grads += [g_wg, g_bg]
+        return grads
 
     # ---- losses ----------------------------------------------------------------------------------
     def calculate_prediction_loss(self, head_ids, tail_pos_ids, tail_neg_ids):
@@ -518,13 +750,15 @@ class LiteralKG(nn.Module):
     # ---- scoring -----------------------------------------------------------------------------------
     def calc_score(self, head_ids, tail_ids):
         """model.py:473-486."""
-        all_embed = self.gat_embeddings()
-        return ops.score(all_embed, head_ids, tail_ids)
+        with torch.no_grad():
+            all_embed = self.gat_embeddings()
+            return ops.score(all_embed, head_ids, tail_ids)
 
     def predict_links(self, head_ids, tail_ids):
         """model.py:488-491."""
-        all_embed = self.gat_embeddings()
-        return ops.predict(all_embed, head_ids, tail_ids, self.milestone_score)
+        with torch.no_grad():
+            all_embed = self.gat_embeddings()
+            return ops.predict(all_embed, head_ids, tail_ids, self.milestone_score)
 
     def topk(self, head_ids, tail_ids, k, target_tails=None, all_embed=None, tail_index=None):
         """Extension (BASELINE.json north star; no reference counterpart): per head the k best tails among
@@ -532,7 +766,8 @@ class LiteralKG(nn.Module):
         Large candidate sets go through the fused scoring + top-k kernels (no B x Nt score matrix);
         ``tail_index`` (``ops.ScoreIndex`` of the tails) can be reused across head batches."""
         if all_embed is None:
-            all_embed = self.gat_embeddings()
+            with torch.no_grad():
+                all_embed = self.gat_embeddings()
         n_tails = tail_index.m if tail_index is not None else len(tail_ids)
         fused = target_tails is None and ops.fused_topk_applicable(n_tails, all_embed.shape[1], k)
         if fused:
@@ -579,7 +814,8 @@ class LiteralKG(nn.Module):
 
     def get_final_embeddings(self, entity_ids):
         """model.py:493-497."""
-        return self.gat_embeddings()[entity_ids]
+        with torch.no_grad():
+            return self.gat_embeddings()[entity_ids]
 
     def forward(self, *input, device, mode):
         """model.py:521-532."""

@@ -149,6 +149,8 @@ def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=weight.device)
     a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
+    if activation & _lib.ACT_ACCUMULATE:
+        assert out is not None
     with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
         _lib.check(_lib.load().lkg_linear_fwd(C.byref(a), m, C.byref(b), n,
                                               _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
@@ -157,7 +159,7 @@ def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor
 
 
 def gate(segments: Sequence, w_pair: torch.Tensor, bias_pair: torch.Tensor, x_ent: torch.Tensor,
-         out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, out_planes=None, gz_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Literal gate (gate.py:22-28): out = (1 - z) * x_ent + z * tanh(g) with (g, z) interleaved in w_pair.
     ``out_planes``: its scale record must bound max(1, max|x_ent|) (see ``scale_from_bound``)."""
     wp = pack_weight(w_pair, segments)
@@ -170,7 +172,7 @@ def gate(segments: Sequence, w_pair: torch.Tensor, bias_pair: torch.Tensor, x_en
     with _dev_guard(x_ent, "gate"):
         _lib.check(_lib.load().lkg_gate_fwd(C.byref(a), m, C.byref(b), bias_pair.data_ptr(), dim, x_ent.data_ptr(),
                                             x_ent.stride(0), out.data_ptr(), out.stride(0), *_planes_out(out_planes),
-                                            _lib.stream()))
+                                            _lib.ptr(gz_out), 0 if gz_out is None else gz_out.stride(0), _lib.stream()))
     return out
 
 
@@ -179,7 +181,8 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
               r1: Optional[torch.Tensor], r2: Optional[torch.Tensor],
               ln_weight: torch.Tensor, ln_bias: torch.Tensor, drop_mask: Optional[torch.Tensor],
               x_out: torch.Tensor, xn_out: Optional[torch.Tensor], xn_planes=None, local_row_base: int = 0,
-              z: Optional[torch.Tensor] = None) -> torch.Tensor:
+              z: Optional[torch.Tensor] = None, o_out: Optional[torch.Tensor] = None,
+              side_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One aggregator layer (lkg_aggregate_fwd).  r1 / r2: [N, d_out] views (any row stride) or [d_out] biases.
     With a row partition, r1 / r2 / drop_mask / xn_out / xn_planes hold the rows from ``local_row_base`` on.
     ``z`` (bi-interaction, wide rows): pre-projected sum term ego @ Pb, [N, d_out] view; then pa = pb = None."""
@@ -205,6 +208,8 @@ def aggregate(plan: GraphPlan, a_values: torch.Tensor, ego: torch.Tensor, d_out:
             _lib.f32c(ln_weight).data_ptr(), _lib.f32c(ln_bias).data_ptr(), _lib.ptr(drop_mask),
             x_out.data_ptr(), x_out.stride(0), _lib.ptr(xn_out), 0 if xn_out is None else xn_out.stride(0),
             *_planes_out(xn_planes), int(local_row_base), _lib.ptr(z), 0 if z is None else z.stride(0),
+            _lib.ptr(o_out), 0 if o_out is None else o_out.stride(0),
+            _lib.ptr(side_out), 0 if side_out is None else side_out.stride(0),
             plan.scratch(), _lib.stream()))
     return x_out
 
@@ -339,3 +344,108 @@ def score_topk(emb: torch.Tensor, heads: torch.Tensor, tails: Optional[torch.Ten
         stats["candidates"] = ws[:4 * nh * streams].view(torch.int32).view(nh, streams).sum(1)
         stats["cap"], stats["cap_per_stream"], stats["sample_tiles"] = cap, cap // streams, sample_tiles
     return vals, pos
+
+
+# ---- backward of the embedding pass (csrc/backward.cu) ------------------------------------------------------
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1, "fp32 matrix with unit inner stride"
+    return t
+
+
+def spmm_t(plan: GraphPlan, a_values: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out += A_in^T @ x  (backward of torch.sparse.mm(A_in, .), model.py:106)."""
+    t_tail, t_head, t_perm = plan.transposed()
+    _rowmajor(x); _rowmajor(out)
+    with _dev_guard(x, f"spmm_t_d{x.shape[1]}"):
+        _lib.check(_lib.load().lkg_spmm_coo(t_tail.data_ptr(), t_head.data_ptr(), t_perm.data_ptr(), a_values.data_ptr(),
+                                            plan.nnz, x.data_ptr(), x.stride(0), x.shape[1], out.data_ptr(),
+                                            out.stride(0), _lib.stream()))
+    return out
+
+
+def layer_bwd_rows(y: torch.Tensor, o: torch.Tensor, has_o2: bool, mask: Optional[torch.Tensor],
+                   dy_in: Optional[torch.Tensor], dyn: Optional[torch.Tensor], ln_weight: torch.Tensor,
+                   d_o: torch.Tensor, dgb: torch.Tensor) -> torch.Tensor:
+    n, c = y.shape
+    for t in (y, o, d_o):
+        _rowmajor(t)
+    with _dev_guard(y, "layer_bwd_rows"):
+        _lib.check(_lib.load().lkg_layer_bwd_rows(
+            n, c, int(has_o2), y.data_ptr(), y.stride(0), o.data_ptr(), o.stride(0), _lib.ptr(mask),
+            _lib.ptr(dy_in), 0 if dy_in is None else _rowmajor(dy_in).stride(0),
+            _lib.ptr(dyn), 0 if dyn is None else _rowmajor(dyn).stride(0),
+            _lib.f32c(ln_weight).data_ptr(), d_o.data_ptr(), d_o.stride(0), dgb.data_ptr(), _lib.stream()))
+    return d_o
+
+
+def bi_bwd_rows(d_o2: torch.Tensor, p2: torch.Tensor, x: torch.Tensor, side: torch.Tensor, w_out: torch.Tensor,
+                dx: torch.Tensor, accumulate: bool) -> None:
+    n, d = x.shape
+    c = d_o2.shape[1]
+    for t in (d_o2, x, side, w_out, dx):
+        _rowmajor(t)
+    p2 = _lib.f32c(p2)
+    assert tuple(p2.shape) == (d, c)
+    with _dev_guard(x, f"bi_bwd_rows_d{d}"):
+        _lib.check(_lib.load().lkg_bi_bwd_rows(n, d, c, d_o2.data_ptr(), d_o2.stride(0), p2.data_ptr(), x.data_ptr(),
+                                               x.stride(0), side.data_ptr(), side.stride(0), w_out.data_ptr(),
+                                               w_out.stride(0), dx.data_ptr(), dx.stride(0), int(accumulate),
+                                               _lib.stream()))
+
+
+def xt_y(x: Optional[torch.Tensor], y: torch.Tensor, x2: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x^T @ y reduced over the rows (x None: column sums of y, shape [1, cy]); optional elementwise factor x2."""
+    _rowmajor(y)
+    n, cy = y.shape
+    dx = 1 if x is None else _rowmajor(x).shape[1]
+    if out is None:
+        out = torch.zeros((dx, cy), dtype=torch.float32, device=y.device)
+    with _dev_guard(y, f"xt_y_{dx}x{cy}"):
+        _lib.check(_lib.load().lkg_xt_y(_lib.ptr(x), 0 if x is None else x.stride(0), _lib.ptr(x2),
+                                        0 if x2 is None else _rowmajor(x2).stride(0), dx, y.data_ptr(), y.stride(0), cy, n,
+                                        out.data_ptr(), out.stride(0), _lib.stream()))
+    return out
+
+
+def xt_y_planes(xp, yp, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x^T @ y over the rows on the tensor cores; xp / yp: Planes or PlanesView of [n, dx] and [n, cy]."""
+    assert xp.rows == yp.rows
+    if out is None:
+        out = torch.zeros((xp.k, yp.k), dtype=torch.float32, device=xp.rec.device)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and tuple(out.shape) == (xp.k, yp.k)
+    a, b = _lib.planes_operand([xp]), _lib.planes_operand([yp])
+    with _dev_guard(out, f"xt_y_tc_{xp.k}x{yp.k}"):
+        _lib.check(_lib.load().lkg_xt_y_planes(C.byref(a), C.byref(b), xp.rows, out.data_ptr(), out.stride(0),
+                                               _lib.stream()))
+    return out
+
+
+def colsum(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _rowmajor(y)
+    if out is None:
+        out = torch.zeros(y.shape[1], dtype=torch.float32, device=y.device)
+    with _dev_guard(y, "colsum"):
+        _lib.check(_lib.load().lkg_colsum(y.data_ptr(), y.stride(0), y.shape[0], y.shape[1], out.data_ptr(), _lib.stream()))
+    return out
+
+
+def gate_bwd(dh: torch.Tensor, gz: torch.Tensor, ent: torch.Tensor, d_pre: torch.Tensor, d_ent: torch.Tensor) -> None:
+    n, dim = dh.shape
+    for t in (dh, gz, ent, d_pre, d_ent):
+        _rowmajor(t)
+    with _dev_guard(dh, "gate_bwd"):
+        _lib.check(_lib.load().lkg_gate_bwd(dh.data_ptr(), dh.stride(0), gz.data_ptr(), gz.stride(0), ent.data_ptr(),
+                                            ent.stride(0), n, dim, d_pre.data_ptr(), d_pre.stride(0), d_ent.data_ptr(),
+                                            d_ent.stride(0), _lib.stream()))
+
+
+def leaky_bwd(grad: torch.Tensor, out: torch.Tensor, d_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, c = out.shape
+    grad = grad if (grad.dtype == torch.float32 and grad.stride(1) == 1) else _lib.f32c(grad)
+    if d_pre is None:
+        d_pre = torch.empty((n, c), dtype=torch.float32, device=out.device)
+    with _dev_guard(out, "leaky_bwd"):
+        _lib.check(_lib.load().lkg_leaky_bwd(grad.data_ptr(), grad.stride(0), out.data_ptr(), out.stride(0), n, c,
+                                             d_pre.data_ptr(), d_pre.stride(0), _lib.stream()))
+    return d_pre

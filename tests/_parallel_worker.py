@@ -75,6 +75,7 @@ def gpu_partitioned_model(rank, world, port, out_dir):
             m.entity_embed.weight.mul_(30)
         return m
 
+    torch.set_grad_enabled(False)                        # inference path (the backward pass is single-GPU)
     single, multi = make(), make()
     part = RowPartition(n)
     multi.set_partition(part)

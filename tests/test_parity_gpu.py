@@ -15,6 +15,14 @@ from _golden import CASES, Golden
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The parity tests exercise the inference path; with grad enabled gat_embeddings() takes the training path
+    (same kernels + saved activations), which tests/test_backward_gpu.py covers."""
+    with torch.no_grad():
+        yield
+
 REL = 1e-3
 
 

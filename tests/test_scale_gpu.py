@@ -9,6 +9,14 @@ import torch
 import literalkg_oracle as O
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The parity tests exercise the inference path; with grad enabled gat_embeddings() takes the training path
+    (same kernels + saved activations), which tests/test_backward_gpu.py covers."""
+    with torch.no_grad():
+        yield
 REL = 1e-3
 
 

@@ -10,6 +10,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The parity tests exercise the inference path; with grad enabled gat_embeddings() takes the training path
+    (same kernels + saved activations), which tests/test_backward_gpu.py covers."""
+    with torch.no_grad():
+        yield
+
+
 def ref_topk(emb, heads, tails, k):
     s = emb[heads].double() @ emb[tails].double().t()
     sf = s.float()                                             # correctly rounded fp32 scores
