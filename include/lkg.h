@@ -229,10 +229,10 @@ int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const float* y, int
                        int64_t ld_dy, const float* dyn /*nullable*/, int64_t ld_dyn, const float* ln_weight,
                        float* d_o, int64_t ld_do, float* dgamma_dbeta, void* stream);
 /* Product path of bi-interaction (model.py:127-128): V = do2 @ P2^T;  w_out = V * x (the operand of the
- * A^T gather);  dx (+)= V * side. */
+ * A^T gather);  dx (+)= V * side;  xs_out (nullable) = x * side, the row operand of d P2 = (x * side)^T do2. */
 int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o2, int64_t ld_do, const float* p2 /*[d, c]*/,
                     const float* x, int64_t ld_x, const float* side, int64_t ld_side, float* w_out, int64_t ld_w,
-                    float* dx, int64_t ld_dx, int32_t accumulate, void* stream);
+                    float* dx, int64_t ld_dx, int32_t accumulate, float* xs_out, int64_t ld_xs, void* stream);
 /* Parameter gradients: out[i, j] += sum_rows x[row, i] * (x2 ? x2[row, i] : 1) * y[row, j]; x == NULL with dx == 1
  * gives the column sums of y (bias gradients).  out [dx, cy] is accumulated into (zero it first). */
 int lkg_xt_y(const float* x /*nullable*/, int64_t ld_x, const float* x2 /*nullable*/, int64_t ld_x2, int32_t dx,
@@ -250,6 +250,21 @@ int lkg_gate_bwd(const float* dh, int64_t ld_dh, const float* gz, int64_t ld_gz,
 /* d_pre = grad * LeakyReLU'(out) from the activated output (model.py:311). */
 int lkg_leaky_bwd(const float* grad, int64_t ld_g, const float* out, int64_t ld_out, int64_t n, int32_t c,
                   float* d_pre, int64_t ld_d, void* stream);
+
+/* ---- loss heads of the training modes: value and gradients over one minibatch ---------------------------------
+ * Both losses are batch means (+ l2_lambda * the reference's _L2_loss_mean terms).  `loss` (nullable) is a device
+ * scalar ACCUMULATED into (zero it first); the gradient buffers (nullable: forward only) are accumulated into as
+ * well; grad_scale (nullable = 1) is the upstream d / d loss as a device scalar, so no call synchronises. */
+/* calculate_prediction_loss (model.py:316-348): BPR, -log sigmoid(h.t+ - h.t-) on rows of the final embeddings. */
+int lkg_bpr_loss(const float* emb, int64_t ld_emb, int32_t g_dim, const int64_t* h, const int64_t* pos,
+                 const int64_t* neg, int64_t batch, float l2_lambda, float* loss, const float* grad_scale,
+                 float* d_emb, int64_t ld_d, void* stream);
+/* calc_triplet_loss (model.py:364-428): TransR, rows projected by gat_trans_M[r] ([R, g_dim, r_dim]),
+ * -log sigmoid(|h_r + e_r - t-_r|^2 - |h_r + e_r - t+_r|^2).  d_relation [R, r_dim], d_trans_m like trans_m. */
+int lkg_transr_loss(const float* emb, int64_t ld_emb, int32_t g_dim, const float* relation, int64_t ld_rel,
+                    int32_t r_dim, const float* trans_m, const int64_t* h, const int64_t* r, const int64_t* pos,
+                    const int64_t* neg, int64_t batch, float l2_lambda, float* loss, const float* grad_scale,
+                    float* d_emb, int64_t ld_d, float* d_relation, float* d_trans_m, void* stream);
 
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
 /* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final

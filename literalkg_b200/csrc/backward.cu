@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) layer_bwd_rows_kernel(LayerBwdParams p) {
     }
 }
 
-// ---- product path of the bi-interaction layer: V = do2 @ P2^T; W = V * x; dx (+)= V * side -----------------------
+// ---- product path of the bi-interaction layer: V = do2 @ P2^T; W = V * x; dx (+)= V * side; xs = x * side ---------
 struct BiBwdParams {
     int64_t n;
     int d, c;
@@ -271,32 +271,68 @@ struct BiBwdParams {
     const float* side;   int64_t ld_side;
     float* w_out;        int64_t ld_w;
     float* dx;           int64_t ld_dx;
+    float* xs_out;       int64_t ld_xs;      // nullable: x * side, the row operand of d P2 = (x * side)^T do2
     int accumulate;
+    int ps;                                  // padded row stride of P2 in shared memory (floats), = 4 * odd
 };
 
+// One warp per row.  The row's do2 (<= 64 values) is broadcast from shared memory into registers once; lane i then
+// produces V[i], V[i + 32], ...: a row of P2 is 16-byte vector loads (stride 4 * odd floats: conflict free for the 8
+// lanes of a quarter warp), one FMA per loaded weight.  Shared-memory bandwidth bound: d * c * 4 bytes per row.
+template <int CQ>   // float4 chunks of do2: c <= 4 CQ
 __global__ void __launch_bounds__(256) bi_bwd_rows_kernel(BiBwdParams p) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ps = p.c + 1;                                  // lanes read consecutive rows of P2: odd stride
+    const int ps = p.ps;
     float* sp = smem;
-    float* sdo = smem + (size_t)p.d * ps + warp * 64;
-    for (int i = threadIdx.x; i < p.d * p.c; i += blockDim.x) sp[(i / p.c) * ps + (i % p.c)] = p.p2[i];
+    float* sdo = smem + (size_t)p.d * ps + warp * (4 * CQ);
+    for (int i = threadIdx.x; i < p.d * ps; i += blockDim.x) {
+        const int r = i / ps, c = i - r * ps;
+        sp[i] = c < p.c ? p.p2[r * p.c + c] : 0.f;
+    }
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * 8;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n; row += stride) {
-        for (int c = lane; c < p.c; c += 32) sdo[c] = __ldg(p.d_o2 + row * p.ld_do + c);
+        for (int c = lane; c < 4 * CQ; c += 32) sdo[c] = c < p.c ? __ldg(p.d_o2 + row * p.ld_do + c) : 0.f;
         __syncwarp();
-        for (int i = lane; i < p.d; i += 32) {
-            const float* w = sp + i * ps;
-            float v = 0.f;
-            for (int c = 0; c < p.c; ++c) v = fmaf(sdo[c], w[c], v);
-            const float xv = __ldg(p.x + row * p.ld_x + i);
-            const float sv = __ldg(p.side + row * p.ld_side + i);
-            p.w_out[row * p.ld_w + i] = v * xv;
-            float* dst = p.dx + row * p.ld_dx + i;
-            *dst = p.accumulate ? fmaf(v, sv, *dst) : v * sv;
+        float4 dq[CQ];
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) dq[q] = reinterpret_cast<const float4*>(sdo)[q];
+        __syncwarp();
+        // UN elements per lane and step: every global load of the step is in flight before the first FMA (the kernel
+        // is otherwise bound by the x / side / dx round trips, not by shared memory)
+        constexpr int UN = 5;
+        for (int i0 = lane; i0 < p.d; i0 += 32 * UN) {
+            float xv[UN], sv[UN], dv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + 32 * u;
+                const bool ok = i < p.d;
+                xv[u] = ok ? __ldg(p.x + row * p.ld_x + i) : 0.f;
+                sv[u] = ok ? __ldg(p.side + row * p.ld_side + i) : 0.f;
+                dv[u] = (ok && p.accumulate) ? p.dx[row * p.ld_dx + i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < p.d) {
+                    const float4* w = reinterpret_cast<const float4*>(sp + i * ps);
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < CQ; ++q) {
+                        const float4 ww = w[q];
+                        v0 = fmaf(dq[q].x, ww.x, v0);
+                        v1 = fmaf(dq[q].y, ww.y, v1);
+                        v0 = fmaf(dq[q].z, ww.z, v0);
+                        v1 = fmaf(dq[q].w, ww.w, v1);
+                    }
+                    const float v = v0 + v1;
+                    p.w_out[row * p.ld_w + i] = v * xv[u];
+                    if (p.xs_out) p.xs_out[row * p.ld_xs + i] = xv[u] * sv[u];
+                    p.dx[row * p.ld_dx + i] = fmaf(v, sv[u], dv[u]);
+                }
+            }
         }
-        __syncwarp();
     }
 }
 
@@ -480,19 +516,30 @@ extern "C" int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const fl
 
 extern "C" int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o2, int64_t ld_do, const float* p2,
                                const float* x, int64_t ld_x, const float* side, int64_t ld_side, float* w_out,
-                               int64_t ld_w, float* dx, int64_t ld_dx, int32_t accumulate, void* stream_) {
+                               int64_t ld_w, float* dx, int64_t ld_dx, int32_t accumulate, float* xs_out, int64_t ld_xs,
+                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(d_o2 && p2 && x && side && w_out && dx && d > 0 && c > 0, "null argument");
     if (c > 64) LKG_FAIL(LKG_ERR_UNSUPPORTED, "bi backward: d_out %d > 64", c);
-    const size_t smem = ((size_t)d * (c + 1) + 8 * 64) * sizeof(float);
+    const int cq = (c + 3) / 4;
+    int ps = 4 * cq;
+    if ((ps / 4) % 2 == 0) ps += 4;                           // 4 * odd
+    const size_t smem = ((size_t)d * ps + 8 * 64) * sizeof(float);
     if (smem > 227 * 1024) LKG_FAIL(LKG_ERR_UNSUPPORTED, "bi backward: d_in %d x d_out %d does not fit shared memory", d, c);
-    LKG_CUDA(cudaFuncSetAttribute(bi_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BiBwdParams p{n, d, c, d_o2, ld_do, p2, x, ld_x, side, ld_side, w_out, ld_w, dx, ld_dx, accumulate};
-    const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 2);
-    bi_bwd_rows_kernel<<<grid, 256, smem, stream>>>(p);
-    LKG_LAUNCH_CHECK("bi_bwd_rows_kernel");
-    return LKG_OK;
+    BiBwdParams p{n, d, c, d_o2, ld_do, p2, x, ld_x, side, ld_side, w_out, ld_w, dx, ld_dx, xs_out, ld_xs, accumulate, ps};
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * per_sm);
+#define LKG_BI_CASE(Q)                                                                                              \
+    if (cq <= Q) {                                                                                                   \
+        LKG_CUDA(cudaFuncSetAttribute(bi_bwd_rows_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        bi_bwd_rows_kernel<Q><<<grid, 256, smem, stream>>>(p);                                                       \
+        LKG_LAUNCH_CHECK("bi_bwd_rows_kernel");                                                                      \
+        return LKG_OK;                                                                                               \
+    }
+    LKG_BI_CASE(4) LKG_BI_CASE(8) LKG_BI_CASE(16)
+#undef LKG_BI_CASE
+    LKG_FAIL(LKG_ERR_UNSUPPORTED, "bi backward: d_out %d", c);
 }
 
 extern "C" int lkg_xt_y(const float* x, int64_t ld_x, const float* x2, int64_t ld_x2, int32_t dx, const float* y,

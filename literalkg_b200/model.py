@@ -232,6 +232,49 @@ class _GatEmbeddingsFn(torch.autograd.Function):
         return (None, None, *[g if has else None for g, has in zip(grads, ctx.present)])
 
 
+class _BprLossFn(torch.autograd.Function):
+    """calculate_prediction_loss (model.py:316-348) as one kernel forward and one backward (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, emb, h, pos, neg, lam):
+        emb = emb if (emb.dtype == torch.float32 and emb.stride(1) == 1) else _lib.f32c(emb)
+        loss = torch.zeros((), dtype=torch.float32, device=emb.device)
+        ops.bpr_loss(emb, h, pos, neg, lam, loss)
+        ctx.save_for_backward(emb, h, pos, neg)
+        ctx.lam = lam
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, h, pos, neg = ctx.saved_tensors
+        d_emb = torch.zeros_like(emb)
+        ops.bpr_loss(emb, h, pos, neg, ctx.lam, None, grad_scale=g.float().contiguous(), d_emb=d_emb)
+        return d_emb, None, None, None, None
+
+
+class _TransRLossFn(torch.autograd.Function):
+    """calc_triplet_loss (model.py:364-428): no [B, G, D] copy of W_r, gradients scattered by the kernel."""
+
+    @staticmethod
+    def forward(ctx, emb, rel, trans_m, h, r, pos, neg, lam):
+        emb = emb if (emb.dtype == torch.float32 and emb.stride(1) == 1) else _lib.f32c(emb)
+        loss = torch.zeros((), dtype=torch.float32, device=emb.device)
+        ops.transr_loss(emb, rel, trans_m, h, r, pos, neg, lam, loss)
+        ctx.save_for_backward(emb, rel, trans_m, h, r, pos, neg)
+        ctx.lam = lam
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, rel, trans_m, h, r, pos, neg = ctx.saved_tensors
+        d_emb = torch.zeros_like(emb)
+        d_rel = torch.zeros(rel.shape, dtype=torch.float32, device=emb.device)
+        d_m = torch.zeros(trans_m.shape, dtype=torch.float32, device=emb.device)
+        ops.transr_loss(emb, rel, trans_m, h, r, pos, neg, ctx.lam, None, grad_scale=g.float().contiguous(),
+                        d_emb=d_emb, d_relation=d_rel, d_trans_m=d_m)
+        return d_emb, d_rel, d_m, None, None, None, None, None
+
+
 class LiteralKG(nn.Module):
     """model.py:167-532."""
 
@@ -634,13 +677,10 @@ class LiteralKG(nn.Module):
                 g["pa"] = ops.xt_y_planes(xk_pl, do1_pl)
             if use_pb:
                 g["pb"] = ops.xt_y_planes(xk_pl, t1_pl)        # (A x)^T do1 == x^T (A^T do1)
-            if has_o2:
-                g["p2"] = ops.xt_y(x_k, do2, x2=sv["side"])
             if not residual:
                 g["c1"] = colsum(do1)
                 if has_o2:
                     g["c2"] = colsum(do2)
-            layer_grads[k] = (g, dgb[:c], dgb[c:])
             # d loss / d x_k = do1 Pa^T + t1 Pb^T + (do2 P2^T) * side + A^T ((do2 P2^T) * x_k)
             dx = dh0 if k == 0 else torch.empty((n, dk), **f32)
             acc = _lib.ACT_ACCUMULATE if k == 0 else _lib.ACT_NONE
@@ -652,10 +692,12 @@ class LiteralKG(nn.Module):
             if segs:
                 ops.linear(segs, torch.cat(ws, dim=1).contiguous(), None, acc, out=dx)
             if has_o2:
-                wbuf = torch.empty((n, dk), **f32)
-                ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True)
+                wbuf, xs = torch.empty((n, dk), **f32), torch.empty((n, dk), **f32)
+                ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True, xs_out=xs)
                 ops.spmm_t(plan, a_values, wbuf, dx)
-                del wbuf
+                g["p2"] = ops.xt_y_planes(ops.split_planes(xs), ops.split_planes(do2))   # (x * side)^T do2
+                del wbuf, xs
+            layer_grads[k] = (g, dgb[:c], dgb[c:])
             dy_in = dx
         g_wq = g_cq = None
         if residual:
@@ -694,32 +736,15 @@ class LiteralKG(nn.Module):
 
     # ---- losses ----------------------------------------------------------------------------------
     def calculate_prediction_loss(self, head_ids, tail_pos_ids, tail_neg_ids):
-        """model.py:316-348 (BPR)."""
+        """model.py:316-348 (BPR on the final embeddings)."""
         self.gat_embed = self.gat_embeddings()
-        head_embed = self.gat_embed[head_ids]
-        tail_pos_embed = self.gat_embed[tail_pos_ids]
-        tail_neg_embed = self.gat_embed[tail_neg_ids]
-        pos_score = torch.sum(head_embed * tail_pos_embed, dim=1)
-        neg_score = torch.sum(head_embed * tail_neg_embed, dim=1)
-        prediction_loss = torch.mean((-1.0) * F.logsigmoid(pos_score - neg_score))
-        l2_loss = _L2_loss_mean(head_embed) + _L2_loss_mean(tail_pos_embed) + _L2_loss_mean(tail_neg_embed)
-        return prediction_loss + self.prediction_l2loss_lambda * l2_loss
+        return _BprLossFn.apply(self.gat_embed, head_ids, tail_pos_ids, tail_neg_ids, float(self.prediction_l2loss_lambda))
 
     def calc_triplet_loss(self, h, r, pos_t, neg_t):
         """model.py:364-428 (TransR on the GAT embeddings)."""
-        r_embed = self.relation_embed(r)
-        W_r = self.gat_trans_M[r]
         self.gat_embed = self.gat_embeddings()
-        head_embed, tail_pos_embed, tail_neg_embed = self.gat_embed[h], self.gat_embed[pos_t], self.gat_embed[neg_t]
-        r_mul_h = torch.bmm(head_embed.unsqueeze(1), W_r).squeeze(1)
-        r_mul_pos_t = torch.bmm(tail_pos_embed.unsqueeze(1), W_r).squeeze(1)
-        r_mul_neg_t = torch.bmm(tail_neg_embed.unsqueeze(1), W_r).squeeze(1)
-        pos_score = torch.sum(torch.pow(r_mul_h + r_embed - r_mul_pos_t, 2), dim=1)
-        neg_score = torch.sum(torch.pow(r_mul_h + r_embed - r_mul_neg_t, 2), dim=1)
-        triplet_loss = torch.mean((-1.0) * F.logsigmoid(neg_score - pos_score))
-        l2_loss = (_L2_loss_mean(r_mul_h) + _L2_loss_mean(r_embed) + _L2_loss_mean(r_mul_pos_t)
-                   + _L2_loss_mean(r_mul_neg_t))
-        return triplet_loss + self.kg_l2loss_lambda * l2_loss
+        return _TransRLossFn.apply(self.gat_embed, self.relation_embed.weight, self.gat_trans_M, h, r, pos_t, neg_t,
+                                   float(self.kg_l2loss_lambda))
 
     # ---- attention update ------------------------------------------------------------------------
     def update_attention(self, h_list, t_list, r_list, relations):

@@ -379,7 +379,7 @@ def layer_bwd_rows(y: torch.Tensor, o: torch.Tensor, has_o2: bool, mask: Optiona
 
 
 def bi_bwd_rows(d_o2: torch.Tensor, p2: torch.Tensor, x: torch.Tensor, side: torch.Tensor, w_out: torch.Tensor,
-                dx: torch.Tensor, accumulate: bool) -> None:
+                dx: torch.Tensor, accumulate: bool, xs_out: Optional[torch.Tensor] = None) -> None:
     n, d = x.shape
     c = d_o2.shape[1]
     for t in (d_o2, x, side, w_out, dx):
@@ -390,6 +390,7 @@ def bi_bwd_rows(d_o2: torch.Tensor, p2: torch.Tensor, x: torch.Tensor, side: tor
         _lib.check(_lib.load().lkg_bi_bwd_rows(n, d, c, d_o2.data_ptr(), d_o2.stride(0), p2.data_ptr(), x.data_ptr(),
                                                x.stride(0), side.data_ptr(), side.stride(0), w_out.data_ptr(),
                                                w_out.stride(0), dx.data_ptr(), dx.stride(0), int(accumulate),
+                                               _lib.ptr(xs_out), 0 if xs_out is None else _rowmajor(xs_out).stride(0),
                                                _lib.stream()))
 
 
@@ -449,3 +450,37 @@ def leaky_bwd(grad: torch.Tensor, out: torch.Tensor, d_pre: Optional[torch.Tenso
         _lib.check(_lib.load().lkg_leaky_bwd(grad.data_ptr(), grad.stride(0), out.data_ptr(), out.stride(0), n, c,
                                              d_pre.data_ptr(), d_pre.stride(0), _lib.stream()))
     return d_pre
+
+
+# ---- loss heads (csrc/loss.cu) ------------------------------------------------------------------------------------
+def _ids(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.int64).contiguous()
+
+
+def bpr_loss(emb: torch.Tensor, h, pos, neg, l2_lambda: float, loss: Optional[torch.Tensor],
+             grad_scale: Optional[torch.Tensor] = None, d_emb: Optional[torch.Tensor] = None) -> None:
+    _rowmajor(emb)
+    h, pos, neg = (_ids(x, emb.device) for x in (h, pos, neg))
+    with _dev_guard(emb, "bpr_loss"):
+        _lib.check(_lib.load().lkg_bpr_loss(emb.data_ptr(), emb.stride(0), emb.shape[1], h.data_ptr(), pos.data_ptr(),
+                                            neg.data_ptr(), h.numel(), float(l2_lambda), _lib.ptr(loss),
+                                            _lib.ptr(grad_scale), _lib.ptr(d_emb),
+                                            0 if d_emb is None else _rowmajor(d_emb).stride(0), _lib.stream()))
+
+
+def transr_loss(emb: torch.Tensor, relation: torch.Tensor, trans_m: torch.Tensor, h, r, pos, neg, l2_lambda: float,
+                loss: Optional[torch.Tensor], grad_scale: Optional[torch.Tensor] = None,
+                d_emb: Optional[torch.Tensor] = None, d_relation: Optional[torch.Tensor] = None,
+                d_trans_m: Optional[torch.Tensor] = None) -> None:
+    _rowmajor(emb)
+    relation, trans_m = _lib.f32c(relation), _lib.f32c(trans_m)
+    assert trans_m.shape[1] == emb.shape[1] and trans_m.shape[2] == relation.shape[1]
+    h, r, pos, neg = (_ids(x, emb.device) for x in (h, r, pos, neg))
+    for t in (d_relation, d_trans_m):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    with _dev_guard(emb, "transr_loss"):
+        _lib.check(_lib.load().lkg_transr_loss(
+            emb.data_ptr(), emb.stride(0), emb.shape[1], relation.data_ptr(), relation.stride(0), relation.shape[1],
+            trans_m.data_ptr(), h.data_ptr(), r.data_ptr(), pos.data_ptr(), neg.data_ptr(), h.numel(), float(l2_lambda),
+            _lib.ptr(loss), _lib.ptr(grad_scale), _lib.ptr(d_emb), 0 if d_emb is None else _rowmajor(d_emb).stride(0),
+            _lib.ptr(d_relation), _lib.ptr(d_trans_m), _lib.stream()))

@@ -158,7 +158,7 @@ def test_layer_bwd_rows(c, has_o2, use_mask, use_dy, use_dyn):
     assert rel_err(dgb[c:], lb.grad) < 1e-4
 
 
-@pytest.mark.parametrize("d,c", [(300, 32), (32, 32), (64, 16)])
+@pytest.mark.parametrize("d,c", [(300, 32), (32, 32), (64, 16), (300, 64), (128, 10)])
 def test_bi_bwd_rows(d, c):
     from literalkg_b200 import ops
     n = 777
@@ -170,10 +170,12 @@ def test_bi_bwd_rows(d, c):
     dx0 = torch.randn(n, d, generator=g, device="cuda")
     v = do2.double() @ p2.double().t()
     for acc in (True, False):
-        w, dx = torch.empty(n, d, device="cuda"), dx0.clone()
-        ops.bi_bwd_rows(do2, p2, x, side, w, dx, accumulate=acc)
+        w, dx, xs = torch.empty(n, d, device="cuda"), dx0.clone(), torch.empty(n, d, device="cuda")
+        ops.bi_bwd_rows(do2, p2, x, side, w, dx, accumulate=acc, xs_out=xs if acc else None)
         assert rel_err(w, v * x.double()) < 1e-5
         assert rel_err(dx, (dx0.double() if acc else 0) + v * side.double()) < 1e-5
+        if acc:
+            assert torch.equal(xs, x * side)
 
 
 def test_gate_and_leaky_bwd():
@@ -192,6 +194,47 @@ def test_gate_and_leaky_bwd():
     out = torch.randn(n, 256, generator=g, device="cuda")
     gr = torch.randn(n, 256, generator=g, device="cuda")
     assert torch.equal(ops.leaky_bwd(gr, out), gr * torch.where(out > 0, 1.0, 0.01).float())
+
+
+def test_loss_heads_vs_torch():
+    """lkg_bpr_loss / lkg_transr_loss (value + every gradient) against the reference formulas in float64
+    (model.py:316-348, 364-428); batch indices repeat, so the gradient scatter must accumulate."""
+    from literalkg_b200.model import _BprLossFn, _TransRLossFn
+    n, G, D, R, B = 500, 256, 300, 5, 681
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(n, G, generator=g) * 0.3
+    rel = torch.randn(R, D, generator=g) * 0.3
+    M = torch.randn(R, G, D, generator=g) * 0.05
+    h, p, ng = (torch.randint(0, n, (B,), generator=g) for _ in range(3))
+    r = torch.randint(0, R, (B,), generator=g)
+    lam = 1e-2
+    l2 = lambda x: torch.mean(torch.sum(x * x, dim=1) / 2.)
+
+    e64 = emb.double().requires_grad_(True)
+    he, pe, ne = e64[h], e64[p], e64[ng]
+    ref = torch.mean(-torch.nn.functional.logsigmoid((he * pe).sum(1) - (he * ne).sum(1))) + lam * (l2(he) + l2(pe) + l2(ne))
+    (ref * 0.7).backward()
+    ec = emb.cuda().requires_grad_(True)
+    out = _BprLossFn.apply(ec, h.cuda(), p.cuda(), ng.cuda(), lam)
+    (out * 0.7).backward()
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(ec.grad, e64.grad) < 1e-5
+
+    e64 = emb.double().requires_grad_(True)
+    r64, m64 = rel.double().requires_grad_(True), M.double().requires_grad_(True)
+    W = m64[r]
+    a, b, c = (torch.bmm(e64[i].unsqueeze(1), W).squeeze(1) for i in (h, p, ng))
+    er = r64[r]
+    pos_s, neg_s = ((a + er - b) ** 2).sum(1), ((a + er - c) ** 2).sum(1)
+    ref = torch.mean(-torch.nn.functional.logsigmoid(neg_s - pos_s)) + lam * (l2(a) + l2(er) + l2(b) + l2(c))
+    (ref * 1.3).backward()
+    ec, rc, mc = (t.cuda().requires_grad_(True) for t in (emb, rel, M))
+    out = _TransRLossFn.apply(ec, rc, mc, h.cuda(), r.cuda(), p.cuda(), ng.cuda(), lam)
+    (out * 1.3).backward()
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(ec.grad, e64.grad) < 1e-5
+    assert rel_err(rc.grad, r64.grad) < 1e-5
+    assert rel_err(mc.grad, m64.grad) < 1e-5
 
 
 def test_linear_accumulate():
