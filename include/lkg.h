@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LKG_ABI_VERSION 3
+#define LKG_ABI_VERSION 5
 
 typedef enum {
     LKG_OK = 0,
@@ -64,7 +64,20 @@ typedef struct {
     const int32_t* row_sched;   /* [row_end - row_begin][8] the same order as 32-byte records {row, att_rowptr[row],
                                    att_rowptr[row+1], rowptr[row], rowptr[row+1], 0, 0, 0} (required by
                                    lkg_attn_update; 16-byte aligned) */
+    int64_t n_solo_rows;        /* leading rows of row_order with more than LKG_SOLO_DEGREE triples (0 = unknown): the
+                                   narrow-row aggregation kernel gives each of them a warp of its own */
+    /* Segmented heavy rows.  A row with more than LKG_SEG_DEGREE triples may appear in row_sched as nseg <= LKG_MAX_SEGS
+     * records {row, att sub-range, agg sub-range, nseg, ticket, segment index}: different warps process the pieces, a
+     * per-row ticket counter elects the last one to finish the row (softmax / combine).  Records of ordinary rows have
+     * nseg == 0.  The host side builds the expanded schedule (graph.py); n_sched == 0 means "one record per row". */
+    int64_t n_sched;            /* records in row_sched */
+    int32_t* seg_tickets;       /* [number of segmented rows] zero between launches (the electing warp resets it) */
+    float* seg_scratch;         /* [segmented rows * LKG_MAX_SEGS][seg_stride] partial sums of the aggregation kernel */
+    int64_t seg_stride;         /* floats per scratch slot (>= d_in + d_out) */
 } lkg_graph;
+#define LKG_SOLO_DEGREE 256
+#define LKG_SEG_DEGREE 512
+#define LKG_MAX_SEGS 8
 
 /* fp16 "planes" operand of the tensor-core GEMMs.  A value x is stored as hi = fp16(s*x) and
  * lo = fp16(s*x - hi): two fp16 matrices [rows, ld] that are `plane_stride` elements apart (hi first), 22

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_PKG, "liblkg.so")
 
 LKG_MAX_SEGMENTS = 4
 LKG_SCALE_FLOATS = 8
-ABI_VERSION = 3
+ABI_VERSION = 5
+SOLO_DEGREE, SEG_DEGREE, MAX_SEGS, SEG_STRIDE = 256, 512, 8, 576
 ACT_NONE, ACT_LEAKY_RELU, ACT_ACCUMULATE = 0, 1, 256
 
 i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
@@ -22,7 +23,8 @@ i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 class LkgGraph(C.Structure):
     _fields_ = [("n_entities", i64), ("n_edges", i64), ("nnz", i64), ("n_relations", i32),
                 ("row_begin", i64), ("row_end", i64), ("att_rowptr", vp), ("att_tail", vp), ("att_rel", vp), ("att_seg", vp),
-                ("rowptr", vp), ("col", vp), ("row_order", vp), ("row_sched", vp)]
+                ("rowptr", vp), ("col", vp), ("row_order", vp), ("row_sched", vp), ("n_solo_rows", i64),
+                ("n_sched", i64), ("seg_tickets", vp), ("seg_scratch", vp), ("seg_stride", i64)]
 
 
 class LkgPlanes(C.Structure):

@@ -53,6 +53,7 @@ struct AggParams {
     int64_t ld_o;
     float* side_out;   // training: saved side = A @ ego per local row (nullable), row stride ld_side
     int64_t ld_side;
+    int n_solo;        // narrow kernel: leading rows of row_order that are scheduled one per warp
 };
 
 template <int S, int NC, int MODE>
@@ -307,12 +308,18 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
 
     const int n = (int)(p.g.row_end - p.g.row_begin);
     const int row0 = (int)p.g.row_begin;
+    // Work units from the dynamic counter: the first n_solo rows of the (degree sorted) order are so long that one
+    // of them is a unit of its own -- the whole warp walks its neighbour list -- instead of four of them queueing
+    // behind each other in one warp (a 4 096-neighbour row is ~128 dependent round trips); after them, RPW rows each.
+    const int n_solo = RPW > 1 ? min(p.n_solo, n) : 0;
     for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, RPW);
-        base = __shfl_sync(kFull, base, 0);
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(p.counter, 1);
+        unit = __shfl_sync(kFull, unit, 0);
+        const bool solo = unit < n_solo;
+        const int base = solo ? unit : n_solo + (unit - n_solo) * RPW;
         if (base >= n) break;
-        const bool live = base + grp < n;
+        const bool live = solo ? grp == 0 : base + grp < n;
         const int row = live ? (p.g.row_order ? __ldg(p.g.row_order + base + grp) : row0 + base + grp) : 0;
         const int64_t lrow = row - p.local_row_base;
         const int u0 = live ? __ldg(p.g.rowptr + row) : 0;
@@ -321,12 +328,12 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) max_deg = max(max_deg, __shfl_xor_sync(kFull, max_deg, o));
         max_deg = __shfl_sync(kFull, max_deg, 0);
-        const bool coop = RPW > 1 && max_deg > kCoopDegree;
+        const bool coop = RPW > 1 && (solo || max_deg > kCoopDegree);
 
         // ---- phase 1: side = sum_j A[row, j] * ego[col_j], this lane's float4 -------------------------
         float4 side = make_float4(0, 0, 0, 0);
         const float* ego_l = p.ego + 4 * gl;
-        for (int pass = 0; pass < (coop ? RPW : 1); ++pass) {
+        for (int pass = 0; pass < (coop ? (solo ? 1 : RPW) : 1); ++pass) {
             // group mode: every group walks its own row, LPR neighbours per step; coop mode: the warp walks the
             // row of group `pass`, 32 neighbours per step (group g takes neighbours [g LPR, (g+1) LPR) of the step)
             const int b0 = coop ? __shfl_sync(kFull, u0, pass * LPR) : u0;
@@ -335,11 +342,20 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
             const int step = coop ? 32 : LPR;
             const int trips = coop ? (b1 - b0 + 31) / 32 : (max_deg + LPR - 1) / LPR;
             float4 acc = make_float4(0, 0, 0, 0);
+            // the (column, value) pair of the NEXT step is loaded before the gathers of this one are issued
+            int cl_n = -1;
+            float av_n = 0.f;
+            if (trips > 0 && b0 + my < b1) {
+                cl_n = __ldg(p.g.col + b0 + my);
+                av_n = __ldg(p.a_val + b0 + my);
+            }
             for (int it = 0; it < trips; ++it) {
-                const int u = b0 + it * step + my;
-                const bool ok = u < b1;
-                const int cl = ok ? __ldg(p.g.col + u) : -1;
-                const float av = ok ? __ldg(p.a_val + u) : 0.f;
+                const int cl = cl_n;
+                const float av = av_n;
+                const int un = b0 + (it + 1) * step + my;
+                const bool okn = it + 1 < trips && un < b1;
+                cl_n = okn ? __ldg(p.g.col + un) : -1;
+                av_n = okn ? __ldg(p.a_val + un) : 0.f;
 #pragma unroll
                 for (int j0 = 0; j0 < LPR; j0 += U) {
                     float4 x[U];
@@ -589,24 +605,25 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const int n_rows = (int)(p.g.row_end - p.g.row_begin);
+    const int n_rows = p.g.n_sched > 0 ? (int)p.g.n_sched : (int)(p.g.row_end - p.g.row_begin);   // schedule records
     const int4* sched = reinterpret_cast<const int4*>(p.g.row_sched);
     uint32_t issued = 0, consumed = 0;
     const bool need_ego = MODE != kOneTerm || p.sum_ego;
     const int zvec = d_out >> 2;                                 // float4 per z row
 
-    struct Rec { int row, u0, u1; };
+    struct Rec { int row, u0, u1, nseg, ticket, seg; };
     auto fetch_idx = [&]() {
         int i = 0;
         if (lane == 0) i = atomicAdd(p.counter, 1);
         return i;
     };
     auto load_rec = [&](int i) {
-        Rec r{0, 0, 0};
+        Rec r{0, 0, 0, 0, 0, 0};
         if (i < n_rows) {
             const int4 a = __ldg(sched + 2 * i);
+            const int4 b = __ldg(sched + 2 * i + 1);
             r.row = a.x; r.u0 = a.w;
-            r.u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * i + 1));
+            r.u1 = b.x; r.nseg = b.y; r.ticket = b.z; r.seg = b.w;
         }
         return r;
     };
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
         int idx2 = fetch_idx();
         const int row = rec.row, u0 = rec.u0, u1 = rec.u1;
         const int64_t lrow = row - p.local_row_base;
-        Rec rec2{0, 0, 0};
+        Rec rec2{0, 0, 0, 0, 0, 0};
         Head head1;
         bool fetched = false;
         auto prefetch_rows = [&]() {                 // with this row's copies in flight: loads of the rows to come
@@ -710,7 +727,53 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
             issued += pre_issued;
         }
 
+        // ---- segmented row: park this piece's partial sums; the piece that arrives last adds them up (in segment
+        //      order: the result does not depend on which warp that is) and finishes the row ------------------------
+        bool finish = true;
+        if (rec.nseg > 0) {
+            float4* slot = reinterpret_cast<float4*>(p.g.seg_scratch +
+                                                     ((int64_t)rec.ticket * LKG_MAX_SEGS + rec.seg) * p.g.seg_stride);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int v = lane + 32 * s;
+                if (v < nvec) __stcg(slot + v, side[s]);
+            }
+            if (Z && lane < zvec) __stcg(slot + nvec + lane, zside);
+            __threadfence();
+            __syncwarp();
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(p.g.seg_tickets + rec.ticket, 1);
+                if (t == rec.nseg - 1) p.g.seg_tickets[rec.ticket] = 0;    // ready for the next launch
+            }
+            t = __shfl_sync(kFull, t, 0);
+            finish = t == rec.nseg - 1;
+            if (finish) {
+                __threadfence();
+#pragma unroll
+                for (int s = 0; s < S; ++s) side[s] = make_float4(0, 0, 0, 0);
+                zside = make_float4(0, 0, 0, 0);
+                for (int q = 0; q < rec.nseg; ++q) {
+                    const float4* src = reinterpret_cast<const float4*>(
+                        p.g.seg_scratch + ((int64_t)rec.ticket * LKG_MAX_SEGS + q) * p.g.seg_stride);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const int v = lane + 32 * s;
+                        if (v < nvec) {
+                            const float4 x = __ldcg(src + v);
+                            side[s].x += x.x; side[s].y += x.y; side[s].z += x.z; side[s].w += x.w;
+                        }
+                    }
+                    if (Z && lane < zvec) {
+                        const float4 x = __ldcg(src + nvec + lane);
+                        zside.x += x.x; zside.y += x.y; zside.z += x.z; zside.w += x.w;
+                    }
+                }
+            }
+        }
+
         // ---- phase 2: u-vectors to the staging buffer, folded combine with lane = output channel -------------
+        if (finish) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int v = lane + 32 * s;
@@ -842,6 +905,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
                 }
             }
         }
+        }   // finish
         idx = idx1; rec = rec1; head = head1;
         idx1 = idx2; rec1 = rec2;
     }
@@ -977,10 +1041,14 @@ extern "C" int lkg_aggregate_fwd(const lkg_graph* g, const float* a_values, cons
     p.local_row_base = local_row_base;
     LKG_REQUIRE(!o_out || (ld_o % 4 == 0 && aligned16(o_out)), "o_out rows must be 16-byte aligned");
     LKG_REQUIRE(!side_out || (ld_side % 4 == 0 && aligned16(side_out)), "side_out rows must be 16-byte aligned");
+    LKG_REQUIRE(g->n_sched == 0 || !g->seg_tickets ||
+                    (g->seg_scratch && g->seg_stride % 4 == 0 && g->seg_stride >= d_in + d_out && aligned16(g->seg_scratch)),
+                "the plan's segment scratch is too small for d_in %d + d_out %d", d_in, d_out);
     p.o_out = o_out;
     p.ld_o = ld_o;
     p.side_out = side_out;
     p.ld_side = ld_side;
+    p.n_solo = g->row_order ? (int)g->n_solo_rows : 0;
     p.counter = static_cast<int*>(workspace);
     // lane c reads sp[d * ps + c]: any stride is conflict free for 32 consecutive channels; pad to a
     // multiple of 4 floats to keep rows 16-byte aligned

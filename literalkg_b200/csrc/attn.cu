@@ -77,23 +77,28 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
     if (lane < kRing) ring_bar_init(&bars[lane]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    const int n_rows = (int)(g.row_end - g.row_begin);
+    const int n_rows = g.n_sched > 0 ? (int)g.n_sched : (int)(g.row_end - g.row_begin);   // schedule records
     uint32_t issued = 0, consumed = 0;              // running counts over the kernel: slot = count % kRing,
                                                     // parity of a slot's use = (count / kRing) & 1
     const int4* sched = reinterpret_cast<const int4*>(g.row_sched);
 
-    struct Rec { int row, e0, e1, u0, u1; };
+    struct Rec { int row, e0, e1, u0, u1, nseg, ticket; };
     auto fetch_idx = [&]() {                         // dynamic balance: the heaviest rows are first in the schedule
         int i = 0;
         if (lane == 0) i = atomicAdd(row_counter, 1);
         return i;                                    // valid in lane 0 until broadcast
     };
     auto load_rec = [&](int i) {
-        Rec r{0, 0, 0, 0, 0};
+        Rec r{0, 0, 0, 0, 0, 0, 0};
         if (i < n_rows) {
             const int4 a = __ldg(sched + 2 * i);
+            const int4 b = __ldg(sched + 2 * i + 1);
             r.row = a.x; r.e0 = a.y; r.e1 = a.z; r.u0 = a.w;
-            r.u1 = __ldg(reinterpret_cast<const int*>(sched + 2 * i + 1));
+            r.u1 = b.x; r.nseg = b.y; r.ticket = b.z;
+            if (r.nseg > 0) {      // a piece of a segmented row: the logit slots / softmax span the whole row
+                r.u0 = __ldg(g.rowptr + r.row);
+                r.u1 = __ldg(g.rowptr + r.row + 1);
+            }
         }
         return r;
     };
@@ -126,9 +131,11 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         int idx2 = fetch_idx();                      // row i+2: broadcast and record load after the ring is filled
         const int row = rec.row, e0 = rec.e0, e1 = rec.e1, u0 = rec.u0, nu = rec.u1 - rec.u0;
         (void)row;
-        const bool in_smem = nu <= kSegCap;
+        const bool segmented = rec.nseg > 0;          // the row's pieces share the slots in `val` (zeroed by the host)
+        const bool in_smem = !segmented && nu <= kSegCap;
         float* logit = in_smem ? s_logit : val + u0;                   // slot of pair u: logit[u - u0]
-        for (int i = lane; i < nu; i += 32) logit[i] = 0.f;
+        if (!segmented)
+            for (int i = lane; i < nu; i += 32) logit[i] = 0.f;
         float4 eh[S], w[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -137,7 +144,7 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         }
         __syncwarp();   // zeroing of the slots visible before the logits are written
 
-        Rec rec2{0, 0, 0, 0, 0};
+        Rec rec2{0, 0, 0, 0, 0, 0, 0};
         Head head1;
         int cur_rel = -1;
         // the row's triples in chunks of 32: one coalesced load of (tail, relation, pair) per chunk, then the tail rows
@@ -253,8 +260,20 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         }
         if (!in_smem) __threadfence();          // the long-row reductions are performed before other lanes read them
         __syncwarp();
+        bool finish = true;
+        if (segmented) {                        // the piece that arrives last runs the row's softmax
+            int t = 0;
+            if (lane == 0) {
+                t = atomicAdd(g.seg_tickets + rec.ticket, 1);
+                if (t == rec.nseg - 1) g.seg_tickets[rec.ticket] = 0;      // ready for the next launch
+            }
+            t = __shfl_sync(kFull, t, 0);
+            finish = t == rec.nseg - 1;
+            __threadfence();
+        }
 
         // softmax over the row's unique pairs (__ldcg: the long-row logits were reduced in L2, bypass L1)
+        if (finish) {
         float m = -INFINITY;
         for (int i = lane; i < nu; i += 32) m = fmaxf(m, in_smem ? logit[i] : __ldcg(logit + i));
         m = warp_max(m);
@@ -267,6 +286,7 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
         for (int i = lane; i < nu; i += 32) val[u0 + i] = logit[i] * inv;
+        }
         __syncwarp();   // the shared slots are reused by the next row
         idx = idx1; rec = rec1; head = head1;
         idx1 = idx2; rec1 = rec2;
@@ -306,6 +326,11 @@ extern "C" int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t 
     int* counter = static_cast<int*>(workspace);
     float* rel_exp = reinterpret_cast<float*>(static_cast<char*>(workspace) + kCounterBytes);
     LKG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    if (g->n_sched > 0 && g->seg_tickets) {
+        // the pieces of a segmented row accumulate into shared logit slots: start them at zero (the kernel zeroes
+        // the slots of every other row itself)
+        LKG_CUDA(cudaMemsetAsync(values, 0, (size_t)g->nnz * sizeof(float), stream));
+    }
     const int total = g->n_relations * dim;
     rel_exp_kernel<<<(total + 255) / 256, 256, 0, stream>>>(relation, ld_relation, g->n_relations, dim, rel_exp);
     LKG_LAUNCH_CHECK("rel_exp_kernel");

@@ -73,7 +73,10 @@ class GraphPlan:
         self.c = _lib.LkgGraph(self.n_entities, self.n_edges, self.nnz, self.n_relations, 0, self.n_entities,
                                self.att_rowptr.data_ptr(), self.att_tail.data_ptr(), self.att_rel.data_ptr(),
                                self.att_seg.data_ptr(), self.rowptr.data_ptr(), self.col.data_ptr(),
-                               self.row_order.data_ptr(), self.row_sched.data_ptr())
+                               self.row_order.data_ptr(), self.row_sched.data_ptr(), 0, 0, None, None, 0)
+        self._row_deg = (self.row_sched[:, 2] - self.row_sched[:, 1])     # triples per row, row_order order
+        self._seg_tickets = self._seg_scratch = None
+        self._expand_schedule()
         self._part_order = self._part_sched = self._part_range = None
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
         self._attn_ws = None
@@ -88,6 +91,41 @@ class GraphPlan:
         return cls(indices[0], indices[1], r, n_entities, 1)
 
     # -- helpers ------------------------------------------------------------------------------
+    def _expand_schedule(self) -> None:
+        """Rows are scheduled by decreasing triple count.  The leading rows longer than SEG_DEGREE are cut into
+        up to MAX_SEGS pieces (records {row, att sub-range, agg sub-range, nseg, ticket, piece}) that different warps
+        process; a row-long dependent chain in ONE warp is what bounds the kernels once the graph is split over
+        several GPUs (a 4 096-triple row streams for ~0.7 ms).  Integer bookkeeping on the device, two scalar
+        read-backs per plan build."""
+        sched, deg = self.row_sched, self._row_deg.long()
+        n_solo, n_heavy = torch.stack([(deg > _lib.SOLO_DEGREE).sum(), (deg > _lib.SEG_DEGREE).sum()]).tolist()
+        self._solo_full = int(n_solo)
+        self.c.n_solo_rows = self._solo_full
+        self.c.n_sched = sched.shape[0]
+        if n_heavy == 0:
+            return
+        hv = sched[:n_heavy].long()
+        nseg = torch.clamp((deg[:n_heavy] + _lib.SEG_DEGREE - 1) // _lib.SEG_DEGREE, max=_lib.MAX_SEGS)
+        rid = torch.repeat_interleave(torch.arange(n_heavy, device=self.device), nseg)        # = ticket of the row
+        piece = torch.arange(rid.numel(), device=self.device) - (torch.cumsum(nseg, 0) - nseg)[rid]
+        ns = nseg[rid]
+
+        def cut(lo, hi):
+            ln = hi - lo
+            return lo + ln * piece // ns, lo + ln * (piece + 1) // ns
+
+        e0, e1 = cut(hv[rid, 1], hv[rid, 2])
+        u0, u1 = cut(hv[rid, 3], hv[rid, 4])
+        seg = torch.stack([hv[rid, 0], e0, e1, u0, u1, ns, rid, piece], dim=1).to(torch.int32)
+        self.row_sched = torch.cat([seg, sched[n_heavy:]]).contiguous()
+        self._seg_tickets = torch.zeros(n_heavy, dtype=torch.int32, device=self.device)
+        self._seg_scratch = torch.empty((n_heavy * _lib.MAX_SEGS, _lib.SEG_STRIDE), dtype=torch.float32, device=self.device)
+        self.c.row_sched = self.row_sched.data_ptr()
+        self.c.n_sched = self.row_sched.shape[0]
+        self.c.seg_tickets = self._seg_tickets.data_ptr()
+        self.c.seg_scratch = self._seg_scratch.data_ptr()
+        self.c.seg_stride = _lib.SEG_STRIDE
+
     def byref(self):
         return C.byref(self.c)
 
@@ -99,14 +137,20 @@ class GraphPlan:
         if begin == 0 and end == self.n_entities:
             self.c.row_order = self.row_order.data_ptr()
             self.c.row_sched = self.row_sched.data_ptr()
+            self.c.n_sched = self.row_sched.shape[0]
+            self.c.n_solo_rows = self._solo_full
             return
         if self._part_order is None or self._part_range != (begin, end):   # the partition's rows, heaviest first
             keep = (self.row_order >= begin) & (self.row_order < end)
             self._part_order = self.row_order[keep].contiguous()
-            self._part_sched = self.row_sched[keep].contiguous()
+            rows = self.row_sched[:, 0]
+            self._part_sched = self.row_sched[(rows >= begin) & (rows < end)].contiguous()
             self._part_range = (begin, end)
+            self._part_solo = int((self._row_deg[keep] > _lib.SOLO_DEGREE).sum().item())
+        self.c.n_solo_rows = self._part_solo
         self.c.row_order = self._part_order.data_ptr()
         self.c.row_sched = self._part_sched.data_ptr()
+        self.c.n_sched = self._part_sched.shape[0]
 
     @staticmethod
     def fingerprint(h: torch.Tensor, t: torch.Tensor, r: torch.Tensor):

@@ -77,6 +77,41 @@ def test_default_dims_vs_oracle(agg, res):
     assert torch.equal(pos.cpu()[clear], tp[:, :10][clear])
 
 
+@pytest.mark.parametrize("agg", ["bi-interaction", "gcn"])
+def test_heavy_rows_vs_oracle(agg):
+    """Head rows with thousands of neighbours (longer than every per-warp staging limit: shared-memory logit slots,
+    solo-scheduled rows of the narrow kernel, many ring refills) next to empty and single-neighbour rows."""
+    import literalkg_b200 as L
+    cfg = O.OracleConfig(aggregation_type=agg, use_residual=True, n_conv_layers=2, mess_dropout=0.0)
+    n, n_rel = 5000, 6
+    rng = np.random.default_rng(5)
+    hubs = np.array([3, 77, 4100, 4999])
+    h = np.concatenate([np.repeat(hubs, [3500, 2100, 700, 300]), rng.integers(0, n, 9000)])
+    t = rng.integers(0, n, h.shape[0])
+    r = rng.integers(0, n_rel, h.shape[0])
+    r[:n_rel] = np.arange(n_rel)
+    key = np.unique((h * n + t) * n_rel + r)
+    rng.shuffle(key)
+    h, t, r = key // (n * n_rel), (key // n_rel) % n, key % n_rel
+    num, txt = L.synthetic.make_literals(n, seed=5)
+    p = O.init_params(cfg, n, n_rel, seed=5)
+    p["entity_embed.weight"] = p["entity_embed.weight"] * 40
+    p["relation_embed.weight"] = p["relation_embed.weight"] * 10
+    args = argparse.Namespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    kt = L.KGTensors(h, t, r, n_entities=n)
+    m = L.LiteralKG(args, n, n_rel, kt.A_in, num, txt)
+    m.load_state_dict(p, strict=False)
+    m = m.cuda().eval()
+    m(kt.h_list, kt.t_list, kt.r_list, kt.relations, device="cuda", mode="update_att")
+    ht, tt, rt = (torch.from_numpy(x) for x in (h, t, r))
+    oi, ov = O.update_attention(p["entity_embed.weight"], p["relation_embed.weight"], ht, tt, rt, kt.relations, n)
+    a = m.A_in.data
+    assert np.array_equal(a.indices().cpu().numpy(), oi.numpy())
+    assert rel_err(a.values(), ov) < REL
+    ref = O.gat_embeddings(p, cfg, oi, ov, num, txt)
+    assert rel_err(m.gat_embeddings(), ref) < REL
+
+
 def test_attention_properties_large():
     """Size-independent properties at a size the oracle is not run on: rows sum to 1, values in (0, 1],
     structure equals the sorted unique (h, t) list, result invariant to the input edge order."""
