@@ -341,7 +341,9 @@ class LiteralKG(nn.Module):
         self._unit_rec = None                             # scale record of planes bounded by 1 (normalised rows)
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
         self._part = None                                 # parallel.RowPartition when the path is row partitioned
+        self._gate_prefetch = None                        # (key, gate stage) started by update_attention
         self.sync_attention = True                        # partitioned update_att: all-reduce the A_in values
+        self.prefetch_gate = True                         # partitioned update_att: start the next pass's gate stage
         self._lit_key = None
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -480,17 +482,22 @@ class LiteralKG(nn.Module):
             qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
         return torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, zcol
 
-    def _gat_embeddings_native(self, keep: Optional[dict] = None, pre: Optional[dict] = None) -> torch.Tensor:
-        """``pre`` (training): {folds, wq, cq, offsets, zcol, packed} built under autograd by the caller (detached
-        values are used here); ``keep`` then receives what the backward pass needs."""
+    def _gate_stage_key(self, part):
+        gate_mod, tables = self._gate_module()
+        ent = self.entity_embed.weight
+        return ((ent.data_ptr(), ent._version), None if gate_mod is None else _param_key(gate_mod),
+                tuple((t.data_ptr(), t._version) for t in tables), None if part is None else (part.begin, part.end))
+
+    def _gate_stage(self, part, keep=None, pre=None) -> dict:
+        """First stage of the embedding pass: buffers, the literal gate on this rank's rows and -- row partitioned,
+        when layer 1 gathers raw h0 rows -- the all-gather of h0, started asynchronously.  It depends on the
+        parameters only, not on A_in: ``update_attention`` runs it ahead of the attention kernel so that the
+        all-gather (1.2 GB at N = 1 M) travels over NVLink while that kernel streams HBM."""
         dev = self._param_device()
-        plan, a_values = self._current_plan()
         n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
-        part = self._part if (self._part is not None and self._part.world > 1) else None
         rb, re = (0, n) if part is None else (part.begin, part.end)
         rows = None if part is None else (rb, re)
         n_own, n_tab = re - rb, (n if part is None else part.padded)
-        plan.set_row_range(rb, re)
         cat = torch.empty((n_own, total), dtype=torch.float32, device=dev)   # concat buffer, this rank's rows
         if part is None:
             h0_tab = h0 = cat[:, :d]                      # gate output lives in the concat buffer
@@ -507,6 +514,38 @@ class LiteralKG(nn.Module):
             gz = torch.empty((n_own, 2 * d), dtype=torch.float32, device=dev)      # activated (g, z) pairs
         _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows,
                                             packed=None if pre is None else pre["packed"], gz_out=gz)
+        work = None
+        if part is not None and self.n_layers > 0:
+            c0 = self.aggregator_layers[0].out_dim
+            z_path = self.use_residual and d >= 128 and c0 % 4 == 0      # see _stack_q
+            if not z_path or self.aggregation_type == 'bi-interaction':
+                work = part.all_gather_rows(h0_tab, async_op=True)
+        return dict(cat=cat, h0_tab=h0_tab, h0=h0, cat_planes=cat_planes, h0_planes=h0_planes, xcol=xcol, gz=gz,
+                    work=work)
+
+    def _gat_embeddings_native(self, keep: Optional[dict] = None, pre: Optional[dict] = None) -> torch.Tensor:
+        """``pre`` (training): {folds, wq, cq, offsets, zcol, packed} built under autograd by the caller (detached
+        values are used here); ``keep`` then receives what the backward pass needs."""
+        dev = self._param_device()
+        plan, a_values = self._current_plan()
+        n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
+        part = self._part if (self._part is not None and self._part.world > 1) else None
+        rb, re = (0, n) if part is None else (part.begin, part.end)
+        rows = None if part is None else (rb, re)
+        n_own, n_tab = re - rb, (n if part is None else part.padded)
+        plan.set_row_range(rb, re)
+        st = None
+        if self._gate_prefetch is not None:
+            key, st = self._gate_prefetch                  # gate output (and its all-gather) started by update_att
+            self._gate_prefetch = None
+            if keep is not None or pre is not None or key != self._gate_stage_key(part):
+                if st["work"] is not None:
+                    st["work"].wait()                      # stale: let the transfer finish, then drop it
+                st = None
+        if st is None:
+            st = self._gate_stage(part, keep, pre)
+        cat, h0_tab, h0, cat_planes, h0_planes, xcol, gz = (st[k_] for k_ in
+                                                           ("cat", "h0_tab", "h0", "cat_planes", "h0_planes", "xcol", "gz"))
         xn_all = cat_planes.view(xcol, total - d, rec=self._unit_record(dev))
         h0q = None
         offsets: List[int] = []
@@ -533,10 +572,9 @@ class LiteralKG(nn.Module):
                 z_tab = torch.empty((n_tab, c0), dtype=torch.float32, device=dev)
                 z_tab[rb:re] = h0q[:, zoff:zoff + c0]
                 part.all_gather_rows(z_tab)
-        needs_h0_rows = self.n_layers > 0 and (z_tab is None or self.aggregation_type == 'bi-interaction')
         if part is not None:
-            if needs_h0_rows:
-                part.all_gather_rows(h0_tab)              # layer 1 gathers arbitrary neighbour rows of h0
+            if st["work"] is not None:
+                st["work"].wait()                         # layer 1 gathers arbitrary neighbour rows of h0
             if self.scale_gat_dim is None:
                 cat[:, :d] = h0
 
@@ -763,6 +801,8 @@ class LiteralKG(nn.Module):
             if part is None:
                 values = ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach())
             else:   # rows are independent: every rank fills the values of its own head rows
+                if self.prefetch_gate:
+                    self._gate_prefetch = (self._gate_stage_key(part), self._gate_stage(part))
                 plan.set_row_range(part.begin, part.end)
                 values = torch.zeros(max(plan.nnz, 1), dtype=torch.float32, device=dev)[:plan.nnz]
                 ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach(), out=values)

@@ -23,6 +23,28 @@ import torch
 import torch.distributed as dist
 
 
+class _comm_profile:
+    """Brackets a blocking collective with CUDA events when ``ops.PROFILE`` is on (bench.py's per-call timing)."""
+
+    def __init__(self, t: torch.Tensor, kind: str, nbytes: int, async_op: bool):
+        from . import ops
+        self.on = ops.PROFILE is not None and t.is_cuda and not async_op
+        self.name = f"{kind}_{nbytes / 1e6:.0f}MB"
+
+    def __enter__(self):
+        if self.on:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            from . import ops
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            ops.PROFILE.events.append((self.name, self.start, end))
+        return False
+
+
 class RowPartition:
     """Rank p owns head rows [p * chunk, min(N, (p + 1) * chunk)), chunk = ceil(N / world)."""
 
@@ -47,30 +69,34 @@ class RowPartition:
         return dist.get_backend(self.group) if dist.is_initialized() else "none"
 
     # ---- collectives -------------------------------------------------------------------------------------
-    def all_gather_rows(self, buf: torch.Tensor) -> torch.Tensor:
+    def all_gather_rows(self, buf: torch.Tensor, async_op: bool = False):
         """``buf`` [padded, d] contiguous with this rank's rows already written: fetches every other rank's
-        row block in place."""
+        row block in place.  ``async_op``: returns a handle whose ``wait()`` orders the current stream after the
+        transfer (NCCL: the collective runs on NCCL's stream next to the kernels launched meanwhile), or None when
+        the transfer already happened."""
         assert buf.is_contiguous() and buf.shape[0] == self.padded
         if self.world == 1:
-            return buf
+            return None if async_op else buf
         own = buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
-        if buf.is_cuda and self._backend() != "nccl":          # gloo has no CUDA all-gather: stage through the host
-            full = torch.empty(buf.numel(), dtype=buf.dtype)
-            dist.all_gather_into_tensor(full, own.cpu().reshape(-1), group=self.group)
-            buf.copy_(full.view(buf.shape))
-        else:
-            dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=self.group)
-        return buf
+        with _comm_profile(buf, "all_gather", buf.numel() * buf.element_size(), async_op):
+            if buf.is_cuda and self._backend() != "nccl":      # gloo has no CUDA all-gather: stage through the host
+                full = torch.empty(buf.numel(), dtype=buf.dtype)
+                dist.all_gather_into_tensor(full, own.cpu().reshape(-1), group=self.group)
+                buf.copy_(full.view(buf.shape))
+                return None if async_op else buf
+            work = dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=self.group, async_op=async_op)
+        return work if async_op else buf
 
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.world == 1:
             return t
-        if t.is_cuda and self._backend() != "nccl":
-            c = t.cpu()
-            dist.all_reduce(c, op=op, group=self.group)
-            t.copy_(c)
-        else:
-            dist.all_reduce(t, op=op, group=self.group)
+        with _comm_profile(t, "all_reduce", t.numel() * t.element_size(), False):
+            if t.is_cuda and self._backend() != "nccl":
+                c = t.cpu()
+                dist.all_reduce(c, op=op, group=self.group)
+                t.copy_(c)
+            else:
+                dist.all_reduce(t, op=op, group=self.group)
         return t
 
     def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
