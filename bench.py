@@ -253,8 +253,14 @@ def run_ours(a):
     ab = {k_: v / world for k_, v in ab.items()}      # one launch covers this rank's 1 / world of the head rows
     dom = max((k for k in kern if k in ab), key=lambda k: kern[k]["ms_total"])
     achieved = ab[dom] / (kern[dom]["ms_avg"] / 1e3) / 1e9
+    traffic = None          # ncu dram bytes per launch of that kernel (one-GPU capture, profiles/r01_traffic.json)
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
+        traffic = None if t is None else t / world
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "kernel_ms_avg": kern[dom]["ms_avg"],
                 "kernels": {k: {"ms_avg": round(v["ms_avg"], 4), "share": round(v["ms_total"] / (ms * a.steps), 4),
                                 **({"GBps": round(ab[k] / v["ms_avg"] / 1e6, 1)} if k in ab else {})}
