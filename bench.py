@@ -310,8 +310,7 @@ def run_ours(a):
                     out = model.topk(hb, None, a.topk, all_embed=emb, tail_index=ti)
             else:   # tails sharded by row ownership, per-rank fused top-k, k-way merge
                 ti = model.sharded_index(emb)
-                for hb in batches:
-                    out = model.topk_sharded(hb, a.topk, emb, tail_index=ti)
+                out = model.topk_sharded(batches, a.topk, emb, tail_index=ti)   # one round of collectives for all
             return out
 
         for _ in range(2):

@@ -279,6 +279,18 @@ int lkg_transr_loss(const float* emb, int64_t ld_emb, int32_t g_dim, const float
                     const int64_t* neg, int64_t batch, float l2_lambda, float* loss, const float* grad_scale,
                     float* d_emb, int64_t ld_d, float* d_relation, float* d_trans_m, void* stream);
 
+/* ---- minibatch assembly (dataloader.py:192-318): per head one positive (tail, relation) drawn uniformly from the
+ *      head's triples and neg_rate negative tails drawn from `candidates` by rejection (not a positive of the head
+ *      under the drawn relation -- any relation when use_relation == 0 -- and not drawn before).  rowptr / tails / rels:
+ *      a CSR over heads whose rows are sorted by (relation, tail) (lkg_graph att_rowptr / att_tail / att_rel).
+ *      Outputs are [n_heads * neg_rate], head / relation / positive repeated neg_rate times like
+ *      generate_batch_by_neg_rate (dataloader.py:320-333).  Counter-based generator: the same seed gives the same
+ *      batch.  n_failed (device int32, accumulated): draws that found no admissible tail in max_tries (output -1). */
+int lkg_sample_batch(const int32_t* rowptr, const int32_t* tails, const int32_t* rels, const int64_t* heads,
+                     int64_t n_heads, const int64_t* candidates, int64_t n_candidates, int32_t neg_rate,
+                     int32_t use_relation, uint64_t seed, int32_t max_tries, int64_t* out_h,
+                     int64_t* out_r /*nullable*/, int64_t* out_pos, int64_t* out_neg, int32_t* n_failed, void* stream);
+
 /* ---- scoring (model.py:473-491) and the top-k / rank extension of BASELINE.json ------------- */
 /* scores[B,Nt] = heads @ tails^T with both operands given as planes (heads: gathered rows of the final
  * embeddings, tails: the candidate rows); minmax_dev (nullable) is an opaque uint32[2] running

@@ -8,7 +8,7 @@ The compute lives in liblkg.so (include/lkg.h); importing this package never fal
 from .gate import Gate, GateMul
 from .graph import GraphPlan
 from .model import Aggregator, LiteralKG
-from .dataloader import KGTensors
+from .dataloader import BatchSampler, KGTensors
 from . import ops, synthetic
 
-__all__ = ["LiteralKG", "Aggregator", "Gate", "GateMul", "GraphPlan", "KGTensors", "ops", "synthetic"]
+__all__ = ["LiteralKG", "Aggregator", "Gate", "GateMul", "GraphPlan", "KGTensors", "BatchSampler", "ops", "synthetic"]

@@ -68,6 +68,7 @@ SIGNATURES = {
     "lkg_colsum": (C.c_int, [vp, i64, i64, i32, vp, vp]),
     "lkg_gate_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, i64, vp, i64, vp]),
     "lkg_leaky_bwd": (C.c_int, [vp, i64, vp, i64, i64, i32, vp, i64, vp]),
+    "lkg_sample_batch": (C.c_int, [vp, vp, vp, vp, i64, vp, i64, i32, i32, C.c_uint64, i32, vp, vp, vp, vp, vp, vp]),
     "lkg_bpr_loss": (C.c_int, [vp, i64, i32, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp]),
     "lkg_transr_loss": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp, vp,
                                   vp]),

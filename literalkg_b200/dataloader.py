@@ -2,8 +2,9 @@
 
 Only the tensor-producing part of the reference loader is on the accelerated path (SURVEY.md 8(a) rows
 a1-a3): ``h_list / t_list / r_list``, the ``relations`` order, ``n_entities / n_relations``, the initial
-``A_in`` (sum of per-relation normalised adjacencies) and the dense literal tables.  Samplers and label
-files stay with the reference (section 8(f)).
+``A_in`` (sum of per-relation normalised adjacencies) and the dense literal tables -- plus the minibatch
+samplers of the two training loops (section 8(f) rank 1), which run as one kernel per batch (``BatchSampler``).
+Label files stay with the reference.
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _lib
 from .graph import GraphPlan
 
 
@@ -137,3 +139,49 @@ class KGTensors:
                 tt[k] = np.asarray(v, dtype=np.float32)
             text_table = tt
         return cls(trip[:, 0], trip[:, 2], trip[:, 1], num_table=num_table, text_table=text_table, **kw)
+
+
+class BatchSampler:
+    """Device-side ``generate_kg_batch`` / ``generate_prediction_batch`` (dataloader.py:221-318).
+
+    ``plan``: GraphPlan of the triples the positives come from (its att arrays are the per-head (tail, relation)
+    lists of ``train_kg_dict`` sorted by (relation, tail)); for fine-tuning, a plan of the (head, tail) pairs with
+    relation 0 (``head_dict``).  ``candidates``: the tails negatives are drawn from (``training_tails`` /
+    ``prediction_tail_ids``; repeats weigh a tail like they do in the reference's list).  Heads are drawn on the
+    host side of the binding exactly as upstream: without replacement when the batch fits the head list
+    (``random.sample``), with replacement otherwise; everything per head is one kernel (csrc/sample.cu)."""
+
+    def __init__(self, plan: GraphPlan, candidates, neg_rate: int, use_relation: bool, seed: int = 2022,
+                 max_tries: int = 10_000):
+        self.plan, self.neg_rate, self.use_relation = plan, int(neg_rate), bool(use_relation)
+        self.device = plan.device
+        self.candidates = torch.as_tensor(candidates, dtype=torch.int64).to(self.device).contiguous()
+        deg = plan.att_rowptr[1:] - plan.att_rowptr[:-1]
+        self.exist_heads = torch.nonzero(deg > 0).reshape(-1)            # list(kg_dict.keys())
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        self.seed, self.calls, self.max_tries = int(seed), 0, int(max_tries)
+        self.n_failed = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def sample(self, batch_size: int):
+        """-> (head, relation or None, pos_tail, neg_tail), int64 [n * neg_rate] with n = batch_size // neg_rate
+        (the division of dataloader.py:224 / :287)."""
+        n = int(batch_size / self.neg_rate)
+        ne = self.exist_heads.numel()
+        if n <= ne:
+            pick = torch.randperm(ne, device=self.device, generator=self.gen)[:n]
+        else:
+            pick = torch.randint(0, ne, (n,), device=self.device, generator=self.gen)
+        heads = self.exist_heads[pick].contiguous()
+        m = n * self.neg_rate
+        i64 = dict(dtype=torch.int64, device=self.device)
+        out_h, out_pos, out_neg = torch.empty(m, **i64), torch.empty(m, **i64), torch.empty(m, **i64)
+        out_r = torch.empty(m, **i64) if self.use_relation else None
+        self.calls += 1
+        p = self.plan
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().lkg_sample_batch(
+                p.att_rowptr.data_ptr(), p.att_tail.data_ptr(), p.att_rel.data_ptr(), heads.data_ptr(), n,
+                self.candidates.data_ptr(), self.candidates.numel(), self.neg_rate, int(self.use_relation),
+                (self.seed * 0x9E3779B1 + self.calls) & 0xFFFFFFFFFFFFFFFF, self.max_tries, out_h.data_ptr(),
+                _lib.ptr(out_r), out_pos.data_ptr(), out_neg.data_ptr(), self.n_failed.data_ptr(), _lib.stream()))
+        return out_h, out_r, out_pos, out_neg

@@ -342,7 +342,13 @@ class LiteralKG(nn.Module):
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
         self._part = None                                 # parallel.RowPartition when the path is row partitioned
         self._gate_prefetch = None                        # (key, gate stage) started by update_attention
-        self.sync_attention = True                        # partitioned update_att: all-reduce the A_in values
+        self.sync_attention = "lazy"                      # partitioned update_att: every rank fills its own rows of A_in;
+                                                          # True = all-reduce at once, "lazy" = on state_dict() /
+                                                          # complete_attention(), False = never
+        self._a_in_pending = None
+        self.cache_embeddings = True                      # eval mode: keep gat_embeddings() until an input changes
+        self._embed_cache = None
+        self._a_in_epoch = 0
         self.prefetch_gate = True                         # partitioned update_att: start the next pass's gate stage
         self._lit_key = None
 
@@ -377,6 +383,7 @@ class LiteralKG(nn.Module):
         plan = GraphPlan.from_coo(a._indices(), self.n_entities)
         values = plan.import_values(a._values())
         self._agg_plan, self._agg_values = plan, values
+        self._a_in_epoch += 1
         self.A_in.data = plan.sparse(values)              # same matrix, coalesced, values shared with the kernels
         return plan, values
 
@@ -395,6 +402,8 @@ class LiteralKG(nn.Module):
 
     def set_partition(self, part) -> None:
         """Row-partition the path over the ranks of ``part`` (``parallel.RowPartition``); None = single GPU."""
+        if part is None:
+            self.complete_attention()
         self._part = part
         self._lit_key = None
 
@@ -455,13 +464,25 @@ class LiteralKG(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._gat_embeddings_autograd()
         with torch.no_grad():
+            # The reference recomputes the whole graph for every head batch of an evaluation (utils/model_utils.py:55-60
+            # -> model.py:474).  In eval mode the result only depends on the parameters, the literal tables and A_in:
+            # it is kept until one of them changes (in-place version counters; update_att bumps the A_in epoch).
+            key = None
+            if self.cache_embeddings and not self.training:
+                key = (tuple((p.data_ptr(), p._version) for n_, p in self.named_parameters() if n_ != "A_in"),
+                       tuple(None if t is None else (t.data_ptr(), t._version)
+                             for t in (self.numerical_literals_embed, self.text_literals_embed)),
+                       self._a_in_epoch, self.A_in.data._values().data_ptr(), id(self._part), bool(gather))
+                if self._embed_cache is not None and self._embed_cache[0] == key:
+                    return self._embed_cache[1]
             out = self._gat_embeddings_native()
             part = self._part
-            if part is None or part.world == 1 or not gather:
-                return out
-            full = torch.empty((part.padded, out.shape[1]), dtype=torch.float32, device=out.device)
-            full[part.begin:part.end] = out
-            return part.all_gather_rows(full)[:self.n_entities]
+            if not (part is None or part.world == 1 or not gather):
+                full = torch.empty((part.padded, out.shape[1]), dtype=torch.float32, device=out.device)
+                full[part.begin:part.end] = out
+                out = part.all_gather_rows(full)[:self.n_entities]
+            self._embed_cache = None if key is None else (key, out)
+            return out
 
     def _stack_q(self, folds):
         """The h0 @ Q GEMM of all layers as ONE stacked weight: rows = [layer 0: q1 + pa | q2 | layer 1: q1 | q2 ...
@@ -807,10 +828,26 @@ class LiteralKG(nn.Module):
                 values = torch.zeros(max(plan.nnz, 1), dtype=torch.float32, device=dev)[:plan.nnz]
                 ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach(), out=values)
                 plan.set_row_range(0, self.n_entities)
-                if self.sync_attention:       # complete A_in on every rank (state dict); the layers only need own rows
+                self._a_in_pending = None
+                if self.sync_attention is True:   # complete A_in on every rank; the layers only need own rows
                     part.all_reduce(values)
+                elif self.sync_attention == "lazy":
+                    self._a_in_pending = values
         self._agg_plan, self._agg_values = plan, values
+        self._a_in_epoch += 1
         self.A_in.data = plan.sparse(values)
+
+    def complete_attention(self) -> None:
+        """Row partitioned: after ``update_att`` every rank holds the attention values of its own head rows (all the
+        embedding pass reads).  This sums the other ranks' rows in (x + 0 is exact) so that ``A_in`` is the full matrix
+        of the reference on every rank -- needed for checkpoints, not for the pass; collective, call it on all ranks."""
+        if self._a_in_pending is not None and self._part is not None:
+            self._part.all_reduce(self._a_in_pending)
+        self._a_in_pending = None
+
+    def state_dict(self, *args, **kwargs):
+        self.complete_attention()
+        return super().state_dict(*args, **kwargs)
 
     # ---- scoring -----------------------------------------------------------------------------------
     def calc_score(self, head_ids, tail_ids):
@@ -844,29 +881,42 @@ class LiteralKG(nn.Module):
     def topk_sharded(self, head_ids, k, local_embed, tail_index=None):
         """Row-partitioned all-entity top-k: every rank scores the heads against the entities it owns
         (``local_embed`` = ``gat_embeddings(gather=False)``) and the per-rank survivors are merged.  Returns
-        (values, entity ids) [B, k], identical on every rank."""
+        (values, entity ids) [B, k], identical on every rank.  ``head_ids`` may be a LIST of head batches: the
+        collectives (head rows, survivors) then run once for all of them and a list of results is returned."""
         part = self._part
         assert part is not None, "topk_sharded needs set_partition()"
+        many = isinstance(head_ids, (list, tuple))
+        batches = list(head_ids) if many else [head_ids]
         dev = local_embed.device
-        head_ids = head_ids.to(device=dev, dtype=torch.int64)
+        sizes = [int(hb.numel()) for hb in batches]
+        heads = torch.cat([hb.to(device=dev, dtype=torch.int64).reshape(-1) for hb in batches])
         # head rows from their owners: a zero-padded [B, G] block summed over the ranks (x + 0 is exact)
-        mine = (head_ids >= part.begin) & (head_ids < part.end)
-        hmat = torch.zeros((head_ids.numel(), local_embed.shape[1]), dtype=torch.float32, device=dev)
-        hmat[mine] = local_embed[head_ids[mine] - part.begin]
+        mine = (heads >= part.begin) & (heads < part.end)
+        hmat = torch.zeros((heads.numel(), local_embed.shape[1]), dtype=torch.float32, device=dev)
+        hmat[mine] = local_embed[heads[mine] - part.begin]
         part.all_reduce(hmat)
         if tail_index is None:
             tail_index = self.sharded_index(local_embed)
-        if ops.fused_topk_applicable(tail_index.m, local_embed.shape[1], k):
-            vals, pos = ops.score_topk(local_embed, None, None, k, tail_index=tail_index, head_emb=hmat)
-        else:
-            both = torch.cat([local_embed, hmat])
-            scores = ops.score(both, torch.arange(hmat.shape[0], device=dev) + local_embed.shape[0],
-                               torch.arange(local_embed.shape[0], device=dev), rec=tail_index.rec)
-            vals, pos, _ = ops.topk_rows(scores, k)
-        ids = torch.where(pos >= 0, pos + part.begin, pos)
+        fused = ops.fused_topk_applicable(tail_index.m, local_embed.shape[1], k)
+        vals_l, ids_l, off = [], [], 0
+        for nb in sizes:
+            hm = hmat[off:off + nb]
+            off += nb
+            if fused:
+                vals, pos = ops.score_topk(local_embed, None, None, k, tail_index=tail_index, head_emb=hm)
+            else:
+                both = torch.cat([local_embed, hm])
+                scores = ops.score(both, torch.arange(nb, device=dev) + local_embed.shape[0],
+                                   torch.arange(local_embed.shape[0], device=dev), rec=tail_index.rec)
+                vals, pos, _ = ops.topk_rows(scores, k)
+            vals_l.append(vals)
+            ids_l.append(torch.where(pos >= 0, pos + part.begin, pos))
         from .parallel import merge_topk
-        return merge_topk(part.all_gather_stack(vals), part.all_gather_stack(ids), k,
-                          lambda sc, kk: ops.topk_rows(sc, kk)[:2])
+        top_v, top_i = merge_topk(part.all_gather_stack(torch.cat(vals_l)), part.all_gather_stack(torch.cat(ids_l)), k,
+                                  lambda sc, kk: ops.topk_rows(sc, kk)[:2])
+        if not many:
+            return top_v, top_i
+        return list(zip(torch.split(top_v, sizes), torch.split(top_i, sizes)))
 
     def sharded_index(self, local_embed):
         """Tail index of this rank's rows with a scale record that bounds EVERY rank's embeddings (the head rows
