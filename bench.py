@@ -270,21 +270,46 @@ def run_ours(a):
     ids_pin = torch.arange(0, a.score_heads, dtype=torch.int64).pin_memory()
     out_pin = torch.empty((a.score_heads, emb.shape[1]), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        hd, td, rd = (x.to(dev, non_blocking=True) for x in (h_pin, t_pin, r_pin))
+    # Input pipeline: the step's edge list is uploaded from pinned memory on a copy stream into one of two device
+    # buffers while the previous step computes (what a production loader does); every timed step still owns one full
+    # H2D copy of its inputs and one D2H read of its result.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(x, device=dev) for x in (h_pin, t_pin, r_pin)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    ids_dev = torch.empty(ids_pin.shape, dtype=torch.int64, device=dev)
+
+    def upload(i):
+        s_ = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s_])             # the step that last read this slot is done with it
+            for dst, src in zip(slots[s_], (h_pin, t_pin, r_pin)):
+                dst.copy_(src, non_blocking=True)
+            ready[s_].record(copy_stream)
+
+    def e2e_step(i):
+        s_ = i % 2
+        torch.cuda.current_stream().wait_event(ready[s_])
+        upload(i + 1)                                        # next step's inputs travel while this one computes
+        hd, td, rd = slots[s_]
+        ids_dev.copy_(ids_pin, non_blocking=True)
         model(hd, td, rd, rels, device=dev, mode="update_att")
+        consumed[s_].record()
         if part is None:
-            res = model.get_final_embeddings(ids_pin.to(dev, non_blocking=True))
+            res = model.get_final_embeddings(ids_dev)
         else:       # every rank reads back the first rows of its own shard
             res = model.gat_embeddings(gather=False)[:a.score_heads]
         out_pin[:res.shape[0]].copy_(res, non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
+    for c_ in consumed:
+        c_.record()
+    upload(0)
+    for i in range(2):
+        e2e_step(i)
     sync()
     start.record()
-    for _ in range(a.steps):
-        e2e_step()
+    for i in range(2, 2 + a.steps):
+        e2e_step(i)
     end.record()
     sync()
     e2e_ms = start.elapsed_time(end) / a.steps

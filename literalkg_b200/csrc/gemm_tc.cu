@@ -25,11 +25,16 @@ namespace {
 
 using namespace tc;
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
-constexpr int kStages = 2;
-constexpr int kThreads = 192;     // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kStages = 4;        // upper bound; a launch uses as many as fit next to its B tile (TcParams::stages)
+constexpr int kThreads = 320;     // warps 0-3 and 6-9 epilogue (column halves), warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kEpiThreads = 256;
 constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
-constexpr uint32_t kStageBytes = kABytes + 2 * kMaxBN * kBK * 2;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kSmemBudget = 227 * 1024;
+__host__ __device__ constexpr uint32_t stage_bytes_for(int bn) { return kABytes + 2u * (uint32_t)bn * kBK * 2u; }
+inline int stages_for(int bn) {
+    const int s = (int)((kSmemBudget - 1024 - 256) / stage_bytes_for(bn));
+    return s > kStages ? kStages : s;
+}
 
 enum EpiKind { kEpiLinear = 0, kEpiGate = 1, kEpiScore = 2 };
 
@@ -44,6 +49,8 @@ struct TcParams {
     int bn;                             // N tile (multiple of 16, <= 256)
     int tiles_m, tiles_n;
     int m_fastest;
+    int stages;                         // pipeline depth of this launch (2 .. kStages)
+    uint32_t stage_bytes;               // kABytes + hi/lo planes of a bn x 64 B tile
     // epilogue
     const float* bias;                  // linear: [n]; gate: interleaved pairs [n]
     int act;
@@ -210,7 +217,9 @@ template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    const uint32_t kStageBytes = p.stage_bytes;
+    const int n_stages = p.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
     uint64_t* full = bars;                 // [kStages]  TMA bytes landed
     uint64_t* empty = bars + kStages;      // [kStages]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * kStages;       // [2]  accumulator complete
@@ -226,13 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         for (int s = 0; s < p.n_segments; ++s)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&p.b_map) : "memory");
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], kEpiThreads);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         mbar_expect_tx(&full[stage], kABytes + b_bytes);
                         tma_load_3d(&p.a_map[s], &full[stage], st, j * kBK, mb * kBM, 0);
                         tma_load_3d(&p.b_map, &full[stage], st + kABytes, p.seg_bcol[s] + j * kBK, nb * p.bn, 0);
-                        if (++stage == kStages) {
+                        if (++stage == (uint32_t)n_stages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         tc_mma_f16(tmem_d, dah, dbl, idesc, 1);
                     }
                     tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
-                    if (++stage == kStages) {
+                    if (++stage == (uint32_t)n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -330,13 +339,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            const int64_t row = (int64_t)mb * kBM + warp * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * kMaxBN;
-            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            // a warp reads the TMEM lanes of its quarter (warp % 4); warps 0-3 take the first half of the tile's
+            // columns, warps 6-9 the second: the epilogue (global loads / stores per 16 columns) was longer than the
+            // MMAs of a tile with four warps
+            const int quarter = warp & 3;
+            const int c_split = ((p.bn / 16 + 1) / 2) * 16;
+            const int c_begin = warp < 4 ? 0 : c_split, c_end = warp < 4 ? min(c_split, p.bn) : p.bn;
+            const int64_t row = (int64_t)mb * kBM + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
+            uint32_t raw[16];
+            if (c_begin < c_end) tc_ld16_nowait(taddr + c_begin, raw);
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float v[16];
-                tc_ld16(taddr + c0, v);
+                tc_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= acc_scale;
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * acc_scale;
+                if (c0 + 16 < c_end) tc_ld16_nowait(taddr + c0 + 16, raw);   // next columns travel during this step
                 epilogue16<EPI>(p, row, nb * p.bn + c0, v, out_scale, lo, hi);
             }
             tc_fence_before();
@@ -381,11 +399,18 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld
     return LKG_OK;
 }
 
-int pick_bn(int n) {
-    // smallest number of N tiles, then the smallest tile (multiple of 16) that covers n
-    const int tiles = (n + kMaxBN - 1) / kMaxBN;
-    int bn = ((n + tiles - 1) / tiles + 15) / 16 * 16;
-    return bn < 16 ? 16 : bn;
+int pick_bn(int n, bool deep) {
+    // smallest number of N tiles, then the smallest tile (multiple of 16) that covers n.  `deep`: take one or two
+    // more tiles when that lets a third pipeline stage fit -- with two stages a k-chunk waits for a whole L2 round
+    // trip of its 80 KB before the next one may start (ncu r01: tile time 2 x the MMA time)
+    int tiles = (n + kMaxBN - 1) / kMaxBN;
+    auto bn_of = [&](int t) {
+        const int b = ((n + t - 1) / t + 15) / 16 * 16;
+        return b < 16 ? 16 : b;
+    };
+    if (deep)
+        for (int extra = 0; extra < 2 && stages_for(bn_of(tiles)) < 3; ++extra) ++tiles;
+    return bn_of(tiles);
 }
 
 template <int EPI>
@@ -401,7 +426,11 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
     }
     p.m = m;
     p.n = n;
-    p.bn = pick_bn(n);
+    p.bn = pick_bn(n, false);   // measured: extra N tiles for a third stage re-read A and gain nothing (gate 2.69 -> 2.83 ms)
+    p.stages = stages_for(p.bn);
+    p.stage_bytes = stage_bytes_for(p.bn);
+    LKG_REQUIRE(p.stages >= 2, "GEMM tile does not fit shared memory");
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
     p.tiles_m = (int)((m + kBM - 1) / kBM);
     p.tiles_n = (n + p.bn - 1) / p.bn;
     int bcol = 0;
@@ -416,10 +445,10 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
                 "B has %d columns, the A segments need %d", b->k[0], bcol);
     if (int rc = make_map(&p.b_map, b->ptr[0], n, b->k[0], b->ld[0], b->plane_stride[0], p.bn)) return rc;
     auto kern = tc_gemm_kernel<EPI>;
-    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
     LKG_LAUNCH_CHECK("tc_gemm_kernel");
     return LKG_OK;
 }

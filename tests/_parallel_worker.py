@@ -31,6 +31,12 @@ def cpu_collectives(rank, world, port, out_dir):
     buf[part.begin:part.end] = ref[part.begin:part.end]
     part.all_gather_rows(buf)
     assert torch.equal(buf[:n], ref[:n])
+    buf2 = torch.full((part.padded, d), -1.0)
+    buf2[part.begin:part.end] = ref[part.begin:part.end]
+    work = part.all_gather_rows(buf2, async_op=True)     # handle form used by the overlapped gate stage
+    if work is not None:
+        work.wait()
+    assert torch.equal(buf2[:n], ref[:n])
     t = torch.full((5,), float(rank + 1))
     part.all_reduce(t)
     assert torch.equal(t, torch.full((5,), float(sum(range(1, world + 1)))))
