@@ -26,8 +26,10 @@ namespace {
 using namespace tc;
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
 constexpr int kStages = 4;        // upper bound; a launch uses as many as fit next to its B tile (TcParams::stages)
-constexpr int kThreads = 320;     // warps 0-3 and 6-9 epilogue (column halves), warp 4 TMA producer, warp 5 MMA issuer
-constexpr int kEpiThreads = 256;
+constexpr int kEpiGroups = 3;     // epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range
+constexpr int kThreads = 64 + 128 * kEpiGroups;   // warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer,
+                                                  // warps 6.. epilogue groups 1..
+constexpr int kEpiThreads = 128 * kEpiGroups;
 constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
 constexpr uint32_t kSmemBudget = 227 * 1024;
 __host__ __device__ constexpr uint32_t stage_bytes_for(int bn) { return kABytes + 2u * (uint32_t)bn * kBK * 2u; }
@@ -339,12 +341,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            // a warp reads the TMEM lanes of its quarter (warp % 4); warps 0-3 take the first half of the tile's
-            // columns, warps 6-9 the second: the epilogue (global loads / stores per 16 columns) was longer than the
+            // a warp reads the TMEM lanes of its quarter (warp % 4); every group of four
+            // warps takes its own range of the tile's columns: the epilogue (global loads / stores per 16 columns) was longer than the
             // MMAs of a tile with four warps
             const int quarter = warp & 3;
-            const int c_split = ((p.bn / 16 + 1) / 2) * 16;
-            const int c_begin = warp < 4 ? 0 : c_split, c_end = warp < 4 ? min(c_split, p.bn) : p.bn;
+            const int group = warp < 4 ? 0 : 1 + (warp - 6) / 4;
+            const int c_per = ((p.bn / 16 + kEpiGroups - 1) / kEpiGroups) * 16;
+            const int c_begin = min(group * c_per, p.bn), c_end = min(c_begin + c_per, p.bn);
             const int64_t row = (int64_t)mb * kBM + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
             uint32_t raw[16];
