@@ -183,6 +183,8 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # 128 MB all-gathers at 8 ranks: 0.30 ms with NCCL's default channel count, 0.21 ms with 32 (scratch/nccl_probe.py)
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -366,7 +368,7 @@ def run_ours(a):
                    "calls": {k_: round(v["ms_avg"], 4) for k_, v in sprof.items()}}
 
     training = None
-    if world == 1 and not a.no_training:
+    if not a.no_training:
         # one optimisation step's worth of kernels: fine-tuning (BPR) loss on the reference's effective minibatch of
         # 681 triples, full-graph forward with saved activations + backward to every parameter
         # (main.py:222-226: loss.backward()); reported next to the inference pass, not part of `value`
@@ -400,6 +402,10 @@ def run_ours(a):
             for layer in model.aggregator_layers:
                 layer.dropout = 0.0
         tms = start.elapsed_time(end) / kt
+        if world > 1:
+            tt = torch.tensor([tms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tms = tt.item()
         training = {"metric": "edges/s, fine-tuning step (forward with saved activations + backward to all parameters, "
                               "batch 681, dropout 0.1)", "value": e / (tms / 1e3), "unit": UNIT, "ms_per_step": tms,
                     "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,

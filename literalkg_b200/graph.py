@@ -81,6 +81,7 @@ class GraphPlan:
         self._scratch = torch.zeros(64, dtype=torch.int32, device=dev)   # dynamic row counter of the kernels
         self._attn_ws = None
         self._transposed = None
+        self._transposed_part = None
 
     # -- constructors ---------------------------------------------------------------------------
     @classmethod
@@ -165,9 +166,18 @@ class GraphPlan:
     def scratch(self) -> int:
         return self._scratch.data_ptr()
 
-    def transposed(self):
+    def transposed(self, rows=None):
         """(t_tail, t_head, t_perm): the unique (h, t) pairs as a COO list sorted by (tail, head); t_perm = position of
-        the pair in agg order.  What the backward of ``A_in @ x`` gathers over (built on first use, cached)."""
+        the pair in agg order.  What the backward of ``A_in @ x`` gathers over (built on first use, cached).
+        ``rows`` = (begin, end): only the pairs whose HEAD lies in that range, heads renumbered from ``begin`` (the
+        row partition: a rank reduces its own head rows into every tail row)."""
+        if rows is not None:
+            if self._transposed_part is None or self._transposed_part[0] != tuple(rows):
+                t_tail, t_head, t_perm = self.transposed()
+                keep = (t_head >= rows[0]) & (t_head < rows[1])           # order by (tail, head) is preserved
+                self._transposed_part = (tuple(rows), (t_tail[keep].contiguous(),
+                                                       (t_head[keep] - rows[0]).contiguous(), t_perm[keep].contiguous()))
+            return self._transposed_part[1]
         if self._transposed is None:
             lib = _lib.load()
             i32 = dict(dtype=torch.int32, device=self.device)

@@ -217,6 +217,13 @@ class _GatEmbeddingsFn(torch.autograd.Function):
     def forward(ctx, model, pre, *leaves):
         keep: dict = {}
         out = model._gat_embeddings_native(keep=keep, pre=pre)
+        part = model._part if (model._part is not None and model._part.world > 1) else None
+        if part is not None:
+            # every rank evaluates the (replicated) loss on the full matrix: the gradient of that replica w.r.t. this
+            # rank's rows is simply its row slice of d loss / d out
+            full = torch.empty((part.padded, out.shape[1]), dtype=torch.float32, device=out.device)
+            full[part.begin:part.end] = out
+            out = part.all_gather_rows(full)[:model.n_entities]
         if getattr(model, "debug_keep_activations", False):      # tests: sign pattern of the LeakyReLU inputs
             model._debug_keep = keep
         ctx.model, ctx.pre, ctx.keep = model, pre, keep
@@ -337,6 +344,8 @@ class LiteralKG(nn.Module):
         self._agg_values: Optional[torch.Tensor] = None   # its values, plan order (shared with A_in.data)
         self._att_plan: Optional[GraphPlan] = None        # plan of the (h, t, r) lists given to update_att
         self._att_key = None
+        self._att_ident = None
+        self._att_refs = None
         self._lit_planes = None                           # fp16 hi/lo planes of the (constant) literal tables
         self._unit_rec = None                             # scale record of planes bounded by 1 (normalised rows)
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
@@ -642,8 +651,6 @@ class LiteralKG(nn.Module):
         The parameter folds and the interleaved gate weight are built under autograd from the
         live parameters, so the kernels only produce gradients w.r.t. the folded tensors and torch chains them on
         to linear / linear_h0 / weight / g / gate_* (tiny d x d matrix products)."""
-        if self._part is not None and self._part.world > 1:
-            raise NotImplementedError("the backward pass is single-GPU in this round: call set_partition(None) to train")
         folds = [layer.folded(self.lamda, self.alpha, k + 1, differentiable=True)
                  for k, layer in enumerate(self.aggregator_layers)]
         wq = cq = None
@@ -669,11 +676,33 @@ class LiteralKG(nn.Module):
         return _GatEmbeddingsFn.apply(self, pre, *leaves)
 
     def _gat_backward(self, keep: dict, pre: dict, g_out: torch.Tensor) -> List[Optional[torch.Tensor]]:
-        """Gradients w.r.t. the leaves of ``_gat_embeddings_autograd`` (same order)."""
+        """Gradients w.r.t. the leaves of ``_gat_embeddings_autograd`` (same order).
+
+        Row partitioned: every rank differentiates its own head rows.  ``A^T x`` sums over ALL head rows, so each rank
+        reduces its own rows' entries into a full-height partial and a reduce-scatter (the dual of the forward's
+        all-gather) hands every rank the sum for its rows; parameter gradients are partial sums that one all-reduce
+        completes, and the rows of d entity_embed are all-gathered (the table is replicated, like its optimizer)."""
         dev = g_out.device
-        n, d, total = self.n_entities, self.embed_dim, self.total_conv_dim
+        d, total = self.embed_dim, self.total_conv_dim
         L = self.n_layers
+        part = self._part if (self._part is not None and self._part.world > 1) else None
+        rb, re = (0, self.n_entities) if part is None else (part.begin, part.end)
+        n = re - rb                                   # rows this rank differentiates
         plan, a_values = keep["plan"], keep["a_values"]
+        own = (lambda t_: t_) if part is None else (lambda t_: t_[rb:re])
+        if part is not None:
+            g_out = g_out[rb:re]
+        t_coo = plan.transposed() if part is None else plan.transposed(rows=(rb, re))
+
+        def spmm_t(x_rows, dst):
+            """dst (this rank's rows) += (A^T x)[rows]; x_rows: this rank's head rows."""
+            if part is None:
+                return ops.spmm_coo(t_coo, a_values, x_rows, dst)
+            full = torch.zeros((part.padded, x_rows.shape[1]), dtype=torch.float32, device=dev)
+            ops.spmm_coo(t_coo, a_values, x_rows, full)
+            dst += part.reduce_scatter_rows(full)[:n]
+            return dst
+
         folds, wq, offsets, zcol = pre["folds"], pre["wq"], pre["offsets"], pre["zcol"]
         f32 = dict(dtype=torch.float32, device=dev)
         colsum = ops.colsum
@@ -711,7 +740,7 @@ class LiteralKG(nn.Module):
             layer, f, sv = self.aggregator_layers[k], folds[k], keep["layers"][k]
             c, dk = layer.out_dim, layer.in_dim
             col -= c
-            x_k, y_k = sv["x"], sv["y"]
+            x_k, y_k = own(sv["x"]), own(sv["y"])
             has_o2 = f["p2"] is not None
             nt = 2 if has_o2 else 1
             d_o = dmat[:, offsets[k]:offsets[k] + nt * c] if residual else torch.empty((n, nt * c), **f32)
@@ -724,7 +753,7 @@ class LiteralKG(nn.Module):
             z_path = fold_ego and zcol >= 0                    # ... and so does the projected sum term
             t1 = dmat[:, zcol:zcol + c] if z_path else torch.empty((n, c), **f32)
             t1.zero_()
-            ops.spmm_t(plan, a_values, do1, t1)                # A^T do1: (A x) Pb backward without the wide gather
+            spmm_t(do1, t1)                                    # A^T do1: (A x) Pb backward without the wide gather
             g = dict.fromkeys(self._FOLD_KEYS)
             use_pa = f["pa"] is not None and not fold_ego
             use_pb = not z_path
@@ -753,7 +782,7 @@ class LiteralKG(nn.Module):
             if has_o2:
                 wbuf, xs = torch.empty((n, dk), **f32), torch.empty((n, dk), **f32)
                 ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True, xs_out=xs)
-                ops.spmm_t(plan, a_values, wbuf, dx)
+                spmm_t(wbuf, dx)
                 g["p2"] = ops.xt_y_planes(ops.split_planes(xs), ops.split_planes(do2))   # (x * side)^T do2
                 del wbuf, xs
             layer_grads[k] = (g, dgb[:c], dgb[c:])
@@ -770,7 +799,7 @@ class LiteralKG(nn.Module):
         gate_mod, tables = self._gate_module()
         g_wpair = g_bpair = None
         if gate_mod is not None:
-            ent = self.entity_embed.weight.detach()
+            ent = own(self.entity_embed.weight.detach())
             w_pair = pre["packed"][0]
             d_pre = torch.empty((n, 2 * d), **f32)
             g_ent = torch.empty((n, d), **f32)
@@ -791,6 +820,17 @@ class LiteralKG(nn.Module):
             grads += [g[key] for key in self._FOLD_KEYS] + [g_lw, g_lb]
         if self.scale_gat_dim is not None:
             grads += [g_wg, g_bg]
+        if part is not None:
+            full = torch.zeros((part.padded, d), **f32)
+            full[rb:re] = g_ent
+            grads[0] = part.all_gather_rows(full)[:self.n_entities]
+            small = [g_ for g_ in grads[1:] if g_ is not None]                # partial sums over this rank's rows
+            flat = torch.cat([g_.reshape(-1) for g_ in small])
+            part.all_reduce(flat)
+            off = 0
+            for g_ in small:
+                g_.copy_(flat[off:off + g_.numel()].view(g_.shape))
+                off += g_.numel()
         return grads
 
     # ---- losses ----------------------------------------------------------------------------------
@@ -811,11 +851,18 @@ class LiteralKG(nn.Module):
         dev = self._param_device()
         i64 = dict(device=dev, dtype=torch.int64, non_blocking=True)
         h, t, r = h_list.to(**i64).contiguous(), t_list.to(**i64).contiguous(), r_list.to(**i64).contiguous()
-        # the CSR plan only depends on the edge list: recognise an unchanged list by content, not by address
-        key = (GraphPlan.fingerprint(h, t, r), tuple(int(x) for x in relations))
-        if self._att_plan is None or self._att_key != key:
-            self._att_plan = GraphPlan(h, t, r, self.n_entities, self.n_relations, relations)
-            self._att_key = key
+        # the CSR plan only depends on the edge list.  The very same tensors (address, length, in-place version) as
+        # last time need no look at all; otherwise an unchanged list is recognised by content (one small kernel + a
+        # scalar read-back), not by address
+        rels = tuple(int(x) for x in relations)
+        ident = (tuple((x.data_ptr(), x.numel(), x._version) for x in (h, t, r)), rels)
+        if self._att_plan is None or self._att_ident != ident:
+            key = (GraphPlan.fingerprint(h, t, r), rels)
+            if self._att_plan is None or self._att_key != key:
+                self._att_plan = GraphPlan(h, t, r, self.n_entities, self.n_relations, relations)
+                self._att_key = key
+            self._att_ident = ident
+            self._att_refs = (h, t, r)          # keeps the addresses from being reused by other tensors
         plan = self._att_plan
         part = self._part if (self._part is not None and self._part.world > 1) else None
         with torch.no_grad():

@@ -87,6 +87,20 @@ class RowPartition:
             work = dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=self.group, async_op=async_op)
         return work if async_op else buf
 
+    def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
+        """``full`` [padded, d]: every rank's partial sums for ALL rows -> [chunk, d], the sum over the ranks of this
+        rank's row block (the dual of ``all_gather_rows``; used by the backward of ``A_in @ x``)."""
+        assert full.is_contiguous() and full.shape[0] == self.padded
+        if self.world == 1:
+            return full
+        with _comm_profile(full, "reduce_scatter", full.numel() * full.element_size(), False):
+            if self._backend() == "nccl" and full.is_cuda:
+                out = torch.empty((self.chunk, full.shape[1]), dtype=full.dtype, device=full.device)
+                dist.reduce_scatter_tensor(out.view(-1), full.view(-1), group=self.group)
+                return out
+            self.all_reduce(full)                              # gloo: no reduce-scatter for these tensors
+            return full[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.world == 1:
             return t

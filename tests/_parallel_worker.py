@@ -12,10 +12,10 @@ import torch
 import torch.distributed as dist
 
 
-def _init(rank, world, port):
+def _init(rank, world, port, backend="gloo"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group(backend, rank=rank, world_size=world)
 
 
 def cpu_collectives(rank, world, port, out_dir):
@@ -37,6 +37,9 @@ def cpu_collectives(rank, world, port, out_dir):
     if work is not None:
         work.wait()
     assert torch.equal(buf2[:n], ref[:n])
+    partial = torch.full((part.padded, d), float(rank + 1))
+    rs = part.reduce_scatter_rows(partial)
+    assert rs.shape == (part.chunk, d) and torch.equal(rs, torch.full((part.chunk, d), float(sum(range(1, world + 1)))))
     t = torch.full((5,), float(rank + 1))
     part.all_reduce(t)
     assert torch.equal(t, torch.full((5,), float(sum(range(1, world + 1)))))
@@ -62,11 +65,13 @@ def cpu_collectives(rank, world, port, out_dir):
 def gpu_partitioned_model(rank, world, port, out_dir):
     """Both ranks share cuda:0 (gloo stages the collectives through the host): the row-partitioned path must
     reproduce the single-GPU results."""
-    _init(rank, world, port)
+    # one GPU per rank over NCCL when the box has them, else both ranks share cuda:0 and gloo stages through the host
+    nccl = torch.cuda.device_count() >= world
+    _init(rank, world, port, "nccl" if nccl else "gloo")
     import literalkg_b200 as L
     import literalkg_oracle as O
     from literalkg_b200.parallel import RowPartition
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(rank if nccl else 0)
     cfg = O.OracleConfig(n_conv_layers=3, mess_dropout=0.0)
     n, n_rel = 20_001, 8
     kg = L.synthetic.make_kg(n, 150_000, n_rel, seed=4, max_out_degree=300)
@@ -118,5 +123,29 @@ def gpu_partitioned_model(rank, world, port, out_dir):
     # a list of head batches shares one round of collectives: same results per batch
     many = multi.topk_sharded([heads[:70], heads[70:]], k, local)
     assert torch.equal(torch.cat([m_[1] for m_ in many]), si2) and torch.equal(torch.cat([m_[0] for m_ in many]), sv2)
-    open(os.path.join(out_dir, f"ok{rank}"), "w").write(f"{err:.3e}")
+    # training modes: the row-partitioned backward (reduce-scatter of the A^T partials, all-reduce of the parameter
+    # gradients, all-gather of the entity-gradient rows) must reproduce the single-GPU gradients on every rank
+    torch.set_grad_enabled(True)
+    gen = torch.Generator().manual_seed(9)
+    bh, bp, bn = (torch.randint(0, n, (512,), generator=gen).cuda() for _ in range(3))
+    br = torch.randint(0, n_rel, (512,), generator=gen).cuda()
+    for mode, batch in (("fine_tuning", (bh, bp, bn)), ("pre_training", (bh, br, bp, bn))):
+        losses = []
+        for m in (single, multi):
+            m.train()
+            m.zero_grad(set_to_none=True)
+            loss = m(*batch, device="cuda", mode=mode)
+            loss.backward()
+            losses.append(loss.item())
+        assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0]), (mode, losses)
+        worst = 0.0
+        for (k1, p1), (k2, p2) in zip(single.named_parameters(), multi.named_parameters()):
+            if k1 == "A_in":
+                continue
+            assert (p1.grad is None) == (p2.grad is None), k1
+            if p1.grad is not None:
+                e_ = ((p1.grad - p2.grad).abs().max() / p1.grad.abs().max().clamp_min(1e-30)).item()
+                assert e_ < 2e-4, (mode, k1, e_)          # per-rank operand scales and summation orders differ
+                worst = max(worst, e_)
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write(f"{err:.3e} grad {worst:.3e}")
     dist.destroy_process_group()
