@@ -230,20 +230,36 @@ def run_ours(a):
         emb = step()
     sync()
     nnz = model._agg_plan.nnz
-    ops.PROFILE = ops.Profile()
+    # timed region: the kernels the roofline is computed for are bracketed by CUDA events on their stream; every other
+    # entry point is only counted (two event records per call are host time, which a 7 ms multi-GPU pass cannot hide).
+    # The full per-call breakdown comes from two more passes after the timed region.
+    roof_names = set(algorithmic_bytes(1, 1, 1, 1, cfg.embed_dim, cfg.conv_dim, 1))
+    ops.PROFILE = ops.Profile(only=roof_names)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         sync()
+        t_host = time.perf_counter()
         start.record()
         for _ in range(a.steps):
             emb = step()
         end.record()
+        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / a.steps     # time to enqueue a pass (no sync inside)
         sync()
     ms = start.elapsed_time(end) / a.steps
     prof = ops.PROFILE
-    ops.PROFILE = None
     kern = prof.summary()
+    for v_ in kern.values():
+        v_["passes"] = a.steps
     launches = prof.launches
+    ops.PROFILE = ops.Profile()
+    for _ in range(2):
+        emb = step()
+    sync()
+    full = ops.PROFILE.summary()
+    ops.PROFILE = None
+    for k_, v_ in full.items():
+        v_["passes"] = 2
+        kern.setdefault(k_, v_)
     if world > 1:
         tms = torch.tensor([ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -264,9 +280,10 @@ def run_ours(a):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab[dom], "kernel_ms_avg": kern[dom]["ms_avg"],
-                "kernels": {k: {"ms_avg": round(v["ms_avg"], 4), "share": round(v["ms_total"] / (ms * a.steps), 4),
+                "kernels": {k: {"ms_avg": round(v["ms_avg"], 4), "share": round(v["ms_total"] / v["passes"] / ms, 4),
                                 **({"GBps": round(ab[k] / v["ms_avg"] / 1e6, 1)} if k in ab else {})}
-                            for k, v in kern.items()}}
+                            for k, v in kern.items()},
+                "host_issue_ms_per_step": host_issue_ms}
 
     # e2e: public API with host buffers; H2D of the step's inputs and D2H of its result inside the timed region
     ids_pin = torch.arange(0, a.score_heads, dtype=torch.int64).pin_memory()

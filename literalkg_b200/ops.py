@@ -17,9 +17,11 @@ class Profile:
     """Optional per-entry-point CUDA-event timing + kernel-launch counting (used by bench.py).  Events are
     recorded on the current stream, which is the stream every kernel of this library is launched on."""
 
-    def __init__(self):
+    def __init__(self, only=None):
         self.events = []          # (name, start_event, end_event)
         self.launches = 0
+        self.only = only          # optional set of entry-point names to time (launches are always counted): two
+                                  # event records per call are host time that a short multi-GPU pass cannot hide
 
     def summary(self):
         torch.cuda.synchronize()
@@ -43,15 +45,17 @@ class _dev_guard:
 
     def __enter__(self):
         self.guard.__enter__()
-        if PROFILE is not None and self.name:
+        self.timed = PROFILE is not None and bool(self.name) and (PROFILE.only is None or self.name in PROFILE.only)
+        if self.timed:
             self.start = torch.cuda.Event(enable_timing=True)
             self.start.record()
 
     def __exit__(self, *exc):
-        if PROFILE is not None and self.name:
+        if self.timed:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
             PROFILE.events.append((self.name, self.start, end))
+        if PROFILE is not None and self.name:
             PROFILE.launches += self.kernels
         return self.guard.__exit__(*exc)
 

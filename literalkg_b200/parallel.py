@@ -28,7 +28,7 @@ class _comm_profile:
 
     def __init__(self, t: torch.Tensor, kind: str, nbytes: int, async_op: bool):
         from . import ops
-        self.on = ops.PROFILE is not None and t.is_cuda and not async_op
+        self.on = ops.PROFILE is not None and ops.PROFILE.only is None and t.is_cuda and not async_op
         self.name = f"{kind}_{nbytes / 1e6:.0f}MB"
 
     def __enter__(self):
