@@ -14,6 +14,36 @@ import torch
 from . import _lib
 
 
+def expand_schedule(sched: torch.Tensor, seg_degree: int = _lib.SEG_DEGREE, max_segs: int = _lib.MAX_SEGS,
+                    solo_degree: int = _lib.SOLO_DEGREE):
+    """``sched`` int32 [N, 8] = {row, att_lo, att_hi, agg_lo, agg_hi, 0, 0, 0} sorted by decreasing triple count ->
+    (schedule with the leading rows of more than ``seg_degree`` triples cut into min(ceil(count / seg_degree),
+    max_segs) records {row, att sub-range, agg sub-range, nseg, ticket, piece}, number of rows above ``solo_degree``,
+    number of segmented rows).  The sub-ranges of a row partition its att range and its agg range exactly, in order;
+    ticket = position of the row among the segmented rows.  Works on any device (tested on CPU)."""
+    deg = (sched[:, 2] - sched[:, 1]).long()
+    if sched.shape[0] == 0:
+        return sched, 0, 0
+    n_solo, n_heavy = (int(x) for x in torch.stack([(deg > solo_degree).sum(), (deg > seg_degree).sum()]).tolist())
+    if n_heavy == 0:
+        return sched, n_solo, 0
+    dev = sched.device
+    hv = sched[:n_heavy].long()
+    nseg = torch.clamp((deg[:n_heavy] + seg_degree - 1) // seg_degree, max=max_segs)
+    rid = torch.repeat_interleave(torch.arange(n_heavy, device=dev), nseg)              # = ticket of the row
+    piece = torch.arange(rid.numel(), device=dev) - (torch.cumsum(nseg, 0) - nseg)[rid]
+    ns = nseg[rid]
+
+    def cut(lo, hi):
+        ln = hi - lo
+        return lo + ln * piece // ns, lo + ln * (piece + 1) // ns
+
+    e0, e1 = cut(hv[rid, 1], hv[rid, 2])
+    u0, u1 = cut(hv[rid, 3], hv[rid, 4])
+    seg = torch.stack([hv[rid, 0], e0, e1, u0, u1, ns, rid, piece], dim=1).to(torch.int32)
+    return torch.cat([seg, sched[n_heavy:]]).contiguous(), n_solo, n_heavy
+
+
 class GraphPlan:
     """att order = kept triples sorted by (h, r, t); agg order = unique (h, t) pairs sorted by (h, t),
     i.e. the coalesced ``A_in`` of the reference.  ``file_seg[i]`` = pair index of input triple i."""
@@ -98,27 +128,13 @@ class GraphPlan:
         process; a row-long dependent chain in ONE warp is what bounds the kernels once the graph is split over
         several GPUs (a 4 096-triple row streams for ~0.7 ms).  Integer bookkeeping on the device, two scalar
         read-backs per plan build."""
-        sched, deg = self.row_sched, self._row_deg.long()
-        n_solo, n_heavy = torch.stack([(deg > _lib.SOLO_DEGREE).sum(), (deg > _lib.SEG_DEGREE).sum()]).tolist()
-        self._solo_full = int(n_solo)
+        sched, n_solo, n_heavy = expand_schedule(self.row_sched)
+        self._solo_full = n_solo
         self.c.n_solo_rows = self._solo_full
         self.c.n_sched = sched.shape[0]
         if n_heavy == 0:
             return
-        hv = sched[:n_heavy].long()
-        nseg = torch.clamp((deg[:n_heavy] + _lib.SEG_DEGREE - 1) // _lib.SEG_DEGREE, max=_lib.MAX_SEGS)
-        rid = torch.repeat_interleave(torch.arange(n_heavy, device=self.device), nseg)        # = ticket of the row
-        piece = torch.arange(rid.numel(), device=self.device) - (torch.cumsum(nseg, 0) - nseg)[rid]
-        ns = nseg[rid]
-
-        def cut(lo, hi):
-            ln = hi - lo
-            return lo + ln * piece // ns, lo + ln * (piece + 1) // ns
-
-        e0, e1 = cut(hv[rid, 1], hv[rid, 2])
-        u0, u1 = cut(hv[rid, 3], hv[rid, 4])
-        seg = torch.stack([hv[rid, 0], e0, e1, u0, u1, ns, rid, piece], dim=1).to(torch.int32)
-        self.row_sched = torch.cat([seg, sched[n_heavy:]]).contiguous()
+        self.row_sched = sched
         self._seg_tickets = torch.zeros(n_heavy, dtype=torch.int32, device=self.device)
         self._seg_scratch = torch.empty((n_heavy * _lib.MAX_SEGS, _lib.SEG_STRIDE), dtype=torch.float32, device=self.device)
         self.c.row_sched = self.row_sched.data_ptr()
