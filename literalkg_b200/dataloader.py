@@ -21,10 +21,26 @@ from .graph import GraphPlan
 
 def read_triples(path: str) -> np.ndarray:
     """``h r t`` per line, space separated; exact duplicate rows dropped keeping the first occurrence and
-    the file order (``load_graph`` dataloader.py:186-190).  Returns int64 [E, 3] in (h, r, t) columns."""
-    arr = np.loadtxt(path, dtype=np.int64, ndmin=2)
-    if arr.shape[1] != 3:
+    the file order (``load_graph`` dataloader.py:186-190).  Returns int64 [E, 3] in (h, r, t) columns.
+
+    The reference walks the frame with ``iterrows`` (~9 s per 200 k rows); here the file goes
+    through pandas' C parser and the de-duplication is one sort of packed 64-bit keys."""
+    try:
+        import pandas as pd
+        arr = pd.read_csv(path, sep=" ", header=None, names=["h", "r", "t"], dtype=np.int64,
+                          engine="c").to_numpy(dtype=np.int64)
+    except Exception:                       # ragged whitespace etc.: the tolerant reader
+        arr = np.loadtxt(path, dtype=np.int64, ndmin=2)
+    if arr.ndim != 2 or arr.shape[1] != 3:
         raise ValueError(f"{path}: expected 3 columns 'h r t'")
+    if arr.shape[0] == 0:
+        return arr
+    if arr.min() >= 0:
+        bits = [max(1, int(arr[:, c].max()).bit_length()) for c in range(3)]
+        if sum(bits) <= 63:                 # one sortable key per row
+            key = (arr[:, 0] << (bits[1] + bits[2])) | (arr[:, 1] << bits[2]) | arr[:, 2]
+            _, first = np.unique(key, return_index=True)
+            return arr[np.sort(first)]
     _, first = np.unique(arr, axis=0, return_index=True)
     return arr[np.sort(first)]
 
