@@ -78,3 +78,39 @@ def test_oracle_matches_live_reference(agg, res, layers, seed):
             for k, v in model.named_parameters():
                 if k != "A_in" and v.grad is not None:
                     close(pg[k].grad, v.grad, 5e-4)
+
+
+def test_reference_checkpoint_loads_into_the_drop_in(tmp_path):
+    """a checkpoint written by the reference (``torch.save(model.state_dict())``,
+    utils/model_utils.py:19-38, sparse ``A_in`` inside) loads into the drop-in class key for key, and what the drop-in
+    saves loads back into the reference.  Host-side only: no kernel runs."""
+    import literalkg_b200 as L
+    import make_golden as G
+    ref_model, _ = G.import_reference()
+    cfg = O.OracleConfig(n_conv_layers=2, embed_dim=20, relation_dim=20, scale_gat_dim=12, conv_dim=8, num_lit_dim=2,
+                         txt_lit_dim=6)
+    n, n_rel = 30, 3
+    h, t, r = G.make_kg(n, n_rel, 90, 7)
+    idx, val, _ = G.ref_laplacian(h, t, r, n, "random-walk")
+    a0 = torch.sparse_coo_tensor(torch.from_numpy(idx), torch.from_numpy(val), (n, n))
+    num, txt = torch.zeros(n, 2), torch.zeros(n, 6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_model.LiteralKG(G.namespace(cfg), n, n_rel, a0, num, txt)
+        path = tmp_path / "ckpt.pth"
+        torch.save(ref.state_dict(), path)
+        ours = L.LiteralKG(G.namespace(cfg), n, n_rel, None, num, txt)
+        missing, unexpected = ours.load_state_dict(torch.load(path), strict=True)
+        assert not missing and not unexpected
+        for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), ours.state_dict().items()):
+            assert k1 == k2 and v1.shape == v2.shape and v1.dtype == v2.dtype
+            if v1.is_sparse:
+                assert torch.equal(v1.coalesce().indices(), v2.coalesce().indices())
+                assert torch.equal(v1.coalesce().values(), v2.coalesce().values())
+            else:
+                assert torch.equal(v1, v2)
+        path2 = tmp_path / "ours.pth"
+        torch.save(ours.state_dict(), path2)
+        ref2 = ref_model.LiteralKG(G.namespace(cfg), n, n_rel, None, num, txt)
+        ref2.load_state_dict(torch.load(path2))
+        assert torch.equal(ref2.entity_embed.weight, ref.entity_embed.weight)
