@@ -351,6 +351,7 @@ class LiteralKG(nn.Module):
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
         self._part = None                                 # parallel.RowPartition when the path is row partitioned
         self._gate_prefetch = None                        # (key, gate stage) started by update_attention
+        self._peer_h0 = None                              # parallel.PeerGather of the h0 table (opt-in)
         self.sync_attention = "lazy"                      # partitioned update_att: every rank fills its own rows of A_in;
                                                           # True = all-reduce at once, "lazy" = on state_dict() /
                                                           # complete_attention(), False = never
@@ -512,6 +513,12 @@ class LiteralKG(nn.Module):
             qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
         return torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, zcol
 
+    @staticmethod
+    def _peer_gather_enabled(part) -> bool:
+        import os
+        return (os.environ.get("LKG_P2P_GATHER", "0") == "1" and part._backend() == "nccl"
+                and torch.cuda.device_count() >= part.world)
+
     def _gate_stage_key(self, part):
         gate_mod, tables = self._gate_module()
         ent = self.entity_embed.weight
@@ -529,10 +536,22 @@ class LiteralKG(nn.Module):
         rows = None if part is None else (rb, re)
         n_own, n_tab = re - rb, (n if part is None else part.padded)
         cat = torch.empty((n_own, total), dtype=torch.float32, device=dev)   # concat buffer, this rank's rows
+        gather_h0 = False
+        if part is not None and self.n_layers > 0:
+            c0 = self.aggregator_layers[0].out_dim
+            z_path = self.use_residual and d >= 128 and c0 % 4 == 0      # see _stack_q
+            gather_h0 = not z_path or self.aggregation_type == 'bi-interaction'
+        peer = None
         if part is None:
             h0_tab = h0 = cat[:, :d]                      # gate output lives in the concat buffer
         else:
-            h0_tab = torch.empty((n_tab, d), dtype=torch.float32, device=dev)   # row index == entity id
+            if gather_h0 and keep is None and self._peer_gather_enabled(part):
+                if self._peer_h0 is None or self._peer_h0.part is not part or self._peer_h0.d != d:
+                    from .parallel import PeerGather
+                    self._peer_h0 = PeerGather(part, d, dev)
+                h0_tab, peer = self._peer_h0.begin()      # persistent, peer-mapped table (copy-engine all-gather)
+            else:
+                h0_tab = torch.empty((n_tab, d), dtype=torch.float32, device=dev)   # row index == entity id
             h0 = h0_tab[rb:re]
         # scaled fp16 hi/lo planes of the concat buffer: A operand of the h0 @ Q and linear_gat tensor-core GEMMs.
         # Two K segments with their own scale records: the gate output and the L2-normalised layer outputs
@@ -545,11 +564,8 @@ class LiteralKG(nn.Module):
         _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows,
                                             packed=None if pre is None else pre["packed"], gz_out=gz)
         work = None
-        if part is not None and self.n_layers > 0:
-            c0 = self.aggregator_layers[0].out_dim
-            z_path = self.use_residual and d >= 128 and c0 % 4 == 0      # see _stack_q
-            if not z_path or self.aggregation_type == 'bi-interaction':
-                work = part.all_gather_rows(h0_tab, async_op=True)
+        if gather_h0:
+            work = peer.start() if peer is not None else part.all_gather_rows(h0_tab, async_op=True)
         return dict(cat=cat, h0_tab=h0_tab, h0=h0, cat_planes=cat_planes, h0_planes=h0_planes, xcol=xcol, gz=gz,
                     work=work)
 

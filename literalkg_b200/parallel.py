@@ -125,6 +125,72 @@ class RowPartition:
         return out.view(self.world, *t.shape).to(t.device)
 
 
+class PeerGather:
+    """All-gather of row blocks by peer-to-peer copies instead of NCCL (opt-in: ``LKG_P2P_GATHER=1``, NCCL backend,
+    one GPU per rank on one NVLink box).
+
+    Why: the layer-1 all-gather of ``h0`` (1.2 GB at N = 1 M) is the largest transfer of the pass and NCCL's kernel
+    competes for the SMs with the HBM-bound attention kernel it is supposed to hide under (measured overlap ~5 %,
+    ``scratch/nccl_probe.py``).  Device-to-device ``copy_`` between peer-mapped buffers goes through the copy engines:
+    no SM is involved, so the transfer really runs next to the kernels.
+
+    Every rank owns two ``[padded, d]`` buffers whose CUDA IPC handles are exchanged once; a gather PUSHES the rank's
+    own rows into the same slot of every peer on a side stream and closes with a one-element NCCL all-reduce issued
+    from that stream (a stream-ordered barrier: it completes when every rank's pushes are done).  Slots alternate per
+    call; slot s is rewritten two calls later, after the barrier of the call in between, which every rank only joins
+    once its main stream is past the kernels that read slot s -- the callers' ``wait()`` / kernel launches and the next
+    ``begin()`` are issued on that main stream in program order.
+
+    Status (round 1): results identical to the NCCL path (tests/test_parallel.py with LKG_P2P_GATHER=1 on two GPUs),
+    but torch's cross-device ``copy_`` into the IPC-mapped peer buffers moves only ~30 GB/s on the test box (2-GPU
+    pass 29.9 ms vs 10.1 ms with NCCL) -- it does not take the NVLink peer path.  Off by default; the transfer needs
+    its own copy kernel over the peer mapping (or explicit cudaMemcpyPeerAsync) before it can replace NCCL."""
+
+    def __init__(self, part: "RowPartition", d: int, device, dtype=torch.float32):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.part, self.d = part, int(d)
+        self.local = [torch.zeros((part.padded, d), dtype=dtype, device=device) for _ in range(2)]
+        mine = [reduce_tensor(b) for b in self.local]
+        everyone = [None] * part.world
+        dist.all_gather_object(everyone, mine, group=part.group)
+        self.peers = []                                 # peers[r][slot]: rank r's buffer mapped into this process
+        for r in range(part.world):
+            self.peers.append(self.local if r == part.rank else [fn(*args) for fn, args in everyone[r]])
+        self.stream = torch.cuda.Stream(device=device)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.calls = 0
+
+    def begin(self):
+        """-> (table, handle): ``table`` [padded, d] is this call's buffer -- write this rank's rows
+        ``[begin, end)`` into it on the current stream, then call ``handle.start()``; ``handle.wait()`` orders the
+        current stream after the arrival of every other rank's rows."""
+        slot = self.calls & 1
+        self.calls += 1
+        return self.local[slot], _PeerHandle(self, slot)
+
+
+class _PeerHandle:
+    def __init__(self, owner: PeerGather, slot: int):
+        self.owner, self.slot, self.done = owner, slot, None
+
+    def start(self):
+        o, part = self.owner, self.owner.part
+        main = torch.cuda.current_stream()
+        o.stream.wait_stream(main)                      # the rows are written, earlier readers of the slot are queued
+        with torch.cuda.stream(o.stream):
+            rows = o.local[self.slot][part.begin:part.end]
+            for r in range(part.world):
+                if r != part.rank:
+                    o.peers[r][self.slot][part.begin:part.end].copy_(rows, non_blocking=True)
+            dist.all_reduce(o.flag, group=part.group)   # stream-ordered barrier: every rank's pushes have landed
+            self.done = torch.cuda.Event()
+            self.done.record(o.stream)
+        return self
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.done)
+
+
 def merge_topk(vals: torch.Tensor, ids: torch.Tensor, k: int, topk_fn) -> Tuple[torch.Tensor, torch.Tensor]:
     """k-way merge of per-rank results.  ``vals`` / ``ids`` [world, B, k] (ids = global tail positions, -1 pads with
     value -inf).  Ranks own ascending, disjoint position ranges and each list is ordered (score desc, position asc),
