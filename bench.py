@@ -7,7 +7,12 @@ One "step" = one pass of the hot path over the whole synthetic graph of BASELINE
 (N = 1 M entities, E = 20 M triples, R = 64 relations, D = 300, C = 32, L = 3 bi-interaction layers,
 G = 256):  update_att (attention logits + duplicate merge + row softmax) followed by gat_embeddings
 (literal gate, 3 aggregator layers, concat + linear_gat).  metric = triples (edges) processed per second.
-Also reported: the all-entity link-prediction scoring of configs[3] (2 048 heads x 1 M tails, top-10).
+`value`: inputs resident in HBM.  `e2e`: the same pass through the public API with the edge list uploaded from pinned
+host memory for every step (double-buffered on a copy stream) and a slice of the result read back.
+Also reported in the same JSON line: `roofline` of the dominant kernel (CUDA events on its stream inside the timed
+region; ncu DRAM traffic from profiles/r01_traffic.json), `cpu_baseline` (the oracle port on the host cores, bounded
+sample), the all-entity link-prediction scoring of configs[3] (2 048 heads x 1 M tails, fused top-10) and one
+training step (fine-tuning loss, forward + backward to every parameter).  N > 1: head rows partitioned over the ranks.
 """
 from __future__ import annotations
 

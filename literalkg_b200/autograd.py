@@ -1,8 +1,10 @@
 """Glue between nn.Module parameters and the forward kernels.
 
 The forward of every stage runs in the hand-written kernels.  Gradient support is attached by
-``literalkg_b200.model`` at the level of the whole ``gat_embeddings`` pass (see ``GatEmbeddingsFn``);
-the standalone ``Gate`` / ``GateMul`` / ``Aggregator`` modules are forward (inference) modules.
+``literalkg_b200.model`` at the level of the whole ``gat_embeddings`` pass (``_GatEmbeddingsFn``: one autograd
+node whose backward is csrc/backward.cu + csrc/xty_tc.cu) and of the loss heads (``_BprLossFn``,
+``_TransRLossFn``: csrc/loss.cu); the standalone ``Gate`` / ``GateMul`` / ``Aggregator`` modules are forward
+(inference) modules.
 """
 from __future__ import annotations
 
