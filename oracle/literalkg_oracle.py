@@ -402,6 +402,90 @@ def triplet_loss(p, all_embed, cfg: OracleConfig, h, r, pos, neg):
 # parameter initialisation with the reference's shapes (model.py:215-261, gate.py) -- used by
 # bench.py / tests to create weights without importing the reference
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# minibatch generators (dataloader.py:192-333)
+# ----------------------------------------------------------------------------------------------
+def build_kg_dict(h, t, r) -> Dict[int, List[Tuple[int, int]]]:
+    """``train_kg_dict[h] -> [(t, r), ...]`` in file order (dataloader.py:395-403)."""
+    d: Dict[int, List[Tuple[int, int]]] = {}
+    for hh, tt, rr in zip(np.asarray(h).tolist(), np.asarray(t).tolist(), np.asarray(r).tolist()):
+        d.setdefault(hh, []).append((tt, rr))
+    return d
+
+
+def generate_kg_batch(kg_dict, batch_size: int, neg_rate: int, training_tails: Sequence[int], rng):
+    """``generate_kg_batch`` (dataloader.py:285-318) with ``sample_pos_triples_for_head`` (:254-271, one positive)
+    and ``sample_neg_triples_for_head`` (:273-283).  ``rng``: a ``random.Random``.  (Upstream passes ``dict.keys()``
+    to ``random.sample``, which Python >= 3.11 rejects; the list of keys is what it means.)"""
+    exist_heads = list(kg_dict.keys())
+    n = int(batch_size / neg_rate)
+    heads = rng.sample(exist_heads, n) if n <= len(exist_heads) else [rng.choice(exist_heads) for _ in range(n)]
+    out_h, out_r, out_p, out_n = [], [], [], []
+    for hd in heads:
+        pos = kg_dict[hd]
+        tail, rel = pos[rng.randrange(len(pos))]
+        negs: List[int] = []
+        while len(negs) < neg_rate:
+            cand = rng.choice(training_tails)
+            if (cand, rel) not in pos and cand not in negs:
+                negs.append(cand)
+        out_h += [hd] * neg_rate                      # generate_batch_by_neg_rate (:320-333)
+        out_r += [rel] * neg_rate
+        out_p += [tail] * neg_rate
+        out_n += negs
+    return (np.asarray(out_h, dtype=np.int64), np.asarray(out_r, dtype=np.int64), np.asarray(out_p, dtype=np.int64),
+            np.asarray(out_n, dtype=np.int64))
+
+
+def generate_prediction_batch(head_dict, batch_size: int, neg_rate: int, tail_ids: Sequence[int], rng):
+    """``generate_prediction_batch`` (dataloader.py:221-252): ``head_dict[h] -> [positive tails]``; negatives from
+    ``prediction_tail_ids`` that are no positive of the head and not drawn before."""
+    exist_heads = list(head_dict)
+    tail_ids = list(tail_ids)
+    n = int(batch_size / neg_rate)
+    heads = rng.sample(exist_heads, n) if n <= len(exist_heads) else [rng.choice(exist_heads) for _ in range(n)]
+    out_h, out_p, out_n = [], [], []
+    for hd in heads:
+        pos = head_dict[hd]
+        tail = pos[rng.randrange(len(pos))]
+        negs: List[int] = []
+        while len(negs) < neg_rate:
+            cand = rng.choice(tail_ids)
+            if cand not in pos and cand not in negs:
+                negs.append(cand)
+        out_h += [hd] * neg_rate
+        out_p += [tail] * neg_rate
+        out_n += negs
+    return (np.asarray(out_h, dtype=np.int64), np.asarray(out_p, dtype=np.int64), np.asarray(out_n, dtype=np.int64))
+
+
+def check_batch_contract(kg_dict, heads, rels, pos, neg, neg_rate: int, candidates, distinct_heads: bool) -> None:
+    """Asserts what the generators above guarantee for a batch (any random stream): heads / relations / positives
+    repeated ``neg_rate`` times, every (h, r, t+) a triple of the graph, negatives from the candidate list, distinct
+    per head and never a positive of the head under the drawn relation (``rels is None``: under any relation)."""
+    heads, pos, neg = (np.asarray(x).reshape(-1, neg_rate) for x in (heads, pos, neg))
+    assert (heads == heads[:, :1]).all() and (pos == pos[:, :1]).all()
+    rr = None
+    if rels is not None:
+        rr = np.asarray(rels).reshape(-1, neg_rate)
+        assert (rr == rr[:, :1]).all()
+    if distinct_heads:
+        assert len(set(heads[:, 0].tolist())) == heads.shape[0]
+    cand = set(int(c) for c in candidates)
+    for i in range(heads.shape[0]):
+        hd = int(heads[i, 0])
+        triples = kg_dict[hd]
+        negs = [int(x) for x in neg[i]]
+        assert len(set(negs)) == neg_rate and all(x in cand for x in negs)
+        if rr is not None:
+            rel = int(rr[i, 0])
+            assert (int(pos[i, 0]), rel) in triples
+            assert all((x, rel) not in triples for x in negs)
+        else:
+            tails = {tt for tt, _ in triples}
+            assert int(pos[i, 0]) in tails and all(x not in tails for x in negs)
+
+
 def init_params(cfg: OracleConfig, n_entities: int, n_relations: int, seed: int = 2022,
                 dtype=torch.float32) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)

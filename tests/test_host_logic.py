@@ -159,3 +159,26 @@ def test_stacked_q_layout():
     assert torch.equal(wq[0:8], (folds[0]["q1"] + folds[0]["pa"]).t()) and torch.equal(wq[8:16], folds[0]["q2"].t())
     assert torch.equal(wq[16:24], folds[1]["q1"].t()) and torch.equal(wq[32:40], folds[0]["pb"].t())
     assert torch.equal(cq[:8], folds[0]["c1"]) and (cq[32:] == 0).all()
+
+
+def test_batch_generator_oracle_and_contract_checker():
+    """The oracle restatement of the reference's batch generators satisfies the contract the device sampler is tested
+    against (tests/test_sampler_gpu.py), and the checker rejects batches that break it."""
+    import random
+    import numpy as np
+    rng = np.random.default_rng(0)
+    h, t, r = rng.integers(0, 60, 900), rng.integers(0, 200, 900), rng.integers(0, 4, 900)
+    kg = O.build_kg_dict(h, t, r)
+    tails = np.unique(t).tolist()
+    bh, br, bp, bn = O.generate_kg_batch(kg, 90, 3, tails, random.Random(1))
+    assert bh.shape == (90,) and len(set(bh.tolist())) == 30
+    O.check_batch_contract(kg, bh, br, bp, bn, 3, tails, distinct_heads=True)
+    bad = bn.copy()
+    bad[0] = bp[0]                                            # a positive of the head as its negative
+    with pytest.raises(AssertionError):
+        O.check_batch_contract(kg, bh, br, bp, bad, 3, tails, distinct_heads=True)
+    big = O.generate_kg_batch(kg, 600, 3, tails, random.Random(2))          # 200 heads > 60 existing: with replacement
+    O.check_batch_contract(kg, *big, 3, tails, distinct_heads=False)
+    head_dict = {k: sorted({tt for tt, _ in v}) for k, v in kg.items()}
+    ph, pp, pn = O.generate_prediction_batch(head_dict, 60, 3, tails, random.Random(3))
+    O.check_batch_contract(kg, ph, None, pp, pn, 3, tails, distinct_heads=True)

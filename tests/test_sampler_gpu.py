@@ -35,6 +35,8 @@ def test_kg_batch_contract():
         assert len(set(negs)) == 3 and all(x in candset for x in negs)              # distinct, from the candidates
         assert all((int(heads[i, 0]), int(r[3 * i]), int(x)) not in triples for x in negs)
     assert int(s.n_failed.item()) == 0
+    import literalkg_oracle as O                              # the same checker the oracle's generators pass on CPU
+    O.check_batch_contract(O.build_kg_dict(kg.h, kg.t, kg.r), h, r, p, ng, 3, cand, distinct_heads=True)
     # reproducible for a seed, different across calls
     s2 = L.BatchSampler(plan, cand, neg_rate=3, use_relation=True, seed=11)
     again = s2.sample(2048)
