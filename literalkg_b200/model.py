@@ -853,12 +853,25 @@ class LiteralKG(nn.Module):
     def calculate_prediction_loss(self, head_ids, tail_pos_ids, tail_neg_ids):
         """model.py:316-348 (BPR on the final embeddings)."""
         self.gat_embed = self.gat_embeddings()
-        return _BprLossFn.apply(self.gat_embed, head_ids, tail_pos_ids, tail_neg_ids, float(self.prediction_l2loss_lambda))
+        return self.prediction_loss_from(self.gat_embed, head_ids, tail_pos_ids, tail_neg_ids)
 
     def calc_triplet_loss(self, h, r, pos_t, neg_t):
         """model.py:364-428 (TransR on the GAT embeddings)."""
         self.gat_embed = self.gat_embeddings()
-        return _TransRLossFn.apply(self.gat_embed, self.relation_embed.weight, self.gat_trans_M, h, r, pos_t, neg_t,
+        return self.triplet_loss_from(self.gat_embed, h, r, pos_t, neg_t)
+
+    # The reference recomputes (and differentiates) the whole graph for every minibatch (main.py:112-124, 213-226).
+    # The two helpers below take the embedding matrix as an argument, so ONE ``gat_embeddings()`` -- one forward and,
+    # after summing the losses, one backward pass over the graph -- can serve several minibatches: gradient
+    # accumulation over those batches at fixed parameters (SURVEY.md 8(f) rank 2; an explicit choice of the caller,
+    # not the reference's one-update-per-batch schedule).
+    def prediction_loss_from(self, all_embed, head_ids, tail_pos_ids, tail_neg_ids):
+        """BPR loss (model.py:316-348) of one minibatch on a given embedding matrix."""
+        return _BprLossFn.apply(all_embed, head_ids, tail_pos_ids, tail_neg_ids, float(self.prediction_l2loss_lambda))
+
+    def triplet_loss_from(self, all_embed, h, r, pos_t, neg_t):
+        """TransR loss (model.py:364-428) of one minibatch on a given embedding matrix."""
+        return _TransRLossFn.apply(all_embed, self.relation_embed.weight, self.gat_trans_M, h, r, pos_t, neg_t,
                                    float(self.kg_l2loss_lambda))
 
     # ---- attention update ------------------------------------------------------------------------

@@ -354,6 +354,39 @@ def test_oracle_gradients(agg, res, layers, ent_scale, tol, monkeypatch):
     assert not bad, (bad, n_flips)
 
 
+def test_one_graph_pass_serves_several_minibatches():
+    """prediction_loss_from / triplet_loss_from on ONE gat_embeddings(): the gradients of the summed losses equal the
+    sum of the gradients of separate full passes (gradient accumulation at fixed parameters)."""
+    import literalkg_b200 as L
+    n, n_rel = 1500, 4
+    cfg = O.OracleConfig(n_conv_layers=2, mess_dropout=0.0)
+    kg = L.synthetic.make_kg(n, 12000, n_rel, seed=8, max_out_degree=100)
+    num, txt = L.synthetic.make_literals(n, seed=8)
+    p = O.init_params(cfg, n, n_rel, seed=8)
+    kt = L.KGTensors(kg.h, kg.t, kg.r, n_entities=n, device="cuda")
+    args = argparse.Namespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    m = L.LiteralKG(args, n, n_rel, kt.A_in, num, txt)
+    m.load_state_dict(p, strict=False)
+    m = m.cuda().train()
+    gen = torch.Generator().manual_seed(1)
+    batches = [tuple(torch.randint(0, n, (128,), generator=gen).cuda() for _ in range(3)) for _ in range(3)]
+    rels = [torch.randint(0, n_rel, (128,), generator=gen).cuda() for _ in range(3)]
+    want = None
+    for (h, ps, ng), r in zip(batches, rels):                 # the reference's schedule: one full pass per minibatch
+        m.zero_grad(set_to_none=True)
+        (m(h, ps, ng, device="cuda", mode="fine_tuning") + m(h, r, ps, ng, device="cuda", mode="pre_training")).backward()
+        g = {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+        want = g if want is None else {k: want[k] + g[k] for k in g}
+    m.zero_grad(set_to_none=True)
+    emb = m.gat_embeddings()                                  # one forward ...
+    total = sum(m.prediction_loss_from(emb, h, ps, ng) + m.triplet_loss_from(emb, h, r, ps, ng)
+                for (h, ps, ng), r in zip(batches, rels))
+    total.backward()                                          # ... one backward over the graph
+    for k, v in m.named_parameters():
+        if k in want:
+            assert rel_err(v.grad, want[k]) < 1e-4, k
+
+
 def test_training_step_reduces_loss():
     """A few optimizer steps through the public API (main.py:112-124): the loss must go down."""
     import literalkg_b200 as L
