@@ -183,6 +183,10 @@ int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t 
                    const float* bias /*nullable [n]*/, int32_t activation, float* out, int64_t ldo,
                    uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
                    void* stream);
+/* Tuning / test knob of the GEMM engine (host call, process wide): 0 = automatic (a CTA pair issuing
+ * tcgen05.mma.cta_group::2 over 256-row tiles whenever there is a tile for every SM pair, else one CTA per 128-row
+ * tile), 1 / 2 = force the CTA-group size.  Results are bit-identical either way (same products, same order). */
+int lkg_gemm_set_cta_group(int32_t cta_group);
 /* Literal gate (gate.py:22-28 / :45-51).  x = (entity | literals...) planes; w_pair = packed planes of
  * the [2*dim, K] matrix with row 2j = g.weight[j,:] and row 2j+1 = the stacked gate_* weights of output
  * j; bias_pair [2*dim] likewise (g.bias[j], gate_bias[j]); x_ent = fp32 entity table for the mix

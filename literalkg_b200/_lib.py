@@ -51,6 +51,7 @@ SIGNATURES = {
     "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, vp, i64, i64, vp]),
     "lkg_packed_weight_cols": (C.c_int, [C.POINTER(i32), i32, C.POINTER(i32)]),
     "lkg_pack_weight": (C.c_int, [vp, i64, i32, C.POINTER(i32), i32, C.POINTER(vp), vp, i64, vp, vp]),
+    "lkg_gemm_set_cta_group": (C.c_int, [i32]),
     "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64,
                                  i64, vp, vp]),
     "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), vp, i32, vp, i64, vp, i64, vp, i64,

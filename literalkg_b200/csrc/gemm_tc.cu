@@ -18,6 +18,8 @@
 //     tile i+1; 4 epilogue warps read them back with tcgen05.ld (32 lanes x 16 columns per instruction);
 //   * persistent CTAs (one per SM), static tile round-robin, N fastest so that co-running CTAs share A tiles in L2;
 //   * the virtual torch.cat of the reference is a list of K segments, each with its own tensor map.
+#include <cstdlib>
+
 #include "tc.cuh"
 
 namespace lkg {
@@ -29,12 +31,13 @@ constexpr int kStages = 4;        // upper bound; a launch uses as many as fit n
 constexpr int kEpiGroups = 3;     // epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range
 constexpr int kThreads = 64 + 128 * kEpiGroups;   // warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer,
                                                   // warps 6.. epilogue groups 1..
-constexpr int kEpiThreads = 128 * kEpiGroups;
+constexpr int kEpiWarps = 4 * kEpiGroups;
 constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
 constexpr uint32_t kSmemBudget = 227 * 1024;
-__host__ __device__ constexpr uint32_t stage_bytes_for(int bn) { return kABytes + 2u * (uint32_t)bn * kBK * 2u; }
-inline int stages_for(int bn) {
-    const int s = (int)((kSmemBudget - 1024 - 256) / stage_bytes_for(bn));
+// bn_cta = rows of the B tile one CTA stages (the whole N tile, or half of it in a CTA pair)
+__host__ __device__ constexpr uint32_t stage_bytes_for(int bn_cta) { return kABytes + 2u * (uint32_t)bn_cta * kBK * 2u; }
+inline int stages_for(int bn_cta) {
+    const int s = (int)((kSmemBudget - 1024 - 256) / stage_bytes_for(bn_cta));
     return s > kStages ? kStages : s;
 }
 
@@ -215,21 +218,30 @@ __device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int c
     }
 }
 
-template <int EPI>
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) per 256-row tile -- the leader issues
+// tcgen05.mma.cta_group::2 (M = 256), every CTA stages its own 128 rows of A and HALF of the B tile, so the bytes a CTA
+// pulls from L2 per tile drop from A + B to A + B/2 (the gate GEMM: 850 KB -> 586 KB; L2 -> SM fill was the bound with
+// cta_group::1: 42 B/cycle/SM x 158 tiles) and a third pipeline stage fits.
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t kStageBytes = p.stage_bytes;
     const int n_stages = p.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
-    uint64_t* full = bars;                 // [kStages]  TMA bytes landed
-    uint64_t* empty = bars + kStages;      // [kStages]  MMAs that read the stage retired
+    uint64_t* full = bars;                 // [kStages]  TMA bytes landed (CG = 2: the leader's counts both CTAs' bytes)
+    uint64_t* empty = bars + kStages;      // [kStages]  MMAs that read the stage retired (CG = 2: multicast commit)
     uint64_t* acc_full = bars + 2 * kStages;       // [2]  accumulator complete
-    uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2]  accumulator drained by the epilogue
+    uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2]  accumulator drained by the epilogue warps (of both CTAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile-scheduling unit: CTA or CTA pair
+    const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int total_tiles = p.tiles_m * p.tiles_n;
+    const int bn_cta = p.bn / CG;          // rows of the B tile this CTA stages
     int n_chunks = 0;
     for (int s = 0; s < p.n_segments; ++s) n_chunks += p.seg_chunks[s];
 
@@ -243,20 +255,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], kEpiThreads);
+            mbar_init(&acc_empty[a], kEpiWarps * CG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t b_bytes = 2u * (uint32_t)p.bn * kBK * 2u;
+    const uint32_t b_bytes = 2u * (uint32_t)bn_cta * kBK * 2u;
 
     auto tile_coords = [&](int tile, int& mb, int& nb) {
         if (p.m_fastest) {
@@ -269,19 +288,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     };
 
     if (warp == 4) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one per CTA) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < total_tiles; tile += n_units) {
                 int mb, nb;
                 tile_coords(tile, mb, nb);
+                const int a_row = (mb * CG + (int)cta_rank) * kBM;
+                const int b_row = nb * p.bn + (int)cta_rank * bn_cta;
                 for (int s = 0; s < p.n_segments; ++s) {
                     for (int j = 0; j < p.seg_chunks[s]; ++j) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* st = smem + stage * kStageBytes;
-                        mbar_expect_tx(&full[stage], kABytes + b_bytes);
-                        tma_load_3d(&p.a_map[s], &full[stage], st, j * kBK, mb * kBM, 0);
-                        tma_load_3d(&p.b_map, &full[stage], st + kABytes, p.seg_bcol[s] + j * kBK, nb * p.bn, 0);
+                        if (CG == 2) {
+                            // both CTAs' bytes are counted on the leader's barrier: the MMA issuer lives there
+                            if (leader) mbar_expect_tx(&full[stage], 2u * (kABytes + b_bytes));
+                            const uint32_t bar = mapa_u32(&full[stage], 0);
+                            tma_load_3d_cg2(&p.a_map[s], bar, st, j * kBK, a_row, 0);
+                            tma_load_3d_cg2(&p.b_map, bar, st + kABytes, p.seg_bcol[s] + j * kBK, b_row, 0);
+                        } else {
+                            mbar_expect_tx(&full[stage], kABytes + b_bytes);
+                            tma_load_3d(&p.a_map[s], &full[stage], st, j * kBK, a_row, 0);
+                            tma_load_3d(&p.b_map, &full[stage], st + kABytes, p.seg_bcol[s] + j * kBK, b_row, 0);
+                        }
                         if (++stage == (uint32_t)n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -291,12 +320,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(p.bn);
+        // ===== MMA issuer (CG = 2: the leader CTA issues for the pair) =====
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc(p.bn, kBM * CG);
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -308,33 +337,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
                     const uint32_t a_lo = a_hi + kBM * kBK * 2;
                     const uint32_t b_hi = a_hi + kABytes;
-                    const uint32_t b_lo = b_hi + (uint32_t)p.bn * kBK * 2;
+                    const uint32_t b_lo = b_hi + (uint32_t)bn_cta * kBK * 2;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         const uint32_t koff = k * 32;   // 16 fp16 = 32 bytes inside the swizzle row
                         const uint64_t dah = umma_desc(a_hi + koff), dal = umma_desc(a_lo + koff);
                         const uint64_t dbh = umma_desc(b_hi + koff), dbl = umma_desc(b_lo + koff);
-                        tc_mma_f16(tmem_d, dah, dbh, idesc, (c | k) != 0);
-                        tc_mma_f16(tmem_d, dal, dbh, idesc, 1);
-                        tc_mma_f16(tmem_d, dah, dbl, idesc, 1);
+                        if (CG == 2) {
+                            tc_mma_f16_cg2(tmem_d, dah, dbh, idesc, (c | k) != 0);
+                            tc_mma_f16_cg2(tmem_d, dal, dbh, idesc, 1);
+                            tc_mma_f16_cg2(tmem_d, dah, dbl, idesc, 1);
+                        } else {
+                            tc_mma_f16(tmem_d, dah, dbh, idesc, (c | k) != 0);
+                            tc_mma_f16(tmem_d, dal, dbh, idesc, 1);
+                            tc_mma_f16(tmem_d, dah, dbl, idesc, 1);
+                        }
                     }
-                    tc_commit(&empty[stage]);          // frees the smem stage when these MMAs retire
+                    // frees the smem stage (in both CTAs) when these MMAs retire
+                    if (CG == 2) tc_commit_cg2(&empty[stage], 3); else tc_commit(&empty[stage]);
                     if (++stage == (uint32_t)n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&acc_full[acc]);             // accumulator ready for the epilogue
+                // accumulator ready for the epilogue warps (of both CTAs)
+                if (CG == 2) tc_commit_cg2(&acc_full[acc], 3); else tc_commit(&acc_full[acc]);
             }
         }
     } else {
-        // ===== epilogue warps 0-3: TMEM lane = tile row =====
+        // ===== epilogue warps: TMEM lane = tile row of this CTA =====
         int it = 0;
         float lo = INFINITY, hi = -INFINITY;
         // powers of two: the rescale is exact
         const float acc_scale = (p.mul_a ? __ldg(p.mul_a + 2) : 1.f) * (p.mul_b ? __ldg(p.mul_b + 2) : 1.f);
         const float out_scale = (p.out_planes && p.out_rec) ? __ldg(p.out_rec + 1) : 1.f;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc_empty_leader0 = CG == 2 ? mapa_u32(&acc_empty[0], 0) : 0u;   // the leader's barriers
+        const uint32_t acc_empty_leader1 = CG == 2 ? mapa_u32(&acc_empty[1], 0) : 0u;
+        for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
             int mb, nb;
             tile_coords(tile, mb, nb);
             const int acc = it & 1;
@@ -348,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const int group = warp < 4 ? 0 : 1 + (warp - 6) / 4;
             const int c_per = ((p.bn / 16 + kEpiGroups - 1) / kEpiGroups) * 16;
             const int c_begin = min(group * c_per, p.bn), c_end = min(c_begin + c_per, p.bn);
-            const int64_t row = (int64_t)mb * kBM + quarter * 32 + lane;
+            const int64_t row = ((int64_t)mb * CG + cta_rank) * kBM + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
             uint32_t raw[16];
             if (c_begin < c_end) tc_ld16_nowait(taddr + c_begin, raw);
@@ -361,7 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 epilogue16<EPI>(p, row, nb * p.bn + c0, v, out_scale, lo, hi);
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            __syncwarp();
+            if (lane == 0) {               // one arrival per epilogue warp, on the barrier the MMA issuer waits on
+                if (CG == 2) mbar_arrive_cluster(acc ? acc_empty_leader1 : acc_empty_leader0); else mbar_arrive(&acc_empty[acc]);
+            }
         }
         if (EPI == kEpiScore && p.minmax) {
 #pragma unroll
@@ -378,9 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still signal / read it
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -402,18 +448,65 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int k, int64_t ld
     return LKG_OK;
 }
 
-int pick_bn(int n, bool deep) {
-    // smallest number of N tiles, then the smallest tile (multiple of 16) that covers n.  `deep`: take one or two
-    // more tiles when that lets a third pipeline stage fit -- with two stages a k-chunk waits for a whole L2 round
-    // trip of its 80 KB before the next one may start (ncu r01: tile time 2 x the MMA time)
-    int tiles = (n + kMaxBN - 1) / kMaxBN;
-    auto bn_of = [&](int t) {
-        const int b = ((n + t - 1) / t + 15) / 16 * 16;
-        return b < 16 ? 16 : b;
-    };
-    if (deep)
-        for (int extra = 0; extra < 2 && stages_for(bn_of(tiles)) < 3; ++extra) ++tiles;
-    return bn_of(tiles);
+int pick_bn(int n) {
+    // smallest number of N tiles, then the smallest tile (multiple of 16) that covers n.  (Measured in round 1: taking
+    // more, narrower N tiles to fit a third cta_group::1 stage re-reads A and gains nothing: gate 2.69 -> 2.83 ms.)
+    const int tiles = (n + kMaxBN - 1) / kMaxBN;
+    const int b = ((n + tiles - 1) / tiles + 15) / 16 * 16;
+    return b < 16 ? 16 : b;
+}
+
+// lkg_gemm_set_cta_group / LKG_GEMM_CG=1|2 force the CTA-group size (A/B measurements, tests); default: pairs whenever
+// every SM pair gets a tile
+int g_forced_cg = -1;
+inline int forced_cg() {
+    if (g_forced_cg < 0) {
+        const char* e = getenv("LKG_GEMM_CG");
+        g_forced_cg = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }
+    return g_forced_cg;
+}
+
+template <int EPI, int CG>
+int launch_tc_cg(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, int n, cudaStream_t stream) {
+    const int bn_cta = p.bn / CG;
+    p.stages = stages_for(bn_cta);
+    p.stage_bytes = stage_bytes_for(bn_cta);
+    LKG_REQUIRE(p.stages >= 2, "GEMM tile does not fit shared memory");
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    p.tiles_m = (int)((m + kBM * CG - 1) / (kBM * CG));
+    p.tiles_n = (n + p.bn - 1) / p.bn;
+    int bcol = 0;
+    for (int s = 0; s < a->n_segments; ++s) {
+        LKG_REQUIRE(a->ptr[s] && a->k[s] > 0, "bad A segment %d", s);
+        p.seg_chunks[s] = (a->k[s] + kBK - 1) / kBK;
+        p.seg_bcol[s] = bcol;
+        bcol += p.seg_chunks[s] * kBK;
+        if (int rc = make_map(&p.a_map[s], a->ptr[s], m, a->k[s], a->ld[s], a->plane_stride[s], kBM)) return rc;
+    }
+    LKG_REQUIRE(b->k[0] == bcol || (a->n_segments == 1 && b->k[0] == a->k[0]),
+                "B has %d columns, the A segments need %d", b->k[0], bcol);
+    if (int rc = make_map(&p.b_map, b->ptr[0], n, b->k[0], b->ld[0], b->plane_stride[0], bn_cta)) return rc;
+    auto kern = tc_gemm_kernel<EPI, CG>;
+    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int units = sm_count() / CG;                       // persistent: one CTA (or CTA pair) per SM (pair)
+    const int grid = CG * (tiles < units ? tiles : units);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    LKG_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    LKG_LAUNCH_CHECK("tc_gemm_kernel");
+    return LKG_OK;
 }
 
 template <int EPI>
@@ -429,31 +522,12 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
     }
     p.m = m;
     p.n = n;
-    p.bn = pick_bn(n, false);   // measured: extra N tiles for a third stage re-read A and gain nothing (gate 2.69 -> 2.83 ms)
-    p.stages = stages_for(p.bn);
-    p.stage_bytes = stage_bytes_for(p.bn);
-    LKG_REQUIRE(p.stages >= 2, "GEMM tile does not fit shared memory");
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    p.tiles_m = (int)((m + kBM - 1) / kBM);
-    p.tiles_n = (n + p.bn - 1) / p.bn;
-    int bcol = 0;
-    for (int s = 0; s < a->n_segments; ++s) {
-        LKG_REQUIRE(a->ptr[s] && a->k[s] > 0, "bad A segment %d", s);
-        p.seg_chunks[s] = (a->k[s] + kBK - 1) / kBK;
-        p.seg_bcol[s] = bcol;
-        bcol += p.seg_chunks[s] * kBK;
-        if (int rc = make_map(&p.a_map[s], a->ptr[s], m, a->k[s], a->ld[s], a->plane_stride[s], kBM)) return rc;
-    }
-    LKG_REQUIRE(b->k[0] == bcol || (a->n_segments == 1 && b->k[0] == a->k[0]),
-                "B has %d columns, the A segments need %d", b->k[0], bcol);
-    if (int rc = make_map(&p.b_map, b->ptr[0], n, b->k[0], b->ld[0], b->plane_stride[0], p.bn)) return rc;
-    auto kern = tc_gemm_kernel<EPI>;
-    LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kThreads, smem_bytes, stream>>>(p);
-    LKG_LAUNCH_CHECK("tc_gemm_kernel");
-    return LKG_OK;
+    p.bn = pick_bn(n);
+    // a CTA pair halves the B bytes every CTA stages; worth it once there are enough 256-row tiles for every SM pair
+    const int64_t pair_tiles = ((m + 2 * kBM - 1) / (2 * kBM)) * ((n + p.bn - 1) / p.bn);
+    int cg = (p.bn % 16 == 0 && pair_tiles >= sm_count() / 2) ? 2 : 1;
+    if (forced_cg() == 1 || (forced_cg() == 2 && p.bn % 16 == 0)) cg = forced_cg();
+    return cg == 2 ? launch_tc_cg<EPI, 2>(p, a, m, b, n, stream) : launch_tc_cg<EPI, 1>(p, a, m, b, n, stream);
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------
@@ -724,6 +798,12 @@ extern "C" int lkg_pack_weight(const float* w, int64_t ldw, int32_t n, const int
     LKG_LAUNCH_CHECK("pack_weight_kernel");
     pack_finalize_kernel<<<1, 1, 0, stream>>>(segs, w_rec);
     LKG_LAUNCH_CHECK("pack_finalize_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_gemm_set_cta_group(int32_t cta_group) {
+    LKG_REQUIRE(cta_group >= 0 && cta_group <= 2, "cta_group must be 0 (automatic), 1 or 2");
+    g_forced_cg = cta_group;
     return LKG_OK;
 }
 

@@ -99,14 +99,60 @@ __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2): two CTAs of one cluster issue ONE M = 256 MMA; the leader (cluster rank 0) issues, each
+// CTA stages its own 128 rows of A and its half of the B tile, accumulators land in both CTAs' TMEM ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the transaction bytes are counted on the barrier at `bar_cluster_addr` (the leader's), the data lands in this CTA
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // K-major, 128-byte swizzle shared memory matrix descriptor (start >> 4, SBO = 8 rows * 128 B, version 1)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0 in bits 7-9 / 10-12; the two formats
 // must agree -- a bf16 x fp16 mix traps as an illegal instruction), both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t umma_idesc(int bn) {
-    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int bn, int m = kBM) {
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 

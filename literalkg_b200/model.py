@@ -347,6 +347,7 @@ class LiteralKG(nn.Module):
         self._att_ident = None
         self._att_refs = None
         self._lit_planes = None                           # fp16 hi/lo planes of the (constant) literal tables
+        self._ent_planes = None                           # (key, planes) of entity_embed.weight, per parameter version
         self._unit_rec = None                             # scale record of planes bounded by 1 (normalised rows)
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
         self._part = None                                 # parallel.RowPartition when the path is row partitioned
@@ -445,7 +446,12 @@ class LiteralKG(nn.Module):
             ent_rows = ent.detach()[sl]
             gate_mod, tables = self._gate_module()
             if gate_mod is not None:
-                ent_planes = ops.split_planes(ent_rows)
+                # operand preparation of a parameter: the fp16 hi/lo planes of the entity table are kept while the
+                # table is unchanged (in-place version counter), like the planes of the constant literal tables
+                pkey = (ent.data_ptr(), ent._version, rows)
+                if self._ent_planes is None or self._ent_planes[0] != pkey:
+                    self._ent_planes = (pkey, ops.split_planes(ent_rows))
+                ent_planes = self._ent_planes[1]
                 out_planes = None
                 if planes_window is not None:
                     # |gate output| <= max(1, max|entity|): convex mix of the entity row and a tanh

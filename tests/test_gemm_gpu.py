@@ -111,3 +111,65 @@ def test_exact_integers():
     w = torch.randint(-8, 9, (256, 128), generator=g, device="cuda").float()
     out = ops.linear([ops.split_planes(x)], w, None, 0)
     assert torch.equal(out, x @ w.t())
+
+
+# ---- CTA pairs (tcgen05.mma.cta_group::2 over 256-row tiles) -------------------------------------------------------
+@pytest.fixture
+def cta_group():
+    """Forces the CTA-group size of the GEMM engine for one test and restores the automatic choice afterwards."""
+    from literalkg_b200 import _lib
+
+    def set_(cg):
+        _lib.check(_lib.load().lkg_gemm_set_cta_group(cg))
+    yield set_
+    set_(0)
+
+
+@pytest.mark.parametrize("m,n,ks", [(256, 64, [64]), (129, 16, [12]), (1000, 600, [300, 302]), (38000, 600, [300, 302]),
+                                    (20001, 224, [300]), (19999, 256, [300, 96]), (513, 208, [64, 64, 64, 64])])
+def test_cta_pair_matches_single_cta(m, n, ks, cta_group):
+    """Same products in the same order: a CTA pair must reproduce the single-CTA result bit for bit, ragged last
+    tiles (rows of the second CTA entirely out of range) and every K-segment layout included."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    segs = [torch.randn(m, k, generator=g, device="cuda") for k in ks]
+    w = torch.randn(n, sum(ks), generator=g, device="cuda") / sum(ks) ** 0.5
+    b = torch.randn(n, generator=g, device="cuda")
+    planes = [ops.split_planes(s) for s in segs]
+    outs = []
+    for cg in (1, 2):
+        cta_group(cg)
+        outs.append(ops.linear(planes, w, b, 1))
+    ref = torch.nn.functional.leaky_relu(torch.cat(segs, 1).double() @ w.double().t() + b.double(), 0.01)
+    assert rel(outs[1], ref) < TOL
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_cta_pair_gate_and_score(cta_group):
+    import literalkg_b200 as L
+    from literalkg_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    m, dim, lits = 30001, 300, [2, 300]
+    mod = L.GateMul(dim, *lits).cuda()
+    xs = [torch.randn(m, dim, generator=g).cuda()] + [torch.randn(m, k, generator=g).cuda() for k in lits]
+    res = []
+    for cg in (1, 2):
+        cta_group(cg)
+        res.append(mod(*xs))
+    d = lambda t: t.double()
+    x = torch.cat([d(t) for t in xs], 1)
+    gg = torch.tanh(x @ d(mod.g.weight).t() + d(mod.g.bias))
+    z = torch.sigmoid(d(xs[0]) @ d(mod.gate_ent.weight).t() + d(xs[1]) @ d(mod.gate_num_lit.weight).t()
+                      + d(xs[2]) @ d(mod.gate_txt_lit.weight).t() + d(mod.gate_bias))
+    assert rel(res[1], (1 - z) * d(xs[0]) + z * gg) < TOL
+    assert torch.equal(res[0], res[1])
+    emb = torch.randn(50000, 256, generator=g).cuda()
+    heads = torch.arange(0, 700, device="cuda") * 3
+    tails = torch.arange(0, 45003, device="cuda")
+    sc = []
+    for cg in (1, 2):
+        cta_group(cg)
+        mm = torch.empty(2, dtype=torch.int32, device="cuda")
+        sc.append((ops.score(emb, heads, tails, mm), mm.clone()))
+    assert rel(sc[1][0], emb[heads].double() @ emb[tails].double().t()) < TOL
+    assert torch.equal(sc[0][0], sc[1][0]) and torch.equal(sc[0][1], sc[1][1])
