@@ -28,16 +28,23 @@ namespace {
 using namespace tc;
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
 constexpr int kStages = 4;        // upper bound; a launch uses as many as fit next to its B tile (TcParams::stages)
-constexpr int kEpiGroups = 3;     // epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range
+constexpr int kEpiGroups = 2;     // epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range
 constexpr int kThreads = 64 + 128 * kEpiGroups;   // warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer,
                                                   // warps 6.. epilogue groups 1..
 constexpr int kEpiWarps = 4 * kEpiGroups;
 constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
 constexpr uint32_t kSmemBudget = 227 * 1024;
+// Epilogue staging: a warp owns 32 TMEM lanes (= tile rows), one thread per row.  Storing a thread's row straight to
+// global memory makes every 16-byte store of the warp hit 32 different lines (32 LSU wavefronts per instruction; ncu
+// r02a: the epilogue, not the MMAs or the L2 -> SM fill, set the tile time of every GEMM of the pass).  Each warp
+// therefore transposes 32 rows x 32 accumulator columns through shared memory (pitch 33 floats: conflict free both
+// ways) and touches global memory with 8 (gate: 4) lanes per row -- whole 128-byte (64-byte) row segments.
+constexpr int kStagePitch = 33;
+constexpr uint32_t kEpiStageBytes = kEpiGroups * 4 * 32 * kStagePitch * 4;
 // bn_cta = rows of the B tile one CTA stages (the whole N tile, or half of it in a CTA pair)
 __host__ __device__ constexpr uint32_t stage_bytes_for(int bn_cta) { return kABytes + 2u * (uint32_t)bn_cta * kBK * 2u; }
 inline int stages_for(int bn_cta) {
-    const int s = (int)((kSmemBudget - 1024 - 256) / stage_bytes_for(bn_cta));
+    const int s = (int)((kSmemBudget - 1024 - 256 - kEpiStageBytes) / stage_bytes_for(bn_cta));
     return s > kStages ? kStages : s;
 }
 
@@ -84,136 +91,159 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     lo = __float2half_rn(x - __half2float(hi));
 }
 
-// ---- epilogues: one thread = one output row, 16 consecutive accumulator columns per call -----------
+// ---- epilogue of one 32-row x 32-column accumulator block, staged in shared memory as st[row * kStagePitch + col] ----
+__device__ __forceinline__ float4 ld4_guard(const float* ptr, int valid, bool vec) {
+    if (vec && valid >= 4) return __ldg(reinterpret_cast<const float4*>(ptr));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid > 0) v.x = __ldg(ptr);
+    if (valid > 1) v.y = __ldg(ptr + 1);
+    if (valid > 2) v.z = __ldg(ptr + 2);
+    if (valid > 3) v.w = __ldg(ptr + 3);
+    return v;
+}
+__device__ __forceinline__ void st4_guard(float* ptr, const float4& v, int valid, bool vec) {
+    if (vec && valid >= 4) {
+        *reinterpret_cast<float4*>(ptr) = v;
+        return;
+    }
+    if (valid > 0) ptr[0] = v.x;
+    if (valid > 1) ptr[1] = v.y;
+    if (valid > 2) ptr[2] = v.z;
+    if (valid > 3) ptr[3] = v.w;
+}
+// hi/lo planes of four consecutive values (already multiplied by the plane scale)
+__device__ __forceinline__ void st_planes4(__half* hrow, int64_t plane_stride, const float4& v, int valid, bool vec) {
+    __align__(8) __half h[4], l[4];
+    split_f16(v.x, h[0], l[0]);
+    split_f16(v.y, h[1], l[1]);
+    split_f16(v.z, h[2], l[2]);
+    split_f16(v.w, h[3], l[3]);
+    __half* lrow = hrow + plane_stride;
+    if (vec && valid >= 4) {
+        *reinterpret_cast<uint2*>(hrow) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lrow) = *reinterpret_cast<const uint2*>(l);
+        return;
+    }
+    for (int j = 0; j < 4; ++j)
+        if (j < valid) {
+            hrow[j] = h[j];
+            lrow[j] = l[j];
+        }
+}
+
+// Alignment facts of a launch that let the epilogue use 16-byte (planes: 8-byte) accesses; computed once per thread.
+struct EpiAlign {
+    bool out4, ent4, gz4, planes4, bias4;
+};
+__device__ __forceinline__ EpiAlign epi_align(const TcParams& p) {
+    EpiAlign a;
+    a.out4 = ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && (p.ldo % 4 == 0);
+    a.ent4 = p.x_ent && ((reinterpret_cast<uintptr_t>(p.x_ent) & 15u) == 0) && (p.ld_ent % 4 == 0);
+    a.gz4 = p.gz_out && ((reinterpret_cast<uintptr_t>(p.gz_out) & 15u) == 0) && (p.ld_gz % 4 == 0);
+    a.planes4 = p.out_planes && ((reinterpret_cast<uintptr_t>(p.out_planes) & 7u) == 0) && (p.ld_planes % 4 == 0) &&
+                (p.plane_stride % 4 == 0);
+    a.bias4 = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0);
+    return a;
+}
+
+// linear / score: 8 lanes per row (4 columns each), 4 rows per pass, 8 passes.  `old` = prefetched previous values of
+// the output (accumulate mode).  col0 = first GEMM column of the block (multiple of 16).
 template <int EPI>
-__device__ __forceinline__ void epilogue16(const TcParams& p, int64_t row, int col0, const float (&acc)[16],
-                                           float out_scale, float& lo, float& hi) {
-    if (row >= p.m) return;
-    if (EPI == kEpiGate) {
-        // columns come in (g, z) pairs; 16 accumulator columns -> 8 output channels
-        const int c0 = col0 >> 1;
-        const int dim = p.n >> 1;
-        if (c0 >= dim) return;
-        const float* erow = p.x_ent + row * p.ld_ent + c0;
-        float* orow = p.out + row * p.ldo + c0;
-        const bool full = c0 + 8 <= dim;
-        float e[8], b[16], o[8];
-        if (full && ((reinterpret_cast<uintptr_t>(erow) & 15u) == 0)) {
-            const float4 e0 = __ldg(reinterpret_cast<const float4*>(erow));
-            const float4 e1 = __ldg(reinterpret_cast<const float4*>(erow) + 1);
-            e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
-        } else {
+__device__ __forceinline__ void epilogue_block(const TcParams& p, const EpiAlign& al, const float* st, int64_t row0,
+                                               int col0, int col_end, int lane, float out_scale, float& lo, float& hi) {
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const int col = col0 + 4 * c4;
+    const int valid = col_end - col;             // columns of this lane inside the tile and the matrix (<= 0: none)
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI == kEpiLinear && p.bias && valid > 0) b = ld4_guard(p.bias + col, valid, al.bias4);
+    float4 old[8];
+    if (EPI == kEpiLinear && p.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = c0 + j < dim ? __ldg(erow + j) : 0.f;
+        for (int it = 0; it < 8; ++it) {
+            const int64_t row = row0 + it * 4 + rsub;
+            old[it] = (row < p.m && valid > 0) ? ld4_guard(p.out + row * p.ldo + col, valid, al.out4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (full) {
+    }
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));   // warp-uniform address
-                b[j] = bb.x; b[j + 1] = bb.y; b[j + 2] = bb.z; b[j + 3] = bb.w;
+    for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + rsub;
+        const int64_t row = row0 + rl;
+        const float* sp = st + rl * kStagePitch + 4 * c4;
+        float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        if (row >= p.m || valid <= 0) continue;
+        if (EPI == kEpiLinear) {
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            if (p.act == LKG_ACT_LEAKY_RELU) {
+                v.x = leaky(v.x); v.y = leaky(v.y); v.z = leaky(v.z); v.w = leaky(v.w);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) b[j] = col0 + j < p.n ? __ldg(p.bias + col0 + j) : 0.f;
-        }
-        float gz[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float g = tanh_acc(acc[2 * j] + b[2 * j]);
-            const float z = sigmoid_acc(acc[2 * j + 1] + b[2 * j + 1]);
-            gz[2 * j] = g;
-            gz[2 * j + 1] = z;
-            o[j] = (1.f - z) * e[j] + z * g;
-        }
-        if (p.gz_out) {
-            float* grow = p.gz_out + row * p.ld_gz + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(grow) & 15u) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(grow + j) = make_float4(gz[j], gz[j + 1], gz[j + 2], gz[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (col0 + j < p.n) grow[j] = gz[j];
+            if (p.accumulate) {
+                v.x += old[it].x; v.y += old[it].y; v.z += old[it].z; v.w += old[it].w;
             }
         }
-        if (full && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
-            reinterpret_cast<float4*>(orow)[0] = make_float4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<float4*>(orow)[1] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
+        if (EPI == kEpiScore) {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c0 + j < dim) orow[j] = o[j];
+            for (int j = 0; j < 4; ++j)
+                if (j < valid) {
+                    lo = fminf(lo, vv[j]);
+                    hi = fmaxf(hi, vv[j]);
+                }
         }
-        if (p.out_planes) {
-            __half* hrow = p.out_planes + row * p.ld_planes + c0;
-            __half* lrow = hrow + p.plane_stride;
-            __align__(16) __half h[8], l[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split_f16(o[j] * out_scale, h[j], l[j]);
-            if (full && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
-                *reinterpret_cast<uint4*>(hrow) = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(lrow) = *reinterpret_cast<const uint4*>(l);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < dim) {
-                        hrow[j] = h[j];
-                        lrow[j] = l[j];
-                    }
-            }
-        }
-    } else {
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int c = col0 + j;
-            float v = acc[j];
-            if (EPI == kEpiLinear) {
-                if (p.bias && c < p.n) v += __ldg(p.bias + c);      // warp-uniform address: one broadcast load
-                if (p.act == LKG_ACT_LEAKY_RELU) v = leaky(v);
-            }
-            o[j] = v;
-            if (EPI == kEpiScore && c < p.n) {
-                lo = fminf(lo, v);
-                hi = fmaxf(hi, v);
-            }
-        }
-        float* dst = p.out + row * p.ldo + col0;
-        if (EPI == kEpiLinear && p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.n) o[j] += dst[j];
-        }
-        if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.n) dst[j] = o[j];
-        }
+        st4_guard(p.out + row * p.ldo + col, v, valid, al.out4);
         if (EPI == kEpiLinear && p.out_planes) {
-            __half* hrow = p.out_planes + row * p.ld_planes + col0;
-            __half* lrow = hrow + p.plane_stride;
-            __align__(16) __half h[16], l[16];
+            const float4 sv = make_float4(v.x * out_scale, v.y * out_scale, v.z * out_scale, v.w * out_scale);
+            st_planes4(p.out_planes + row * p.ld_planes + col, p.plane_stride, sv, valid, al.planes4);
+        }
+    }
+}
+
+// gate: the 32 accumulator columns are 16 (g, z) pairs = 16 output channels; 4 lanes per row (4 channels each),
+// 8 rows per pass, 4 passes.  `e` = the lane's x_ent values, loaded by the caller before the accumulator wait.
+__device__ __forceinline__ void gate_prefetch(const TcParams& p, const EpiAlign& al, int64_t row0, int col0, int col_end,
+                                              int lane, float4 (&e)[4]) {
+    const int ch = (col0 >> 1) + 4 * (lane & 3);
+    const int valid = (col_end >> 1) - ch;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_f16(o[j] * out_scale, h[j], l[j]);
-            if (col0 + 16 <= p.n && ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) &&
-                ((reinterpret_cast<uintptr_t>(lrow) & 15u) == 0)) {
-                reinterpret_cast<uint4*>(hrow)[0] = reinterpret_cast<const uint4*>(h)[0];
-                reinterpret_cast<uint4*>(hrow)[1] = reinterpret_cast<const uint4*>(h)[1];
-                reinterpret_cast<uint4*>(lrow)[0] = reinterpret_cast<const uint4*>(l)[0];
-                reinterpret_cast<uint4*>(lrow)[1] = reinterpret_cast<const uint4*>(l)[1];
-            } else {
+    for (int it = 0; it < 4; ++it) {
+        const int64_t row = row0 + it * 8 + (lane >> 2);
+        e[it] = (row < p.m && valid > 0) ? ld4_guard(p.x_ent + row * p.ld_ent + ch, valid, al.ent4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al, const float* st, int64_t row0,
+                                           int col0, int col_end, int lane, float out_scale, const float4 (&e)[4]) {
+    const int q = lane & 3, rsub = lane >> 2;
+    const int ch = (col0 >> 1) + 4 * q;          // first output channel of this lane
+    const int valid = (col_end >> 1) - ch;       // channels inside the tile and the matrix
+    if (valid <= 0) return;
+    const float4 b0 = ld4_guard(p.bias + col0 + 8 * q, 2 * valid, al.bias4);          // (g, z) bias pairs
+    const float4 b1 = ld4_guard(p.bias + col0 + 8 * q + 4, 2 * valid - 4, al.bias4);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (col0 + j < p.n) {
-                        hrow[j] = h[j];
-                        lrow[j] = l[j];
-                    }
-            }
+    for (int it = 0; it < 4; ++it) {
+        const int rl = it * 8 + rsub;
+        const int64_t row = row0 + rl;
+        const float* sp = st + rl * kStagePitch + 8 * q;
+        const float a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7];
+        if (row >= p.m) continue;
+        float4 g, z, o;
+        g.x = tanh_acc(a0 + b0.x); z.x = sigmoid_acc(a1 + b0.y);
+        g.y = tanh_acc(a2 + b0.z); z.y = sigmoid_acc(a3 + b0.w);
+        g.z = tanh_acc(a4 + b1.x); z.z = sigmoid_acc(a5 + b1.y);
+        g.w = tanh_acc(a6 + b1.z); z.w = sigmoid_acc(a7 + b1.w);
+        o.x = (1.f - z.x) * e[it].x + z.x * g.x;
+        o.y = (1.f - z.y) * e[it].y + z.y * g.y;
+        o.z = (1.f - z.z) * e[it].z + z.z * g.z;
+        o.w = (1.f - z.w) * e[it].w + z.w * g.w;
+        if (p.gz_out) {
+            float* grow = p.gz_out + row * p.ld_gz + col0 + 8 * q;
+            st4_guard(grow, make_float4(g.x, z.x, g.y, z.y), 2 * valid, al.gz4);
+            st4_guard(grow + 4, make_float4(g.z, z.z, g.w, z.w), 2 * valid - 4, al.gz4);
+        }
+        st4_guard(p.out + row * p.ldo + ch, o, valid, al.out4);
+        if (p.out_planes) {
+            const float4 sv = make_float4(o.x * out_scale, o.y * out_scale, o.z * out_scale, o.w * out_scale);
+            st_planes4(p.out_planes + row * p.ld_planes + ch, p.plane_stride, sv, valid, al.planes4);
         }
     }
 }
@@ -228,7 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t kStageBytes = p.stage_bytes;
     const int n_stages = p.stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
+    float* epi_stage = reinterpret_cast<float*>(smem + n_stages * kStageBytes);      // [kEpiWarps][32][kStagePitch]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes + kEpiStageBytes);
     uint64_t* full = bars;                 // [kStages]  TMA bytes landed (CG = 2: the leader's counts both CTAs' bytes)
     uint64_t* empty = bars + kStages;      // [kStages]  MMAs that read the stage retired (CG = 2: multicast commit)
     uint64_t* acc_full = bars + 2 * kStages;       // [2]  accumulator complete
@@ -373,36 +404,60 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const float out_scale = (p.out_planes && p.out_rec) ? __ldg(p.out_rec + 1) : 1.f;
         const uint32_t acc_empty_leader0 = CG == 2 ? mapa_u32(&acc_empty[0], 0) : 0u;   // the leader's barriers
         const uint32_t acc_empty_leader1 = CG == 2 ? mapa_u32(&acc_empty[1], 0) : 0u;
+        const EpiAlign al = epi_align(p);
+        // a warp reads the TMEM lanes of its quarter (warp % 4); every group of four warps takes its own range of the
+        // tile's columns, 32 at a time
+        const int quarter = warp & 3;
+        const int group = warp < 4 ? 0 : 1 + (warp - 6) / 4;
+        float* st = epi_stage + (group * 4 + quarter) * 32 * kStagePitch;
+        const int c_per = ((p.bn + 32 * kEpiGroups - 1) / (32 * kEpiGroups)) * 32;
+        const int c_begin = min(group * c_per, p.bn), c_end = min(c_begin + c_per, p.bn);
         for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
             int mb, nb;
             tile_coords(tile, mb, nb);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const int64_t row0 = ((int64_t)mb * CG + cta_rank) * kBM + quarter * 32;
+            float4 e[4];
+            const int col_end = min(p.n, (nb + 1) * p.bn);     // accumulator columns past it belong to no output
+            if (EPI == kEpiGate && c_begin < c_end) gate_prefetch(p, al, row0, nb * p.bn + c_begin, col_end, lane, e);
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            // a warp reads the TMEM lanes of its quarter (warp % 4); every group of four
-            // warps takes its own range of the tile's columns: the epilogue (global loads / stores per 16 columns) was longer than the
-            // MMAs of a tile with four warps
-            const int quarter = warp & 3;
-            const int group = warp < 4 ? 0 : 1 + (warp - 6) / 4;
-            const int c_per = ((p.bn / 16 + kEpiGroups - 1) / kEpiGroups) * 16;
-            const int c_begin = min(group * c_per, p.bn), c_end = min(c_begin + c_per, p.bn);
-            const int64_t row = ((int64_t)mb * CG + cta_rank) * kBM + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
-            uint32_t raw[16];
-            if (c_begin < c_end) tc_ld16_nowait(taddr + c_begin, raw);
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                float v[16];
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t raw[32];
+                // the accumulator buffers are kMaxBN columns apart: a 32-column read that starts inside the tile
+                // stays inside the allocation; columns past the tile are masked by the block epilogues
+                tc_ld32_nowait(taddr + c0, raw);
                 tc_ld_wait();
+                const bool last = c0 + 32 >= c_end;
+                if (last) {                // every TMEM read of this tile is done: hand the accumulator back now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {       // one arrival per epilogue warp, on the barrier the MMA issuer waits on
+                        if (CG == 2) mbar_arrive_cluster(acc ? acc_empty_leader1 : acc_empty_leader0);
+                        else mbar_arrive(&acc_empty[acc]);
+                    }
+                }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * acc_scale;
-                if (c0 + 16 < c_end) tc_ld16_nowait(taddr + c0 + 16, raw);   // next columns travel during this step
-                epilogue16<EPI>(p, row, nb * p.bn + c0, v, out_scale, lo, hi);
+                for (int j = 0; j < 32; ++j) st[lane * kStagePitch + j] = __uint_as_float(raw[j]) * acc_scale;
+                __syncwarp();
+                const int col0 = nb * p.bn + c0;
+                if (EPI == kEpiGate) {
+                    gate_block(p, al, st, row0, col0, col_end, lane, out_scale, e);
+                    if (!last) gate_prefetch(p, al, row0, col0 + 32, col_end, lane, e);
+                } else {
+                    epilogue_block<EPI>(p, al, st, row0, col0, col_end, lane, out_scale, lo, hi);
+                }
+                __syncwarp();
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {               // one arrival per epilogue warp, on the barrier the MMA issuer waits on
-                if (CG == 2) mbar_arrive_cluster(acc ? acc_empty_leader1 : acc_empty_leader0); else mbar_arrive(&acc_empty[acc]);
+            if (c_begin >= c_end) {        // a group without columns in this launch still owes its arrival
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(acc ? acc_empty_leader1 : acc_empty_leader0);
+                    else mbar_arrive(&acc_empty[acc]);
+                }
             }
         }
         if (EPI == kEpiScore && p.minmax) {
@@ -473,7 +528,7 @@ int launch_tc_cg(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* 
     p.stages = stages_for(bn_cta);
     p.stage_bytes = stage_bytes_for(bn_cta);
     LKG_REQUIRE(p.stages >= 2, "GEMM tile does not fit shared memory");
-    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     p.tiles_m = (int)((m + kBM * CG - 1) / (kBM * CG));
     p.tiles_n = (n + p.bn - 1) / p.bn;
     int bcol = 0;

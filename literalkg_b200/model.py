@@ -357,6 +357,7 @@ class LiteralKG(nn.Module):
                                                           # True = all-reduce at once, "lazy" = on state_dict() /
                                                           # complete_attention(), False = never
         self._a_in_pending = None
+        self._local_edges = False                         # set_partition(local_edges=True)
         self.cache_embeddings = True                      # eval mode: keep gat_embeddings() until an input changes
         self._embed_cache = None
         self._a_in_epoch = 0
@@ -411,11 +412,14 @@ class LiteralKG(nn.Module):
             self._lit_key = key
         return self._lit_planes
 
-    def set_partition(self, part) -> None:
-        """Row-partition the path over the ranks of ``part`` (``parallel.RowPartition``); None = single GPU."""
-        if part is None:
-            self.complete_attention()
+    def set_partition(self, part, local_edges: bool = False) -> None:
+        """Row-partition the path over the ranks of ``part`` (``parallel.RowPartition``); None = single GPU.
+        ``local_edges``: ``update_att`` will be given only the triples whose HEAD this rank owns (a pre-partitioned
+        edge list: E / P triples to upload, sort and keep per rank instead of E); every kernel of the path only ever
+        reads the rows of its own heads, so nothing else changes.  Not a collective: pending attention values of a
+        previous partition must have been completed with ``complete_attention()`` (state_dict() checks)."""
         self._part = part
+        self._local_edges = bool(local_edges) and part is not None and part.world > 1
         self._lit_key = None
 
     def _unit_record(self, dev) -> torch.Tensor:
@@ -911,24 +915,54 @@ class LiteralKG(nn.Module):
                 ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach(), out=values)
                 plan.set_row_range(0, self.n_entities)
                 self._a_in_pending = None
-                if self.sync_attention is True:   # complete A_in on every rank; the layers only need own rows
+                if self._local_edges:             # A_in of this rank = its own head rows only
+                    self._a_in_pending = ("local", plan, values)
+                elif self.sync_attention is True:   # complete A_in on every rank; the layers only need own rows
                     part.all_reduce(values)
                 elif self.sync_attention == "lazy":
-                    self._a_in_pending = values
+                    self._a_in_pending = ("rows", plan, values)
+                elif part.world > 1:
+                    self._a_in_pending = ("never", plan, values)
         self._agg_plan, self._agg_values = plan, values
         self._a_in_epoch += 1
         self.A_in.data = plan.sparse(values)
 
     def complete_attention(self) -> None:
         """Row partitioned: after ``update_att`` every rank holds the attention values of its own head rows (all the
-        embedding pass reads).  This sums the other ranks' rows in (x + 0 is exact) so that ``A_in`` is the full matrix
-        of the reference on every rank -- needed for checkpoints, not for the pass; collective, call it on all ranks."""
-        if self._a_in_pending is not None and self._part is not None:
-            self._part.all_reduce(self._a_in_pending)
+        embedding pass reads).  This completes ``A_in`` to the full matrix of the reference on every rank -- needed
+        for checkpoints, not for the pass.  COLLECTIVE: call it on all ranks (``state_dict()`` refuses to run while it
+        is pending instead of hiding a collective inside a call that is usually made by rank 0 alone).
+        Replicated edge list: the other ranks' values are summed in (x + 0 is exact).  ``local_edges``: the per-rank
+        COO blocks (disjoint, ascending head ranges) are all-gathered and concatenated in rank order, which is the
+        coalesced order of the full matrix."""
+        pend, part = self._a_in_pending, self._part
+        if pend is None or part is None or part.world == 1:
+            self._a_in_pending = None
+            return
+        kind, plan, values = pend
+        if kind == "local":
+            dev = values.device
+            counts = part.all_gather_stack(torch.tensor([plan.nnz], dtype=torch.int64, device=dev)).view(-1).tolist()
+            width = max(max(counts), 1)
+            pad_i = torch.zeros((2, width), dtype=torch.int64, device=dev)
+            pad_v = torch.zeros(width, dtype=torch.float32, device=dev)
+            pad_i[:, :plan.nnz] = plan.indices
+            pad_v[:plan.nnz] = values
+            all_i, all_v = part.all_gather_stack(pad_i), part.all_gather_stack(pad_v)
+            idx = torch.cat([all_i[r][:, :c] for r, c in enumerate(counts)], dim=1)
+            val = torch.cat([all_v[r][:c] for r, c in enumerate(counts)])
+            self.A_in.data = torch.sparse_coo_tensor(idx, val, (self.n_entities, self.n_entities), is_coalesced=True)
+            self._agg_plan = self._agg_values = None          # rebuilt from the full matrix when next needed
+            self._a_in_epoch += 1
+        else:
+            part.all_reduce(values)
         self._a_in_pending = None
 
     def state_dict(self, *args, **kwargs):
-        self.complete_attention()
+        if self._a_in_pending is not None and self._part is not None and self._part.world > 1:
+            raise RuntimeError(
+                "A_in holds only this rank's head rows after a row-partitioned update_att: call "
+                "model.complete_attention() on ALL ranks (it is a collective) before state_dict() / torch.save")
         return super().state_dict(*args, **kwargs)
 
     # ---- scoring -----------------------------------------------------------------------------------
