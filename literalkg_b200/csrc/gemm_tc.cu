@@ -28,10 +28,11 @@ namespace {
 using namespace tc;
 constexpr int kMaxBN = 256;       // columns per tile (UMMA N)
 constexpr int kStages = 4;        // upper bound; a launch uses as many as fit next to its B tile (TcParams::stages)
-constexpr int kEpiGroups = 2;     // epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range
-constexpr int kThreads = 64 + 128 * kEpiGroups;   // warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer,
-                                                  // warps 6.. epilogue groups 1..
-constexpr int kEpiWarps = 4 * kEpiGroups;
+// Epilogue warp groups of 4 (one warp per TMEM lane quarter), each takes a column range of the tile.  Template
+// parameter G of the kernel: 2 for the linear / score epilogues (stores only), 3 for the gate (4 MUFU + ~20 other
+// instructions per output channel: with 8 warps the epilogue, not the MMAs, paced the tile -- ncu r02b).
+// Thread layout: warps 0-3 epilogue group 0, warp 4 TMA producer, warp 5 MMA issuer, warps 6.. epilogue groups 1..
+__host__ __device__ constexpr int threads_for(int groups) { return 64 + 128 * groups; }
 constexpr uint32_t kABytes = 2 * kBM * kBK * 2;            // hi + lo planes of one A chunk
 constexpr uint32_t kSmemBudget = 227 * 1024;
 // Epilogue staging: a warp owns 32 TMEM lanes (= tile rows), one thread per row.  Storing a thread's row straight to
@@ -40,11 +41,11 @@ constexpr uint32_t kSmemBudget = 227 * 1024;
 // therefore transposes 32 rows x 32 accumulator columns through shared memory (pitch 33 floats: conflict free both
 // ways) and touches global memory with 8 (gate: 4) lanes per row -- whole 128-byte (64-byte) row segments.
 constexpr int kStagePitch = 33;
-constexpr uint32_t kEpiStageBytes = kEpiGroups * 4 * 32 * kStagePitch * 4;
+__host__ __device__ constexpr uint32_t epi_stage_bytes(int groups) { return (uint32_t)groups * 4 * 32 * kStagePitch * 4; }
 // bn_cta = rows of the B tile one CTA stages (the whole N tile, or half of it in a CTA pair)
 __host__ __device__ constexpr uint32_t stage_bytes_for(int bn_cta) { return kABytes + 2u * (uint32_t)bn_cta * kBK * 2u; }
-inline int stages_for(int bn_cta) {
-    const int s = (int)((kSmemBudget - 1024 - 256 - kEpiStageBytes) / stage_bytes_for(bn_cta));
+inline int stages_for(int bn_cta, int groups) {
+    const int s = (int)((kSmemBudget - 1024 - 256 - epi_stage_bytes(groups)) / stage_bytes_for(bn_cta));
     return s > kStages ? kStages : s;
 }
 
@@ -227,14 +228,14 @@ __device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al
         const float a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7];
         if (row >= p.m) continue;
         float4 g, z, o;
-        g.x = tanh_acc(a0 + b0.x); z.x = sigmoid_acc(a1 + b0.y);
-        g.y = tanh_acc(a2 + b0.z); z.y = sigmoid_acc(a3 + b0.w);
-        g.z = tanh_acc(a4 + b1.x); z.z = sigmoid_acc(a5 + b1.y);
-        g.w = tanh_acc(a6 + b1.z); z.w = sigmoid_acc(a7 + b1.w);
-        o.x = (1.f - z.x) * e[it].x + z.x * g.x;
-        o.y = (1.f - z.y) * e[it].y + z.y * g.y;
-        o.z = (1.f - z.z) * e[it].z + z.z * g.z;
-        o.w = (1.f - z.w) * e[it].w + z.w * g.w;
+        g.x = tanh_fast(a0 + b0.x); z.x = sigmoid_fast(a1 + b0.y);
+        g.y = tanh_fast(a2 + b0.z); z.y = sigmoid_fast(a3 + b0.w);
+        g.z = tanh_fast(a4 + b1.x); z.z = sigmoid_fast(a5 + b1.y);
+        g.w = tanh_fast(a6 + b1.z); z.w = sigmoid_fast(a7 + b1.w);
+        o.x = fmaf(z.x, g.x - e[it].x, e[it].x);                 // (1 - z) e + z g
+        o.y = fmaf(z.y, g.y - e[it].y, e[it].y);
+        o.z = fmaf(z.z, g.z - e[it].z, e[it].z);
+        o.w = fmaf(z.w, g.w - e[it].w, e[it].w);
         if (p.gz_out) {
             float* grow = p.gz_out + row * p.ld_gz + col0 + 8 * q;
             st4_guard(grow, make_float4(g.x, z.x, g.y, z.y), 2 * valid, al.gz4);
@@ -252,8 +253,11 @@ __device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al
 // tcgen05.mma.cta_group::2 (M = 256), every CTA stages its own 128 rows of A and HALF of the B tile, so the bytes a CTA
 // pulls from L2 per tile drop from A + B to A + B/2 (the gate GEMM: 850 KB -> 586 KB; L2 -> SM fill was the bound with
 // cta_group::1: 42 B/cycle/SM x 158 tiles) and a third pipeline stage fits.
-template <int EPI, int CG>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+template <int EPI, int CG, int G>
+__global__ void __launch_bounds__(threads_for(G), 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+    constexpr int kEpiGroups = G;
+    constexpr int kEpiWarps = 4 * G;
+    constexpr uint32_t kEpiStageBytes = epi_stage_bytes(G);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t kStageBytes = p.stage_bytes;
@@ -444,8 +448,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 __syncwarp();
                 const int col0 = nb * p.bn + c0;
                 if (EPI == kEpiGate) {
+                    float4 e_next[4];      // the next block's x_ent rows travel while this block is computed
+                    if (!last) gate_prefetch(p, al, row0, col0 + 32, col_end, lane, e_next);
                     gate_block(p, al, st, row0, col0, col_end, lane, out_scale, e);
-                    if (!last) gate_prefetch(p, al, row0, col0 + 32, col_end, lane, e);
+                    if (!last) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) e[i] = e_next[i];
+                    }
                 } else {
                     epilogue_block<EPI>(p, al, st, row0, col0, col_end, lane, out_scale, lo, hi);
                 }
@@ -524,8 +533,11 @@ inline int forced_cg() {
 
 template <int EPI, int CG>
 int launch_tc_cg(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, int n, cudaStream_t stream) {
+    constexpr int G = EPI == kEpiGate ? 3 : 2;
+    constexpr uint32_t kEpiStageBytes = epi_stage_bytes(G);
+    constexpr int kThreads = threads_for(G);
     const int bn_cta = p.bn / CG;
-    p.stages = stages_for(bn_cta);
+    p.stages = stages_for(bn_cta, G);
     p.stage_bytes = stage_bytes_for(bn_cta);
     LKG_REQUIRE(p.stages >= 2, "GEMM tile does not fit shared memory");
     const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -542,7 +554,7 @@ int launch_tc_cg(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* 
     LKG_REQUIRE(b->k[0] == bcol || (a->n_segments == 1 && b->k[0] == a->k[0]),
                 "B has %d columns, the A segments need %d", b->k[0], bcol);
     if (int rc = make_map(&p.b_map, b->ptr[0], n, b->k[0], b->ld[0], b->plane_stride[0], bn_cta)) return rc;
-    auto kern = tc_gemm_kernel<EPI, CG>;
+    auto kern = tc_gemm_kernel<EPI, CG, G>;
     LKG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     const int tiles = p.tiles_m * p.tiles_n;
     const int units = sm_count() / CG;                       // persistent: one CTA (or CTA pair) per SM (pair)

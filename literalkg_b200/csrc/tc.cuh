@@ -117,7 +117,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope), the form CUTLASS uses for the 2-SM accumulator hand-back: a
+    // .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR in front of it and made every epilogue warp wait for
+    // its outstanding global stores (ncu r02b: 6 % of the gate kernel's samples)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // the transaction bytes are counted on the barrier at `bar_cluster_addr` (the leader's), the data lands in this CTA
 __device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,

@@ -352,7 +352,7 @@ class LiteralKG(nn.Module):
         self._h0q_cache = None                            # stacked h0 @ Q weight of all layers (parameter derived)
         self._part = None                                 # parallel.RowPartition when the path is row partitioned
         self._gate_prefetch = None                        # (key, gate stage) started by update_attention
-        self._peer_h0 = None                              # parallel.PeerGather of the h0 table (opt-in)
+        self._peer_x = None                               # parallel.PeerExchange: symmetric-memory exchange tables
         self.sync_attention = "lazy"                      # partitioned update_att: every rank fills its own rows of A_in;
                                                           # True = all-reduce at once, "lazy" = on state_dict() /
                                                           # complete_attention(), False = never
@@ -523,11 +523,29 @@ class LiteralKG(nn.Module):
             qs.append(folds[0]["pb"]); cs.append(torch.zeros_like(folds[0]["c1"])); off += folds[0]["pb"].shape[1]
         return torch.cat(qs, dim=1).t().contiguous(), torch.cat(cs), offsets, zcol
 
-    @staticmethod
-    def _peer_gather_enabled(part) -> bool:
-        import os
-        return (os.environ.get("LKG_P2P_GATHER", "0") == "1" and part._backend() == "nccl"
-                and torch.cuda.device_count() >= part.world)
+    def _exchange_table(self, part, name: str, d: int, training: bool):
+        """Symmetric-memory exchange table for the rows of one activation (``parallel.PeerTable``), or None: NCCL
+        all-gather (no NCCL box / symmetric memory unavailable / training pass, whose saved activations must outlive
+        the slot rotation)."""
+        if part is None or training or not part.peer_tables_enabled():
+            return None
+        if self._peer_x is None or self._peer_x.part is not part:
+            from .parallel import PeerExchange
+            self._peer_x = PeerExchange(part, self._param_device())
+        return self._peer_x.table(name, d)
+
+    def _gather_rows(self, part, name: str, src_rows: torch.Tensor, training: bool) -> torch.Tensor:
+        """Exchange of one row-partitioned activation: ``src_rows`` = this rank's rows [n_own, d] -> table [padded, d]
+        (row index == entity id) holding every rank's rows, usable on the current stream."""
+        tab = self._exchange_table(part, name, src_rows.shape[1], training)
+        if tab is not None:
+            table, handle = tab.begin()
+            table[part.begin:part.end] = src_rows
+            handle.start().wait()
+            return table
+        table = torch.empty((part.padded, src_rows.shape[1]), dtype=torch.float32, device=src_rows.device)
+        table[part.begin:part.end] = src_rows
+        return part.all_gather_rows(table)
 
     def _gate_stage_key(self, part):
         gate_mod, tables = self._gate_module()
@@ -555,11 +573,9 @@ class LiteralKG(nn.Module):
         if part is None:
             h0_tab = h0 = cat[:, :d]                      # gate output lives in the concat buffer
         else:
-            if gather_h0 and keep is None and self._peer_gather_enabled(part):
-                if self._peer_h0 is None or self._peer_h0.part is not part or self._peer_h0.d != d:
-                    from .parallel import PeerGather
-                    self._peer_h0 = PeerGather(part, d, dev)
-                h0_tab, peer = self._peer_h0.begin()      # persistent, peer-mapped table (copy-engine all-gather)
+            tab = self._exchange_table(part, "h0", d, keep is not None) if gather_h0 else None
+            if tab is not None:
+                h0_tab, peer = tab.begin()                # symmetric-memory table: rows pushed by the copy engines
             else:
                 h0_tab = torch.empty((n_tab, d), dtype=torch.float32, device=dev)   # row index == entity id
             h0 = h0_tab[rb:re]
@@ -625,9 +641,7 @@ class LiteralKG(nn.Module):
             if part is None:
                 z_tab = h0q[:, zoff:zoff + c0]                     # [N, C] view, row index == entity id
             else:
-                z_tab = torch.empty((n_tab, c0), dtype=torch.float32, device=dev)
-                z_tab[rb:re] = h0q[:, zoff:zoff + c0]
-                part.all_gather_rows(z_tab)
+                z_tab = self._gather_rows(part, "z", h0q[:, zoff:zoff + c0], keep is not None)
         if part is not None:
             if st["work"] is not None:
                 st["work"].wait()                         # layer 1 gathers arbitrary neighbour rows of h0
@@ -643,7 +657,12 @@ class LiteralKG(nn.Module):
                 r2 = h0q[:, offsets[k] + c:offsets[k] + 2 * c] if f["q2"] is not None else None
             else:
                 r1, r2 = f["c1"], f["c2"]
-            x_out = torch.empty((n_tab, c), dtype=torch.float32, device=dev)
+            exchange = part is not None and k + 1 < self.n_layers     # the next layer reads every row of this one
+            xtab = self._exchange_table(part, f"x{k}", c, keep is not None) if exchange else None
+            if xtab is not None:
+                x_out, xhandle = xtab.begin()             # the kernel writes this rank's rows straight into the table
+            else:
+                x_out = torch.empty((n_tab, c), dtype=torch.float32, device=dev)
             saved = None
             if keep is not None:
                 saved = {}
@@ -652,8 +671,11 @@ class LiteralKG(nn.Module):
             layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
                       xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows,
                       z=z_tab if k == 0 else None, saved=saved)
-            if part is not None and k + 1 < self.n_layers:
-                part.all_gather_rows(x_out)               # the next layer reads every row of this one
+            if exchange:
+                if xtab is not None:
+                    xhandle.start().wait()
+                else:
+                    part.all_gather_rows(x_out)
             x = x_out
             col += c
         plan.set_row_range(0, n)

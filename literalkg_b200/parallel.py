@@ -1,24 +1,33 @@
-"""Row partition of the path over the GPUs of one box: one process per GPU, NCCL over NVLink.
+"""Row partition of the path over the GPUs of one box: one process per GPU, NCCL / NVLink.
 
 The reference has no working multi-GPU code (a dead ``nn.DataParallel``, main.py:82-84); this is the B200
-analogue of the scaling axis it lacks.  Head rows are split into equal contiguous ranges; every rank keeps the
-full CSR plan (0.4 GB at 20 M triples) and the raw parameter tables, and owns its rows of every activation:
+analogue of the scaling axis it lacks.  Head rows are split into contiguous ranges -- equal row counts by default,
+nnz-balanced with ``RowPartition.balanced`` (real KGs group ids by entity type) -- and every rank owns its rows of
+every activation:
 
-    update_att       rows independent, no collective (optional all-reduce to complete the ``A_in`` values)
+    update_att       rows independent, no collective (``complete_attention`` gathers ``A_in`` for checkpoints)
     gate, h0 @ Q     row local
-    layer k          reads the whole ego table -> one all-gather of the (N/P x d_k) row blocks per layer, written in
-                     place into a [P * chunk, d_k] buffer whose row index is the global entity id
+    layer k          reads the whole ego table -> one exchange of the row blocks per layer, in place in a
+                     [rows, d_k] table whose row index is the global entity id
     linear_gat       row local; the final embeddings stay sharded -- each rank scores its own candidate tails
-    scoring / top-k  head rows are summed from their owners (all-reduce of a zero-padded [B, G] block), local fused
-                     top-k over the local tails, all-gather of the P x [B, k] survivors, k-way merge on every rank
+    scoring / top-k  head rows from their owners, local fused top-k over the local tails, all-gather of the
+                     P x [B, k] survivors, k-way merge on every rank
 
-The collectives go through ``torch.distributed`` (NCCL on the GPU box).  With the ``gloo`` backend (CPU tests, or two
-processes sharing one GPU in the test-suite) CUDA tensors are staged through host memory.
+Two transports for the per-layer exchange:
+  * ``PeerTable`` (default on NCCL boxes): the table lives in symmetric memory (CUDA VMM mappings of every rank's
+    copy, ``torch.distributed._symmetric_memory`` for allocation / rendezvous / barrier only); a rank PUSHES its row
+    block into every peer's copy with device-to-device copies on a side stream -- copy engines over NVLink, no SM is
+    involved, so the 1.2 GB ``h0`` exchange really runs next to the HBM-bound attention kernel (NCCL's all-gather
+    kernel competes with it for the SMs: ~5 % overlap measured in round 1);
+  * NCCL all-gather / reduce-scatter (training pass, and the fallback when symmetric memory is unavailable).
+Collectives go straight to ``torch.distributed``; host staging for CPU-only test backends lives in the tests.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import os
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -46,29 +55,83 @@ class _comm_profile:
 
 
 class RowPartition:
-    """Rank p owns head rows [p * chunk, min(N, (p + 1) * chunk)), chunk = ceil(N / world)."""
+    """Rank p owns head rows [bounds[p], bounds[p + 1]).  Default: equal chunks of ceil(N / world) rows (tables are
+    then padded to ``chunk * world`` rows so that one flat all-gather moves them); ``bounds``: any non-decreasing
+    list of world + 1 row indices from 0 to N (tables have exactly N rows, exchanges are per-rank views)."""
 
-    def __init__(self, n_entities: int, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+    def __init__(self, n_entities: int, rank: Optional[int] = None, world: Optional[int] = None, group=None,
+                 bounds: Optional[Sequence[int]] = None):
         self.group = group
         self.world = dist.get_world_size(group) if world is None else int(world)
         self.rank = dist.get_rank(group) if rank is None else int(rank)
         self.n = int(n_entities)
         self.chunk = (self.n + self.world - 1) // self.world
-        self.begin = min(self.n, self.rank * self.chunk)
-        self.end = min(self.n, self.begin + self.chunk)
-        self.padded = self.chunk * self.world          # rows of an all-gather buffer (row index == entity id)
+        if bounds is None:
+            self.uniform = True
+            self.bounds = [min(self.n, r * self.chunk) for r in range(self.world)] + [self.n]
+            self.padded = self.chunk * self.world          # rows of an exchange table (row index == entity id)
+        else:
+            b = [int(x) for x in bounds]
+            if len(b) != self.world + 1 or b[0] != 0 or b[-1] != self.n or any(y < x for x, y in zip(b, b[1:])):
+                raise ValueError("bounds must be world + 1 non-decreasing row indices from 0 to n_entities")
+            self.uniform = False
+            self.bounds = b
+            self.padded = self.n
+        self.begin, self.end = self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    @classmethod
+    def balanced(cls, n_entities: int, heads, rank: Optional[int] = None, world: Optional[int] = None, group=None,
+                 row_cost: float = 4.0) -> "RowPartition":
+        """Contiguous ranges of (nearly) equal cost, cost(row) = its triples + ``row_cost`` (the row-local work: gate,
+        GEMM rows, table rows; ~2.7 KB per row against ~1.2 KB per triple at the reference dims).  ``heads``: the
+        head column of the edge list (numpy / tensor, any order).  Deterministic: every rank computes the same cut."""
+        w = dist.get_world_size(group) if world is None else int(world)
+        h = heads.detach().cpu().numpy() if isinstance(heads, torch.Tensor) else np.asarray(heads)
+        cost = np.bincount(h.astype(np.int64), minlength=int(n_entities)).astype(np.float64) + float(row_cost)
+        cum = np.cumsum(cost)
+        cuts = np.searchsorted(cum, cum[-1] * np.arange(1, w) / w, side="left") + 1 if n_entities else np.zeros(w - 1)
+        bounds = [0] + [int(min(max(c, 0), n_entities)) for c in cuts] + [int(n_entities)]
+        for i in range(1, len(bounds)):
+            bounds[i] = max(bounds[i], bounds[i - 1])
+        return cls(n_entities, rank, w, group, bounds)
 
     @property
     def n_own(self) -> int:
         return self.end - self.begin
 
+    def rows_of(self, r: int) -> Tuple[int, int]:
+        return self.bounds[r], self.bounds[r + 1]
+
     def owner_of(self, rows: torch.Tensor) -> torch.Tensor:
-        return torch.div(rows, self.chunk, rounding_mode="floor")
+        b = torch.as_tensor(self.bounds[1:], device=rows.device, dtype=rows.dtype)
+        return torch.searchsorted(b, rows, right=True)
 
     def _backend(self) -> str:
         return dist.get_backend(self.group) if dist.is_initialized() else "none"
 
-    # ---- collectives -------------------------------------------------------------------------------------
+    def _views(self, buf: torch.Tensor) -> List[torch.Tensor]:
+        return [buf[b:e] for b, e in zip(self.bounds[:-1], self.bounds[1:])]
+
+    # ---- collectives (overridden by the CPU-staging subclass of the tests) ---------------------------------------
+    def _all_gather_flat(self, out: torch.Tensor, own: torch.Tensor, async_op: bool):
+        return dist.all_gather_into_tensor(out, own, group=self.group, async_op=async_op)
+
+    def _all_gather_list(self, outs: List[torch.Tensor], own: torch.Tensor, async_op: bool):
+        """Uneven row blocks: one broadcast per owner into its (in place) view.  The works complete in issue order on
+        the backend's stream, so waiting for the last one waits for all of them."""
+        last = None
+        for r, o in enumerate(outs):
+            if o.numel():
+                src = r if self.group is None else dist.get_global_rank(self.group, r)
+                last = dist.broadcast(o, src=src, group=self.group, async_op=async_op)
+        return last if async_op else None
+
+    def _reduce_scatter_flat(self, out: torch.Tensor, full: torch.Tensor):
+        dist.reduce_scatter_tensor(out, full, group=self.group)
+
+    def _all_reduce(self, t: torch.Tensor, op):
+        dist.all_reduce(t, op=op, group=self.group)
+
     def all_gather_rows(self, buf: torch.Tensor, async_op: bool = False):
         """``buf`` [padded, d] contiguous with this rank's rows already written: fetches every other rank's
         row block in place.  ``async_op``: returns a handle whose ``wait()`` orders the current stream after the
@@ -77,40 +140,34 @@ class RowPartition:
         assert buf.is_contiguous() and buf.shape[0] == self.padded
         if self.world == 1:
             return None if async_op else buf
-        own = buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
         with _comm_profile(buf, "all_gather", buf.numel() * buf.element_size(), async_op):
-            if buf.is_cuda and self._backend() != "nccl":      # gloo has no CUDA all-gather: stage through the host
-                full = torch.empty(buf.numel(), dtype=buf.dtype)
-                dist.all_gather_into_tensor(full, own.cpu().reshape(-1), group=self.group)
-                buf.copy_(full.view(buf.shape))
-                return None if async_op else buf
-            work = dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=self.group, async_op=async_op)
+            if self.uniform:
+                own = buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+                work = self._all_gather_flat(buf.view(-1), own.reshape(-1), async_op)
+            else:
+                work = self._all_gather_list(self._views(buf), buf[self.begin:self.end], async_op)
         return work if async_op else buf
 
     def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
-        """``full`` [padded, d]: every rank's partial sums for ALL rows -> [chunk, d], the sum over the ranks of this
-        rank's row block (the dual of ``all_gather_rows``; used by the backward of ``A_in @ x``)."""
+        """``full`` [padded, d]: every rank's partial sums for ALL rows -> the sum over the ranks of this rank's row
+        block ([chunk, d] for equal chunks, [n_own, d] otherwise); the dual of ``all_gather_rows``, used by the
+        backward of ``A_in @ x``."""
         assert full.is_contiguous() and full.shape[0] == self.padded
         if self.world == 1:
             return full
         with _comm_profile(full, "reduce_scatter", full.numel() * full.element_size(), False):
-            if self._backend() == "nccl" and full.is_cuda:
+            if self.uniform:
                 out = torch.empty((self.chunk, full.shape[1]), dtype=full.dtype, device=full.device)
-                dist.reduce_scatter_tensor(out.view(-1), full.view(-1), group=self.group)
+                self._reduce_scatter_flat(out.view(-1), full.view(-1))
                 return out
-            self.all_reduce(full)                              # gloo: no reduce-scatter for these tensors
-            return full[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+            self._all_reduce(full, dist.ReduceOp.SUM)          # uneven blocks: sum everywhere, keep the own rows
+            return full[self.begin:self.end]
 
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.world == 1:
             return t
         with _comm_profile(t, "all_reduce", t.numel() * t.element_size(), False):
-            if t.is_cuda and self._backend() != "nccl":
-                c = t.cpu()
-                dist.all_reduce(c, op=op, group=self.group)
-                t.copy_(c)
-            else:
-                dist.all_reduce(t, op=op, group=self.group)
+            self._all_reduce(t, op)
         return t
 
     def all_gather_stack(self, t: torch.Tensor) -> torch.Tensor:
@@ -118,59 +175,43 @@ class RowPartition:
         if self.world == 1:
             return t.unsqueeze(0)
         t = t.contiguous()
-        staged = t.is_cuda and self._backend() != "nccl"
-        src = t.cpu() if staged else t
-        out = torch.empty(self.world * src.numel(), dtype=src.dtype, device=src.device)
-        dist.all_gather_into_tensor(out, src.reshape(-1), group=self.group)     # flat: accepted by every backend
-        return out.view(self.world, *t.shape).to(t.device)
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self._all_gather_flat(out, t.reshape(-1), False)
+        return out.view(self.world, *t.shape)
+
+    def peer_tables_enabled(self) -> bool:
+        return (os.environ.get("LKG_P2P_GATHER", "1") != "0" and self.world > 1 and self._backend() == "nccl"
+                and torch.cuda.is_available())
 
 
-class PeerGather:
-    """All-gather of row blocks by peer-to-peer copies instead of NCCL (opt-in: ``LKG_P2P_GATHER=1``, NCCL backend,
-    one GPU per rank on one NVLink box).
+class PeerTable:
+    """Exchange table [padded, d] fp32 in symmetric memory: every rank maps every other rank's copy, a rank writes
+    its own row block and PUSHES it into all peer copies (see the module docstring).  ``slots`` copies alternate per
+    call: slot s is rewritten two calls later, after the barrier of the call in between, which every rank only
+    joins once its compute stream is past the kernels that read slot s (the callers' ``wait()``, kernel launches and
+    the next ``begin()`` are issued on that stream in program order)."""
 
-    Why: the layer-1 all-gather of ``h0`` (1.2 GB at N = 1 M) is the largest transfer of the pass and NCCL's kernel
-    competes for the SMs with the HBM-bound attention kernel it is supposed to hide under (measured overlap ~5 %,
-    ``scratch/nccl_probe.py``).  Device-to-device ``copy_`` between peer-mapped buffers goes through the copy engines:
-    no SM is involved, so the transfer really runs next to the kernels.
-
-    Every rank owns two ``[padded, d]`` buffers whose CUDA IPC handles are exchanged once; a gather PUSHES the rank's
-    own rows into the same slot of every peer on a side stream and closes with a one-element NCCL all-reduce issued
-    from that stream (a stream-ordered barrier: it completes when every rank's pushes are done).  Slots alternate per
-    call; slot s is rewritten two calls later, after the barrier of the call in between, which every rank only joins
-    once its main stream is past the kernels that read slot s -- the callers' ``wait()`` / kernel launches and the next
-    ``begin()`` are issued on that main stream in program order.
-
-    Status (round 1): results identical to the NCCL path (tests/test_parallel.py with LKG_P2P_GATHER=1 on two GPUs),
-    but torch's cross-device ``copy_`` into the IPC-mapped peer buffers moves only ~30 GB/s on the test box (2-GPU
-    pass 29.9 ms vs 10.1 ms with NCCL) -- it does not take the NVLink peer path.  Off by default; the transfer needs
-    its own copy kernel over the peer mapping (or explicit cudaMemcpyPeerAsync) before it can replace NCCL."""
-
-    def __init__(self, part: "RowPartition", d: int, device, dtype=torch.float32):
-        from torch.multiprocessing.reductions import reduce_tensor
-        self.part, self.d = part, int(d)
-        self.local = [torch.zeros((part.padded, d), dtype=dtype, device=device) for _ in range(2)]
-        mine = [reduce_tensor(b) for b in self.local]
-        everyone = [None] * part.world
-        dist.all_gather_object(everyone, mine, group=part.group)
-        self.peers = []                                 # peers[r][slot]: rank r's buffer mapped into this process
-        for r in range(part.world):
-            self.peers.append(self.local if r == part.rank else [fn(*args) for fn, args in everyone[r]])
+    def __init__(self, part: RowPartition, d: int, device, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.part, self.d, self.slots = part, int(d), int(slots)
+        self.rows = part.padded
+        group = part.group if part.group is not None else dist.group.WORLD
+        self.t = symm_mem.empty((self.slots, self.rows, self.d), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.t, group)
         self.stream = torch.cuda.Stream(device=device)
-        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
         self.calls = 0
 
     def begin(self):
-        """-> (table, handle): ``table`` [padded, d] is this call's buffer -- write this rank's rows
-        ``[begin, end)`` into it on the current stream, then call ``handle.start()``; ``handle.wait()`` orders the
-        current stream after the arrival of every other rank's rows."""
-        slot = self.calls & 1
+        """-> (table, handle): ``table`` [padded, d] is this call's copy -- write this rank's rows ``[begin, end)``
+        into it on the current stream, then call ``handle.start()``; ``handle.wait()`` orders the current stream
+        after the arrival of every other rank's rows."""
+        slot = self.calls % self.slots
         self.calls += 1
-        return self.local[slot], _PeerHandle(self, slot)
+        return self.t[slot], _PeerHandle(self, slot)
 
 
 class _PeerHandle:
-    def __init__(self, owner: PeerGather, slot: int):
+    def __init__(self, owner: PeerTable, slot: int):
         self.owner, self.slot, self.done = owner, slot, None
 
     def start(self):
@@ -178,17 +219,46 @@ class _PeerHandle:
         main = torch.cuda.current_stream()
         o.stream.wait_stream(main)                      # the rows are written, earlier readers of the slot are queued
         with torch.cuda.stream(o.stream):
-            rows = o.local[self.slot][part.begin:part.end]
-            for r in range(part.world):
-                if r != part.rank:
-                    o.peers[r][self.slot][part.begin:part.end].copy_(rows, non_blocking=True)
-            dist.all_reduce(o.flag, group=part.group)   # stream-ordered barrier: every rank's pushes have landed
+            b, e = part.begin, part.end
+            if e > b:
+                rows = o.t[self.slot, b:e]
+                off = (self.slot * o.rows + b) * o.d
+                for step in range(1, part.world):       # staggered destinations: no two ranks start on the same peer
+                    r = (part.rank + step) % part.world
+                    o.hdl.get_buffer(r, (e - b, o.d), torch.float32, off).copy_(rows, non_blocking=True)
+            o.hdl.barrier()                             # stream ordered: every rank's pushes have landed
             self.done = torch.cuda.Event()
             self.done.record(o.stream)
         return self
 
     def wait(self):
         torch.cuda.current_stream().wait_event(self.done)
+
+
+class PeerExchange:
+    """The exchange tables of one model: created on first use per (name, width), NCCL fallback when symmetric memory
+    cannot be set up on this box (reported once)."""
+
+    def __init__(self, part: RowPartition, device):
+        self.part, self.device = part, device
+        self.tables = {}
+        self.failed: Optional[str] = None
+
+    def table(self, name: str, d: int) -> Optional[PeerTable]:
+        if self.failed is not None:
+            return None
+        key = (name, int(d))
+        if key not in self.tables:
+            try:
+                self.tables[key] = PeerTable(self.part, d, self.device)
+            except Exception as ex:                     # noqa: BLE001 -- any setup failure means "use NCCL"
+                self.failed = f"{type(ex).__name__}: {ex}"
+                if self.part.rank == 0:
+                    import sys
+                    print(f"[literalkg_b200] symmetric-memory exchange unavailable ({self.failed}); using NCCL "
+                          "all-gather", file=sys.stderr, flush=True)
+                return None
+        return self.tables[key]
 
 
 def merge_topk(vals: torch.Tensor, ids: torch.Tensor, k: int, topk_fn) -> Tuple[torch.Tensor, torch.Tensor]:

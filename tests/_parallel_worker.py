@@ -18,11 +18,65 @@ def _init(rank, world, port, backend="gloo"):
     dist.init_process_group(backend, rank=rank, world_size=world)
 
 
+def staged_partition_cls():
+    """RowPartition whose collectives stage CUDA tensors through the host: lets two test ranks share one GPU over
+    gloo.  Test-only (the product talks to torch.distributed / NCCL directly)."""
+    from literalkg_b200.parallel import RowPartition
+
+    class Staged(RowPartition):
+        def _all_gather_flat(self, out, own, async_op):
+            c = torch.empty(out.numel(), dtype=out.dtype)
+            dist.all_gather_into_tensor(c, own.detach().cpu().reshape(-1), group=self.group)
+            out.copy_(c)
+            return None
+
+        def _all_gather_list(self, outs, own, async_op):
+            for r, o in enumerate(outs):
+                if o.numel():
+                    c = o.detach().cpu().contiguous()
+                    dist.broadcast(c, src=r, group=self.group)
+                    o.copy_(c)
+            return None
+
+        def _reduce_scatter_flat(self, out, full):
+            c = full.detach().cpu()
+            dist.all_reduce(c, group=self.group)
+            n = out.numel()
+            out.copy_(c[self.rank * n:(self.rank + 1) * n])
+
+        def _all_reduce(self, t, op):
+            c = t.detach().cpu()
+            dist.all_reduce(c, op=op, group=self.group)
+            t.copy_(c)
+
+    return Staged
+
+
 def cpu_collectives(rank, world, port, out_dir):
     """Host-side logic of the row partition on CPU tensors over gloo."""
     _init(rank, world, port)
-    from literalkg_b200.parallel import RowPartition, merge_topk
+    from literalkg_b200.parallel import merge_topk
+    RowPartition = staged_partition_cls()               # gloo has no reduce-scatter: host-staged in the test subclass
     n, d = 1003, 8                                      # not divisible by the world size
+    # nnz-balanced ranges (uneven row counts): every rank computes the same cut; exchanges go through per-rank views
+    gh = torch.Generator().manual_seed(3)
+    heads = (torch.rand(5000, generator=gh) ** 3 * n).long()          # skewed: low ids are heavy
+    bal = RowPartition.balanced(n, heads)
+    assert bal.bounds[0] == 0 and bal.bounds[-1] == n and not bal.uniform and bal.padded == n
+    cost = torch.bincount(heads, minlength=n).double() + 4.0
+    per = [cost[b:e].sum().item() for b, e in zip(bal.bounds[:-1], bal.bounds[1:])]
+    assert max(per) <= 1.25 * (sum(per) / world) + cost.max().item()
+    assert bal.n_own != RowPartition(n).n_own or world == 1
+    rows = torch.arange(n)
+    own = bal.owner_of(rows)
+    assert all(bool(((rows[own == r] >= bal.bounds[r]) & (rows[own == r] < bal.bounds[r + 1])).all()) for r in range(world))
+    refb = torch.arange(n * d, dtype=torch.float32).reshape(n, d)
+    bufb = torch.full((n, d), -1.0)
+    bufb[bal.begin:bal.end] = refb[bal.begin:bal.end]
+    bal.all_gather_rows(bufb)
+    assert torch.equal(bufb, refb)
+    rsb = bal.reduce_scatter_rows(torch.full((n, d), float(rank + 1)))
+    assert rsb.shape == (bal.n_own, d) and bool((rsb == float(sum(range(1, world + 1)))).all())
     part = RowPartition(n)
     assert part.world == world and part.rank == rank
     assert part.chunk * world >= n and part.begin == min(n, rank * part.chunk)
@@ -71,6 +125,8 @@ def gpu_partitioned_model(rank, world, port, out_dir):
     import literalkg_b200 as L
     import literalkg_oracle as O
     from literalkg_b200.parallel import RowPartition
+    if not nccl:
+        RowPartition = staged_partition_cls()
     torch.cuda.set_device(rank if nccl else 0)
     cfg = O.OracleConfig(n_conv_layers=3, mess_dropout=0.0)
     n, n_rel = 20_001, 8
@@ -92,7 +148,13 @@ def gpu_partitioned_model(rank, world, port, out_dir):
     multi.set_partition(part)
     for m in (single, multi):
         m(kt.h_list, kt.t_list, kt.r_list, kt.relations, device="cuda", mode="update_att")
+    try:                                                 # a checkpoint before the (collective) completion must not
+        multi.state_dict()                               # silently hold one rank's rows, nor hide a collective
+        raise AssertionError("state_dict() must refuse while A_in is partial")
+    except RuntimeError as ex:
+        assert "complete_attention" in str(ex)
     multi.complete_attention()                           # lazy by default: the pass only reads a rank's own rows
+    assert "A_in" in multi.state_dict()
     assert torch.equal(multi.A_in.data.indices(), single.A_in.data.indices())
     assert torch.equal(multi.A_in.data.values(), single.A_in.data.values())        # rows are independent: bit exact
     ref = single.gat_embeddings()
@@ -102,6 +164,21 @@ def gpu_partitioned_model(rank, world, port, out_dir):
     err = ((full - ref).abs().max() / ref.abs().max()).item()
     assert err < 2e-5, err                               # per-rank operand scales differ: not bit exact
     assert torch.equal(full[part.begin:part.end], local)
+    # pre-partitioned edge list + nnz-balanced (uneven) row ranges: a rank is given only the triples of its own heads
+    bal = RowPartition.balanced(n, kg.h)
+    assert bal.bounds != part.bounds
+    loc = make()
+    loc.set_partition(bal, local_edges=True)
+    mine = (kt.h_list >= bal.begin) & (kt.h_list < bal.end)
+    loc(kt.h_list[mine].int(), kt.t_list[mine].int(), kt.r_list[mine].int(), kt.relations, device="cuda", mode="update_att")
+    full_l = loc.gat_embeddings()
+    assert full_l.shape == ref.shape and ((full_l - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    loc.complete_attention()                             # all-gather of the per-rank COO blocks = the full A_in
+    assert torch.equal(loc.A_in.data.indices(), single.A_in.data.indices())
+    assert torch.equal(loc.A_in.data.values(), single.A_in.data.values())
+    full_l2 = loc.gat_embeddings()                       # plan rebuilt from the completed matrix
+    assert ((full_l2 - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    del loc
     heads = torch.arange(0, 150, device="cuda") * 131 % n
     k = 10
     sv, si = multi.topk_sharded(heads, k, local)
