@@ -228,14 +228,31 @@ __device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al
         const float a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7];
         if (row >= p.m) continue;
         float4 g, z, o;
-        g.x = tanh_fast(a0 + b0.x); z.x = sigmoid_fast(a1 + b0.y);
-        g.y = tanh_fast(a2 + b0.z); z.y = sigmoid_fast(a3 + b0.w);
-        g.z = tanh_fast(a4 + b1.x); z.z = sigmoid_fast(a5 + b1.y);
-        g.w = tanh_fast(a6 + b1.z); z.w = sigmoid_fast(a7 + b1.w);
-        o.x = fmaf(z.x, g.x - e[it].x, e[it].x);                 // (1 - z) e + z g
-        o.y = fmaf(z.y, g.y - e[it].y, e[it].y);
-        o.z = fmaf(z.z, g.z - e[it].z, e[it].z);
-        o.w = fmaf(z.w, g.w - e[it].w, e[it].w);
+        if (p.gz_out) {
+            // training pass: the saved (g, z) feed the backward; the slower variants with full relative accuracy
+            // near zero keep the forward on the reference's side of every LeakyReLU kink the golden gradients were
+            // recorded on (a single flipped sign moves a 32-entry bias gradient by percents in ANY fp32 code)
+            g.x = tanh_acc(a0 + b0.x); z.x = sigmoid_acc(a1 + b0.y);
+            g.y = tanh_acc(a2 + b0.z); z.y = sigmoid_acc(a3 + b0.w);
+            g.z = tanh_acc(a4 + b1.x); z.z = sigmoid_acc(a5 + b1.y);
+            g.w = tanh_acc(a6 + b1.z); z.w = sigmoid_acc(a7 + b1.w);
+        } else {
+            g.x = tanh_fast(a0 + b0.x); z.x = sigmoid_fast(a1 + b0.y);
+            g.y = tanh_fast(a2 + b0.z); z.y = sigmoid_fast(a3 + b0.w);
+            g.z = tanh_fast(a4 + b1.x); z.z = sigmoid_fast(a5 + b1.y);
+            g.w = tanh_fast(a6 + b1.z); z.w = sigmoid_fast(a7 + b1.w);
+        }
+        if (p.gz_out) {
+            o.x = (1.f - z.x) * e[it].x + z.x * g.x;
+            o.y = (1.f - z.y) * e[it].y + z.y * g.y;
+            o.z = (1.f - z.z) * e[it].z + z.z * g.z;
+            o.w = (1.f - z.w) * e[it].w + z.w * g.w;
+        } else {
+            o.x = fmaf(z.x, g.x - e[it].x, e[it].x);             // (1 - z) e + z g
+            o.y = fmaf(z.y, g.y - e[it].y, e[it].y);
+            o.z = fmaf(z.z, g.z - e[it].z, e[it].z);
+            o.w = fmaf(z.w, g.w - e[it].w, e[it].w);
+        }
         if (p.gz_out) {
             float* grow = p.gz_out + row * p.ld_gz + col0 + 8 * q;
             st4_guard(grow, make_float4(g.x, z.x, g.y, z.y), 2 * valid, al.gz4);

@@ -910,20 +910,21 @@ class LiteralKG(nn.Module):
     def update_attention(self, h_list, t_list, r_list, relations):
         """model.py:444-471.  Entirely on device: no host round trip, no per-relation Python loop."""
         dev = self._param_device()
-        i64 = dict(device=dev, dtype=torch.int64, non_blocking=True)
-        h, t, r = h_list.to(**i64).contiguous(), t_list.to(**i64).contiguous(), r_list.to(**i64).contiguous()
         # the CSR plan only depends on the edge list.  The very same tensors (address, length, in-place version) as
         # last time need no look at all; otherwise an unchanged list is recognised by content (one small kernel + a
-        # scalar read-back), not by address
+        # scalar read-back), not by address.  int32 / host lists are accepted (converted on the device).
         rels = tuple(int(x) for x in relations)
-        ident = (tuple((x.data_ptr(), x.numel(), x._version) for x in (h, t, r)), rels)
+        ident = (tuple((x.data_ptr(), x.numel(), x._version, x.dtype, str(x.device)) for x in (h_list, t_list, r_list)),
+                 rels)
         if self._att_plan is None or self._att_ident != ident:
+            i64 = dict(device=dev, dtype=torch.int64, non_blocking=True)
+            h, t, r = h_list.to(**i64).contiguous(), t_list.to(**i64).contiguous(), r_list.to(**i64).contiguous()
             key = (GraphPlan.fingerprint(h, t, r), rels)
             if self._att_plan is None or self._att_key != key:
                 self._att_plan = GraphPlan(h, t, r, self.n_entities, self.n_relations, relations)
                 self._att_key = key
             self._att_ident = ident
-            self._att_refs = (h, t, r)          # keeps the addresses from being reused by other tensors
+            self._att_refs = (h_list, t_list, r_list)   # keeps the addresses from being reused by other tensors
         plan = self._att_plan
         part = self._part if (self._part is not None and self._part.world > 1) else None
         with torch.no_grad():
