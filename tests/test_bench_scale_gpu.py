@@ -105,7 +105,7 @@ def sampled_rows(kg, n, n_heavy=24, n_random=1500, seed=5):
 def test_cfg3_structure_and_attention_on_sampled_rows(cfg3):
     m, kg, n = cfg3["m"], cfg3["kg"], cfg3["n"]
     rows, deg = sampled_rows(kg, n)
-    assert deg.max() == 4096 and (deg[rows] > 512).sum() >= 20     # segmented heavy rows are in the sample
+    assert deg.max() >= 4096 and (deg[rows] > 512).sum() >= 20     # segmented heavy rows are in the sample
     a = m.A_in.data
     idx, vals = a.indices(), a.values()
     assert idx.shape[1] == m._agg_plan.nnz and idx.dtype == torch.int64 and idx.shape[1] > 2 ** 24
