@@ -283,6 +283,52 @@ int lkg_transr_loss(const float* emb, int64_t ld_emb, int32_t g_dim, const float
                     const int64_t* neg, int64_t batch, float l2_lambda, float* loss, const float* grad_scale,
                     float* d_emb, int64_t ld_d, float* d_relation, float* d_trans_m, void* stream);
 
+/* ---- variant heads ------------------------------------------------------------------------
+ * TransE triplet loss of the BCE variant (model_bce.py:329-368): -log sigmoid(|h + e_r - t-|^2 - |h + e_r - t+|^2) on
+ * rows of the final embeddings (relation_dim must equal their width) + l2_lambda * the four _L2_loss_mean terms.  Same
+ * conventions as the two losses above; d_relation [R, dim] contiguous. */
+int lkg_transe_loss(const float* emb, int64_t ld_emb, int32_t dim, const float* relation, int64_t ld_rel,
+                    const int64_t* h, const int64_t* r, const int64_t* pos, const int64_t* neg, int64_t batch,
+                    float l2_lambda, float* loss, const float* grad_scale, float* d_emb, int64_t ld_d,
+                    float* d_relation, void* stream);
+/* The `mlp` mode head (model.py:499-519 initialize_MLP / train_MLP, model_bce.py:423-436):
+ *   x = [emb[h] | emb[t]] -> norm1(relu(fc1 x)) -> norm2(relu(fc2 .)) -> sigmoid(fc3 .)
+ * as a chain of fused fully-connected steps over one minibatch.  The input of a step is
+ *   pair mode   (rows_a / rows_b != NULL): in = embedding matrix, element (b, c) = in[rows_a[b], c] for c < half,
+ *               in[rows_b[b], c - half] otherwise (the torch.cat of the two gathered row blocks, never written);
+ *   affine mode (in_scale / in_shift != NULL): in[b, c] * in_scale[c] + in_shift[c] (the previous BatchNorm, folded);
+ *   plain       otherwise.
+ * out[b, j] = act(sum_c input(b, c) w[j, c] + bias[j]), act: 0 none, 1 ReLU, 2 sigmoid.  stats (nullable, device
+ * double[2 n], zero it first): column sums of out and out^2 for the BatchNorm that follows. */
+int lkg_mlp_fc_fwd(const float* in, int64_t ld_in, const int64_t* rows_a, const int64_t* rows_b, int32_t half,
+                   const float* in_scale, const float* in_shift, int64_t m, int32_t k, const float* w, int64_t ldw,
+                   const float* bias /*nullable*/, int32_t n, int32_t act, float* out, int64_t ld_out, double* stats,
+                   void* stream);
+/* nn.BatchNorm1d bookkeeping: training != 0: batch mean / biased variance from stats (m rows), running buffers updated
+ * with `momentum` and the unbiased variance; training == 0: the running buffers.  Writes scale = gamma * rstd,
+ * shift = beta - mean * scale (the folded affine of the next step) and mean / rstd (nullable) for the backward. */
+int lkg_bn_finalize(const double* stats, int64_t m, int32_t n, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, int32_t training, float* scale,
+                    float* shift, float* mean_out, float* rstd_out, void* stream);
+/* dw[j, c] += sum_b dz[b, j] input(b, c), db[j] (nullable) += sum_b dz[b, j]; input as in lkg_mlp_fc_fwd. */
+int lkg_mlp_fc_bwd_weight(const float* dz, int64_t ld_dz, const float* in, int64_t ld_in, const int64_t* rows_a,
+                          const int64_t* rows_b, int32_t half, const float* in_scale, const float* in_shift, int64_t m,
+                          int32_t k, int32_t n, float* dw, int64_t ld_dw, float* db, void* stream);
+/* dx[b, c] = sum_j dz[b, j] w[j, c].  Pair mode: ACCUMULATED into dx[rows_a[b], c] / dx[rows_b[b], c - half] (dx = the
+ * gradient of the embedding matrix).  Otherwise written to dx [m, k]; with bn_stats (device double[2 k], zero it first)
+ * the sums of the BatchNorm backward are accumulated: sum_b dx and sum_b dx * xhat, xhat = (a - mean) * rstd. */
+int lkg_mlp_fc_bwd_input(const float* dz, int64_t ld_dz, int64_t m, int32_t n, const float* w, int64_t ldw, int32_t k,
+                         float* dx, int64_t ld_dx, const int64_t* rows_a, const int64_t* rows_b, int32_t half,
+                         const float* a, int64_t ld_a, const float* mean, const float* rstd, double* bn_stats,
+                         void* stream);
+/* BatchNorm + ReLU backward: dz = [a > 0] gamma rstd (dy - s1 / m - xhat s2 / m) with the sums of bn_stats
+ * (training == 0: dz = [a > 0] gamma rstd dy); dgamma += s2, dbeta += s1. */
+int lkg_bn_relu_bwd(const float* dy, int64_t ld_dy, const float* a, int64_t ld_a, const float* mean, const float* rstd,
+                    const float* gamma, const double* bn_stats, int64_t m, int32_t k, int32_t training, float* dz,
+                    int64_t ld_dz, float* dgamma, float* dbeta, void* stream);
+/* dz = dy * y * (1 - y). */
+int lkg_sigmoid_bwd(const float* dy, const float* y, int64_t m, float* dz, void* stream);
+
 /* ---- minibatch assembly (dataloader.py:192-318): per head one positive (tail, relation) drawn uniformly from the
  *      head's triples and neg_rate negative tails drawn from `candidates` by rejection (not a positive of the head
  *      under the drawn relation -- any relation when use_relation == 0 -- and not drawn before).  rowptr / tails / rels:

@@ -73,6 +73,13 @@ SIGNATURES = {
     "lkg_bpr_loss": (C.c_int, [vp, i64, i32, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp]),
     "lkg_transr_loss": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp, vp,
                                   vp]),
+    "lkg_transe_loss": (C.c_int, [vp, i64, i32, vp, i64, vp, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp, vp]),
+    "lkg_mlp_fc_fwd": (C.c_int, [vp, i64, vp, vp, i32, vp, vp, i64, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
+    "lkg_bn_finalize": (C.c_int, [vp, i64, i32, vp, vp, C.c_float, C.c_float, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "lkg_mlp_fc_bwd_weight": (C.c_int, [vp, i64, vp, i64, vp, vp, i32, vp, vp, i64, i32, i32, vp, i64, vp, vp]),
+    "lkg_mlp_fc_bwd_input": (C.c_int, [vp, i64, i64, i32, vp, i64, i32, vp, i64, vp, vp, i32, vp, i64, vp, vp, vp, vp]),
+    "lkg_bn_relu_bwd": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, i64, vp, vp, vp]),
+    "lkg_sigmoid_bwd": (C.c_int, [vp, vp, i64, vp, vp]),
     "lkg_score": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i64, vp, i64, vp, vp]),
     "lkg_minmax_reset": (C.c_int, [vp, vp]),
     "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),

@@ -122,24 +122,4 @@ __device__ __forceinline__ float tanh_acc(float x) {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + __expf(-x)); }
 
-// Epilogue variants, 4-5 instructions each (2 MUFU): absolute error ~2e-7 like the ones above (they differ only in
-// RELATIVE accuracy near zero, which a value that is mixed into an O(1) sum does not need).
-//   tanh(x) = 1 - 2 / (1 + e^{2x})      (e = +inf -> 1, e = 0 -> -1: saturates without a branch)
-//   sigmoid(x) = 1 / (1 + e^{-x})
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-    const float e = ex2_approx(2.8853900817779268f * x);          // e^{2x}
-    return fmaf(-2.f, rcp_approx(1.f + e), 1.f);
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
-
 }  // namespace lkg

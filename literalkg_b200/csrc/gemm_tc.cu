@@ -228,31 +228,18 @@ __device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al
         const float a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3], a4 = sp[4], a5 = sp[5], a6 = sp[6], a7 = sp[7];
         if (row >= p.m) continue;
         float4 g, z, o;
-        if (p.gz_out) {
-            // training pass: the saved (g, z) feed the backward; the slower variants with full relative accuracy
-            // near zero keep the forward on the reference's side of every LeakyReLU kink the golden gradients were
-            // recorded on (a single flipped sign moves a 32-entry bias gradient by percents in ANY fp32 code)
-            g.x = tanh_acc(a0 + b0.x); z.x = sigmoid_acc(a1 + b0.y);
-            g.y = tanh_acc(a2 + b0.z); z.y = sigmoid_acc(a3 + b0.w);
-            g.z = tanh_acc(a4 + b1.x); z.z = sigmoid_acc(a5 + b1.y);
-            g.w = tanh_acc(a6 + b1.z); z.w = sigmoid_acc(a7 + b1.w);
-        } else {
-            g.x = tanh_fast(a0 + b0.x); z.x = sigmoid_fast(a1 + b0.y);
-            g.y = tanh_fast(a2 + b0.z); z.y = sigmoid_fast(a3 + b0.w);
-            g.z = tanh_fast(a4 + b1.x); z.z = sigmoid_fast(a5 + b1.y);
-            g.w = tanh_fast(a6 + b1.z); z.w = sigmoid_fast(a7 + b1.w);
-        }
-        if (p.gz_out) {
-            o.x = (1.f - z.x) * e[it].x + z.x * g.x;
-            o.y = (1.f - z.y) * e[it].y + z.y * g.y;
-            o.z = (1.f - z.z) * e[it].z + z.z * g.z;
-            o.w = (1.f - z.w) * e[it].w + z.w * g.w;
-        } else {
-            o.x = fmaf(z.x, g.x - e[it].x, e[it].x);             // (1 - z) e + z g
-            o.y = fmaf(z.y, g.y - e[it].y, e[it].y);
-            o.z = fmaf(z.z, g.z - e[it].z, e[it].z);
-            o.w = fmaf(z.w, g.w - e[it].w, e[it].w);
-        }
+        // tanh_acc / sigmoid_acc keep RELATIVE accuracy near zero (the gate's pre-activations are ~0.05 at the reference's
+        // initialisation): a 5-instruction 1 - 2 / (1 + e^{2x}) is 2e-7 ABSOLUTE, 30 x worse there, and the LayerNorms
+        // downstream amplify it (bench parity leg: row-error quantiles 3 - 10 x the fp32 reference's).  With 12 epilogue
+        // warps the MMAs, not this math, pace the tile.
+        g.x = tanh_acc(a0 + b0.x); z.x = sigmoid_acc(a1 + b0.y);
+        g.y = tanh_acc(a2 + b0.z); z.y = sigmoid_acc(a3 + b0.w);
+        g.z = tanh_acc(a4 + b1.x); z.z = sigmoid_acc(a5 + b1.y);
+        g.w = tanh_acc(a6 + b1.z); z.w = sigmoid_acc(a7 + b1.w);
+        o.x = (1.f - z.x) * e[it].x + z.x * g.x;
+        o.y = (1.f - z.y) * e[it].y + z.y * g.y;
+        o.z = (1.f - z.z) * e[it].z + z.z * g.z;
+        o.w = (1.f - z.w) * e[it].w + z.w * g.w;
         if (p.gz_out) {
             float* grow = p.gz_out + row * p.ld_gz + col0 + 8 * q;
             st4_guard(grow, make_float4(g.x, z.x, g.y, z.y), 2 * valid, al.gz4);
@@ -267,9 +254,11 @@ __device__ __forceinline__ void gate_block(const TcParams& p, const EpiAlign& al
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) per 256-row tile -- the leader issues
-// tcgen05.mma.cta_group::2 (M = 256), every CTA stages its own 128 rows of A and HALF of the B tile, so the bytes a CTA
-// pulls from L2 per tile drop from A + B to A + B/2 (the gate GEMM: 850 KB -> 586 KB; L2 -> SM fill was the bound with
-// cta_group::1: 42 B/cycle/SM x 158 tiles) and a third pipeline stage fits.
+// tcgen05.mma.cta_group::2 (M = 256), every CTA stages its own 128 rows of A and HALF of the B tile (gate GEMM: 586 KB
+// instead of 850 KB pulled from L2 per CTA and tile, one more pipeline stage, B read from shared memory once for
+// both tensor cores).  Measured (r02c, cfg 3): gate 2.17 -> 2.07 ms, h0 @ Q 0.48 -> 0.43 ms, linear_gat 0.63 -> 0.57 ms;
+// bit-identical results.  What took the gate from 2.57 ms to there was the epilogue (coalesced staging, 12 warps):
+// ncu then shows the tensor pipe 75 % busy at the power-capped 1.27 GHz -- three products per k-step are the floor.
 template <int EPI, int CG, int G>
 __global__ void __launch_bounds__(threads_for(G), 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     constexpr int kEpiGroups = G;
