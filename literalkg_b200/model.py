@@ -282,6 +282,75 @@ class _TransRLossFn(torch.autograd.Function):
         return d_emb, d_rel, d_m, None, None, None, None, None
 
 
+class _TransELossFn(torch.autograd.Function):
+    """calc_triplet_loss of the BCE variant (model_bce.py:329-368): TransE on rows of the final embeddings."""
+
+    @staticmethod
+    def forward(ctx, emb, rel, h, r, pos, neg, lam):
+        emb = emb if (emb.dtype == torch.float32 and emb.stride(1) == 1) else _lib.f32c(emb)
+        loss = torch.zeros((), dtype=torch.float32, device=emb.device)
+        ops.transe_loss(emb, rel, h, r, pos, neg, lam, loss)
+        ctx.save_for_backward(emb, rel, h, r, pos, neg)
+        ctx.lam = lam
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, rel, h, r, pos, neg = ctx.saved_tensors
+        d_emb = torch.zeros_like(emb)
+        d_rel = torch.zeros(rel.shape, dtype=torch.float32, device=emb.device)
+        ops.transe_loss(emb, rel, h, r, pos, neg, ctx.lam, None, grad_scale=g.float().contiguous(), d_emb=d_emb,
+                        d_relation=d_rel)
+        return d_emb, d_rel, None, None, None, None, None
+
+
+class _MlpHeadFn(torch.autograd.Function):
+    """train_MLP (model.py:506-519, model_bce.py:423-436) on one minibatch of (head, tail) pairs:
+    sigmoid(fc3(norm2(relu(fc2(norm1(relu(fc1([emb[h] | emb[t]])))))))) as fused fully-connected steps
+    (csrc/mlp_head.cu); the gathered [B, 2G] block and the BatchNorm outputs are never materialised."""
+
+    @staticmethod
+    def forward(ctx, owner, emb, h, t, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3):
+        emb = emb if (emb.dtype == torch.float32 and emb.stride(1) == 1) else _lib.f32c(emb)
+        dev = emb.device
+        h = h.to(device=dev, dtype=torch.int64).contiguous()
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        m = h.numel()
+        training = owner.norm1.training
+        if training and m < 2:
+            raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d)")
+        stats = (lambda n: torch.zeros(2 * n, dtype=torch.float64, device=dev)) if training else (lambda n: None)
+        st1, st2 = stats(w1.shape[0]), stats(w2.shape[0])
+        a1 = ops.mlp_fc_fwd(emb, w1, b1, ops.ACT_FC_RELU, m, pair=(h, t), stats=st1)
+        sc1, sh1, mean1, rstd1 = ops.bn_finalize(st1, m, owner.norm1, training)
+        a2 = ops.mlp_fc_fwd(a1, w2, b2, ops.ACT_FC_RELU, m, affine=(sc1, sh1), stats=st2)
+        sc2, sh2, mean2, rstd2 = ops.bn_finalize(st2, m, owner.norm2, training)
+        y = ops.mlp_fc_fwd(a2, w3, b3, ops.ACT_FC_SIGMOID, m, affine=(sc2, sh2))
+        ctx.save_for_backward(emb, h, t, w1, w2, w3, g1, g2, a1, a2, y, sc1, sh1, mean1, rstd1, sc2, sh2, mean2, rstd2)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (emb, h, t, w1, w2, w3, g1, g2, a1, a2, y, sc1, sh1, mean1, rstd1, sc2, sh2, mean2, rstd2) = ctx.saved_tensors
+        dev, m, tr = emb.device, h.numel(), ctx.training
+        f64 = lambda n: torch.zeros(2 * n, dtype=torch.float64, device=dev)
+        dz3 = ops.sigmoid_bwd(dy, y).view(m, 1)
+        dw3, db3 = ops.mlp_fc_bwd_weight(dz3, a2, w3.shape[1], affine=(sc2, sh2))
+        s2 = f64(w2.shape[0])
+        dy2 = ops.mlp_fc_bwd_input(dz3, w3, torch.empty((m, w2.shape[0]), dtype=torch.float32, device=dev),
+                                   bn=(a2, mean2, rstd2, s2))
+        dz2, dg2, dbe2 = ops.bn_relu_bwd(dy2, a2, mean2, rstd2, g2, s2, tr)
+        dw2, db2 = ops.mlp_fc_bwd_weight(dz2, a1, w2.shape[1], affine=(sc1, sh1))
+        s1 = f64(w1.shape[0])
+        dy1 = ops.mlp_fc_bwd_input(dz2, w2, torch.empty((m, w1.shape[0]), dtype=torch.float32, device=dev),
+                                   bn=(a1, mean1, rstd1, s1))
+        dz1, dg1, dbe1 = ops.bn_relu_bwd(dy1, a1, mean1, rstd1, g1, s1, tr)
+        dw1, db1 = ops.mlp_fc_bwd_weight(dz1, emb, w1.shape[1], pair=(h, t))
+        d_emb = ops.mlp_fc_bwd_input(dz1, w1, torch.zeros_like(emb), pair=(h, t))
+        return None, d_emb, None, None, dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, dw3, db3
+
+
 class LiteralKG(nn.Module):
     """model.py:167-532."""
 
@@ -1071,6 +1140,34 @@ class LiteralKG(nn.Module):
         with torch.no_grad():
             return self.gat_embeddings()[entity_ids]
 
+    # ---- `mlp` mode: the BCE fine-tuning head (model.py:499-519) ------------------------------------------------
+    def initialize_MLP(self):
+        """model.py:499-504: fc1 / norm1 / fc2 / norm2 / fc3 (same attribute names = same state-dict keys)."""
+        width = self.scale_gat_dim if self.scale_gat_dim is not None else self.total_conv_dim
+        if self.scale_gat_dim is None:
+            raise TypeError("initialize_MLP needs scale_gat_dim (the reference multiplies it by 2, model.py:500)")
+        self.fc1 = nn.Linear(width * 2, 128)
+        self.norm1 = nn.BatchNorm1d(128)
+        self.fc2 = nn.Linear(128, 64)
+        self.norm2 = nn.BatchNorm1d(64)
+        self.fc3 = nn.Linear(64, 1)
+        dev = self.entity_embed.weight.device
+        for mod in (self.fc1, self.norm1, self.fc2, self.norm2, self.fc3):
+            mod.to(dev)
+
+    def mlp_scores_from(self, all_embed, head_ids, tail_ids):
+        """The head of ``train_MLP`` on a given embedding matrix -> [B, 1] probabilities."""
+        if not hasattr(self, "fc1"):
+            raise AttributeError("call initialize_MLP() first (model.py:499)")
+        return _MlpHeadFn.apply(self, all_embed, head_ids, tail_ids, self.fc1.weight, self.fc1.bias,
+                                self.norm1.weight, self.norm1.bias, self.fc2.weight, self.fc2.bias,
+                                self.norm2.weight, self.norm2.bias, self.fc3.weight, self.fc3.bias)
+
+    def train_MLP(self, head_ids, tail_ids):
+        """model.py:506-519."""
+        self.gat_embed = self.gat_embeddings()
+        return self.mlp_scores_from(self.gat_embed, head_ids, tail_ids)
+
     def forward(self, *input, device, mode):
         """model.py:521-532."""
         self.device = device
@@ -1082,4 +1179,6 @@ class LiteralKG(nn.Module):
             return self.update_attention(*input)
         if mode == 'predict':
             return self.predict_links(*input)
-        raise NotImplementedError(f"mode {mode!r} is outside the accelerated path (SURVEY.md section 8(f))")
+        if mode == 'mlp':
+            return self.train_MLP(*input)
+        raise NotImplementedError(f"unknown mode {mode!r}")

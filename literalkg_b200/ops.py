@@ -493,3 +493,130 @@ def transr_loss(emb: torch.Tensor, relation: torch.Tensor, trans_m: torch.Tensor
             trans_m.data_ptr(), h.data_ptr(), r.data_ptr(), pos.data_ptr(), neg.data_ptr(), h.numel(), float(l2_lambda),
             _lib.ptr(loss), _lib.ptr(grad_scale), _lib.ptr(d_emb), 0 if d_emb is None else _rowmajor(d_emb).stride(0),
             _lib.ptr(d_relation), _lib.ptr(d_trans_m), _lib.stream()))
+
+
+# ---- variant heads (csrc/mlp_head.cu): TransE loss and the `mlp` mode head --------------------------------------------
+def transe_loss(emb: torch.Tensor, relation: torch.Tensor, h, r, pos, neg, l2_lambda: float,
+                loss: Optional[torch.Tensor], grad_scale: Optional[torch.Tensor] = None,
+                d_emb: Optional[torch.Tensor] = None, d_relation: Optional[torch.Tensor] = None) -> None:
+    _rowmajor(emb)
+    relation = _lib.f32c(relation)
+    if relation.shape[1] != emb.shape[1]:
+        raise ValueError("the TransE loss adds relation embeddings to rows of the final embeddings: relation_dim "
+                         f"({relation.shape[1]}) must equal their width ({emb.shape[1]}) (model_bce.py:351-354)")
+    h, r, pos, neg = (_ids(x, emb.device) for x in (h, r, pos, neg))
+    assert d_relation is None or (d_relation.dtype == torch.float32 and d_relation.is_contiguous())
+    with _dev_guard(emb, "transe_loss"):
+        _lib.check(_lib.load().lkg_transe_loss(
+            emb.data_ptr(), emb.stride(0), emb.shape[1], relation.data_ptr(), relation.stride(0), h.data_ptr(),
+            r.data_ptr(), pos.data_ptr(), neg.data_ptr(), h.numel(), float(l2_lambda), _lib.ptr(loss),
+            _lib.ptr(grad_scale), _lib.ptr(d_emb), 0 if d_emb is None else _rowmajor(d_emb).stride(0),
+            _lib.ptr(d_relation), _lib.stream()))
+
+
+ACT_FC_NONE, ACT_FC_RELU, ACT_FC_SIGMOID = 0, 1, 2
+
+
+def mlp_fc_fwd(src: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, m: int,
+               pair=None, affine=None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(input @ weight^T + bias) over ``m`` batch rows.  ``pair`` = (rows_a, rows_b): the input is
+    [src[rows_a] | src[rows_b]]; ``affine`` = (scale, shift): the input is src * scale + shift (folded BatchNorm)."""
+    _rowmajor(src)
+    weight = _lib.f32c(weight)
+    n, k = weight.shape
+    out = torch.empty((m, n), dtype=torch.float32, device=src.device)
+    ra = rb = sc = sh = None
+    half = 0
+    if pair is not None:
+        ra, rb = pair
+        half = src.shape[1]
+        assert k == 2 * half
+    if affine is not None:
+        sc, sh = affine
+    with _dev_guard(src, "mlp_fc_fwd"):
+        _lib.check(_lib.load().lkg_mlp_fc_fwd(src.data_ptr(), src.stride(0), _lib.ptr(ra), _lib.ptr(rb), half, _lib.ptr(sc),
+                                              _lib.ptr(sh), m, k, weight.data_ptr(), weight.stride(0),
+                                              _lib.ptr(None if bias is None else _lib.f32c(bias)), n, act, out.data_ptr(),
+                                              out.stride(0), _lib.ptr(stats), _lib.stream()))
+    return out
+
+
+def bn_finalize(stats: Optional[torch.Tensor], m: int, bn: "torch.nn.BatchNorm1d", training: bool):
+    """-> (scale, shift, mean, rstd) of one BatchNorm1d; training updates the running buffers like torch."""
+    n = bn.num_features
+    dev = bn.weight.device
+    scale, shift, mean, rstd = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(4))
+    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    with _dev_guard(scale, "bn_finalize"):
+        _lib.check(_lib.load().lkg_bn_finalize(_lib.ptr(stats), m, n, bn.weight.detach().data_ptr(),
+                                               bn.bias.detach().data_ptr(), float(bn.eps), momentum,
+                                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(), int(training),
+                                               scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                               _lib.stream()))
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return scale, shift, mean, rstd
+
+
+def mlp_fc_bwd_weight(dz: torch.Tensor, src: torch.Tensor, k: int, pair=None, affine=None):
+    """(dW [n, k], db [n]) of one fully-connected step; the input transform is recomputed like in the forward."""
+    _rowmajor(dz); _rowmajor(src)
+    m, n = dz.shape
+    dw = torch.zeros((n, k), dtype=torch.float32, device=dz.device)
+    db = torch.zeros(n, dtype=torch.float32, device=dz.device)
+    ra = rb = sc = sh = None
+    half = 0
+    if pair is not None:
+        ra, rb = pair
+        half = src.shape[1]
+    if affine is not None:
+        sc, sh = affine
+    with _dev_guard(dz, "mlp_fc_bwd_weight"):
+        _lib.check(_lib.load().lkg_mlp_fc_bwd_weight(dz.data_ptr(), dz.stride(0), src.data_ptr(), src.stride(0),
+                                                     _lib.ptr(ra), _lib.ptr(rb), half, _lib.ptr(sc), _lib.ptr(sh), m, k, n,
+                                                     dw.data_ptr(), dw.stride(0), db.data_ptr(), _lib.stream()))
+    return dw, db
+
+
+def mlp_fc_bwd_input(dz: torch.Tensor, weight: torch.Tensor, dx: torch.Tensor, pair=None, bn=None) -> torch.Tensor:
+    """dx = dz @ weight.  ``pair`` = (rows_a, rows_b): accumulated into the rows of ``dx`` (the embedding gradient);
+    ``bn`` = (a, mean, rstd, stats): also accumulates the two column sums of the BatchNorm backward."""
+    _rowmajor(dz); _rowmajor(dx)
+    weight = _lib.f32c(weight)
+    m, n = dz.shape
+    k = weight.shape[1]
+    ra = rb = a = mean = rstd = stats = None
+    half = 0
+    if pair is not None:
+        ra, rb = pair
+        half = dx.shape[1]
+    if bn is not None:
+        a, mean, rstd, stats = bn
+    with _dev_guard(dz, "mlp_fc_bwd_input"):
+        _lib.check(_lib.load().lkg_mlp_fc_bwd_input(dz.data_ptr(), dz.stride(0), m, n, weight.data_ptr(), weight.stride(0), k,
+                                                    dx.data_ptr(), dx.stride(0), _lib.ptr(ra), _lib.ptr(rb), half,
+                                                    _lib.ptr(a), 0 if a is None else a.stride(0), _lib.ptr(mean),
+                                                    _lib.ptr(rstd), _lib.ptr(stats), _lib.stream()))
+    return dx
+
+
+def bn_relu_bwd(dy: torch.Tensor, a: torch.Tensor, mean, rstd, gamma, stats, training: bool):
+    """-> (dz, dgamma, dbeta): BatchNorm (batch or running statistics) + ReLU backward."""
+    m, k = dy.shape
+    dz = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    dgamma = torch.zeros(k, dtype=torch.float32, device=dy.device)
+    dbeta = torch.zeros(k, dtype=torch.float32, device=dy.device)
+    with _dev_guard(dy, "bn_relu_bwd"):
+        _lib.check(_lib.load().lkg_bn_relu_bwd(dy.data_ptr(), dy.stride(0), a.data_ptr(), a.stride(0), mean.data_ptr(),
+                                               rstd.data_ptr(), _lib.f32c(gamma).data_ptr(), stats.data_ptr(), m, k,
+                                               int(training), dz.data_ptr(), dz.stride(0), dgamma.data_ptr(),
+                                               dbeta.data_ptr(), _lib.stream()))
+    return dz, dgamma, dbeta
+
+
+def sigmoid_bwd(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    dy, y = _lib.f32c(dy).reshape(-1), _lib.f32c(y).reshape(-1)
+    dz = torch.empty_like(y)
+    with _dev_guard(y, "sigmoid_bwd"):
+        _lib.check(_lib.load().lkg_sigmoid_bwd(dy.data_ptr(), y.data_ptr(), y.numel(), dz.data_ptr(), _lib.stream()))
+    return dz

@@ -399,9 +399,46 @@ def triplet_loss(p, all_embed, cfg: OracleConfig, h, r, pos, neg):
 
 
 # ----------------------------------------------------------------------------------------------
-# parameter initialisation with the reference's shapes (model.py:215-261, gate.py) -- used by
-# bench.py / tests to create weights without importing the reference
+# variant heads: the `mlp` mode (model.py:499-519, model_bce.py:423-436) and the TransE loss of the
+# BCE variant (model_bce.py:329-368)
 # ----------------------------------------------------------------------------------------------
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1     # nn.BatchNorm1d defaults (model.py:501-503 passes none)
+
+
+def batch_norm(p, pre: str, x, training: bool, update: bool = True):
+    """nn.BatchNorm1d: batch mean / BIASED variance in training (running buffers updated with the UNBIASED one),
+    running buffers in evaluation."""
+    if training:
+        mean, var = x.mean(0), x.var(0, unbiased=False)
+        if update:
+            p[pre + "running_mean"] = (1 - BN_MOMENTUM) * p[pre + "running_mean"] + BN_MOMENTUM * mean.detach()
+            p[pre + "running_var"] = (1 - BN_MOMENTUM) * p[pre + "running_var"] + BN_MOMENTUM * x.var(0, unbiased=True).detach()
+            p[pre + "num_batches_tracked"] = p[pre + "num_batches_tracked"] + 1
+    else:
+        mean, var = p[pre + "running_mean"], p[pre + "running_var"]
+    return (x - mean) / torch.sqrt(var + BN_EPS) * p[pre + "weight"] + p[pre + "bias"]
+
+
+def mlp_head(p, all_embed, head_ids, tail_ids, training: bool, update: bool = True):
+    """train_MLP given gat_embeddings() (model.py:506-519): cat(head, tail) -> norm1(relu(fc1)) -> norm2(relu(fc2))
+    -> sigmoid(fc3), [B, 1]."""
+    x = torch.cat([all_embed[head_ids], all_embed[tail_ids]], dim=1)
+    x = batch_norm(p, "norm1.", torch.relu(F.linear(x, p["fc1.weight"], p["fc1.bias"])), training, update)
+    x = batch_norm(p, "norm2.", torch.relu(F.linear(x, p["fc2.weight"], p["fc2.bias"])), training, update)
+    return torch.sigmoid(F.linear(x, p["fc3.weight"], p["fc3.bias"]))
+
+
+def transe_loss(p, all_embed, cfg: OracleConfig, h, r, pos, neg):
+    """calc_triplet_loss of model_bce.py:329-368: TransE on rows of the final embeddings."""
+    re_ = p["relation_embed.weight"][r]
+    he, pe, ne = all_embed[h], all_embed[pos], all_embed[neg]
+    pos_s = torch.sum((he + re_ - pe) ** 2, dim=1)
+    neg_s = torch.sum((he + re_ - ne) ** 2, dim=1)
+    loss = torch.mean(-F.logsigmoid(neg_s - pos_s))
+    l2 = _l2_mean(he) + _l2_mean(re_) + _l2_mean(pe) + _l2_mean(ne)
+    return loss + cfg.kg_l2loss_lambda * l2
+
+
 # ----------------------------------------------------------------------------------------------
 # minibatch generators (dataloader.py:192-333)
 # ----------------------------------------------------------------------------------------------
@@ -486,6 +523,10 @@ def check_batch_contract(kg_dict, heads, rels, pos, neg, neg_rate: int, candidat
             assert int(pos[i, 0]) in tails and all(x not in tails for x in negs)
 
 
+# ----------------------------------------------------------------------------------------------
+# parameter initialisation with the reference's shapes (model.py:215-261, gate.py) -- used by
+# bench.py / tests to create weights without importing the reference
+# ----------------------------------------------------------------------------------------------
 def init_params(cfg: OracleConfig, n_entities: int, n_relations: int, seed: int = 2022,
                 dtype=torch.float32) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)

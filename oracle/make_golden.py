@@ -168,7 +168,107 @@ def run_case(name, cfg: OracleConfig, n, n_rel, n_edges, seed, laplacian_type="r
     print(f"{name}: N={n} E={len(h)} nnz={out['att/idx'].shape[1]} -> {os.path.getsize(path)/1e3:.0f} kB")
 
 
+def run_head_case(name, cfg: OracleConfig, n, n_rel, n_edges, seed, variant):
+    """The variant heads of the unmodified reference:
+       variant 'bce'  model_bce.LiteralKG: TransE calc_triplet_loss, BPR loss, mode 'mlp' (constructor-built head);
+       variant 'mlp'  model.LiteralKG + initialize_MLP(): mode 'mlp'.
+    Stored: state dict (BatchNorm buffers included), A_in after update_att, final embeddings, the head's output in
+    training mode (batch statistics; the updated running buffers) and in eval mode, nn.BCELoss against random labels
+    and its gradients w.r.t. every parameter, and (bce) the TransE loss + gradients."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref = importlib.import_module("model_bce" if variant == "bce" else "model")
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    h, t, r = make_kg(n, n_rel, n_edges, seed)
+    rng = np.random.default_rng(seed + 1)
+    num_lit = torch.from_numpy(rng.uniform(0, 1, size=(n, cfg.num_lit_dim)).astype(np.float32))
+    num_lit[rng.choice(n, n // 2, replace=False)] = 0
+    txt_lit = torch.from_numpy(rng.normal(0, 0.3, size=(n, cfg.txt_lit_dim)).astype(np.float32))
+    lap_idx, lap_val, relations = ref_laplacian(h, t, r, n, "random-walk")
+    a0 = torch.sparse_coo_tensor(torch.from_numpy(lap_idx), torch.from_numpy(lap_val), (n, n))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = ref.LiteralKG(namespace(cfg), n, n_rel, a0, num_lit, txt_lit)
+        if variant == "mlp":
+            model.initialize_MLP()
+        with torch.no_grad():
+            model.entity_embed.weight.mul_(3.0)
+            for k, v in model.named_parameters():
+                if "norm" in k or k.endswith("gate_bias"):
+                    v.add_(0.1 * torch.randn_like(v))
+            for nm in ("norm1", "norm2"):                 # non-trivial running statistics for the eval-mode output
+                getattr(model, nm).running_mean.add_(0.05 * torch.randn_like(getattr(model, nm).running_mean))
+                getattr(model, nm).running_var.mul_(1.0 + 0.2 * torch.rand_like(getattr(model, nm).running_var))
+        hl, tl, rl = torch.from_numpy(h), torch.from_numpy(t), torch.from_numpy(r)
+        model(hl, tl, rl, relations, device="cpu", mode="update_att")
+    out = {"config": np.frombuffer(json.dumps({**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__},
+                                               "n_entities": n, "n_relations": n_rel,
+                                               "laplacian_type": "random-walk"}).encode(), dtype=np.uint8)}
+    for k, v in model.state_dict().items():
+        if k != "A_in":
+            out["sd/" + k] = v.detach().numpy().copy()
+    a = model.A_in.data.coalesce()
+    out["att/idx"], out["att/val"] = a.indices().numpy().copy(), a.values().numpy().copy()
+    out["in/h"], out["in/t"], out["in/r"] = h, t, r
+    out["in/relations"] = np.asarray(relations, dtype=np.int64)
+    out["in/num_lit"], out["in/txt_lit"] = num_lit.numpy(), txt_lit.numpy()
+    b = 37
+    bh, bt = torch.from_numpy(rng.integers(0, n, size=b)), torch.from_numpy(rng.integers(0, n, size=b))
+    labels = torch.from_numpy(rng.integers(0, 2, size=b).astype(np.float32))
+    out["mlp/h"], out["mlp/t"], out["mlp/labels"] = bh.numpy(), bt.numpy(), labels.numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.eval()
+        with torch.no_grad():
+            out["final"] = model.gat_embeddings().numpy().copy()
+            out["mlp/eval_out"] = model(bh, bt, device="cpu", mode="mlp").numpy().copy()
+        # training-mode output: batch statistics (dropout rate is 0 in these configs, so the trunk is deterministic)
+        model.train()
+        model.zero_grad()
+        y = model(bh, bt, device="cpu", mode="mlp")
+        loss = torch.nn.BCELoss()(y.reshape(-1), labels)          # main_finetuning_BCE.py:88,117-120
+        loss.backward()
+        out["mlp/train_out"] = y.detach().numpy().copy()
+        out["mlp/bce_loss"] = np.asarray(loss.item(), dtype=np.float64)
+        for k, v in model.named_parameters():
+            if v.grad is not None and k != "A_in":
+                out["grad_mlp/" + k] = v.grad.detach().numpy().copy()
+        for nm in ("norm1", "norm2"):
+            out[f"mlp/after/{nm}.running_mean"] = getattr(model, nm).running_mean.numpy().copy()
+            out[f"mlp/after/{nm}.running_var"] = getattr(model, nm).running_var.numpy().copy()
+        if variant == "bce":
+            bp, bn = torch.from_numpy(rng.integers(0, n, size=b)), torch.from_numpy(rng.integers(0, n, size=b))
+            br = torch.from_numpy(rng.integers(0, n_rel, size=b))
+            out["loss/h"], out["loss/r"], out["loss/pos"], out["loss/neg"] = bh.numpy(), br.numpy(), bp.numpy(), bn.numpy()
+            for mode, inp in (("pre_training", (bh, br, bp, bn)), ("fine_tuning", (bh, bp, bn))):
+                model.zero_grad()
+                loss = model(*inp, device="cpu", mode=mode)
+                loss.backward()
+                out[f"loss/{mode}"] = np.asarray(loss.item(), dtype=np.float64)
+                for k, v in model.named_parameters():
+                    if v.grad is not None and k != "A_in":
+                        out[f"grad_{mode}/" + k] = v.grad.detach().numpy().copy()
+    path = os.path.join(ROOT, "tests", "golden_heads", name + ".npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **out)
+    print(f"{name}: N={n} E={len(h)} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
+def main_heads():
+    # embed_dim == relation_dim (update_att adds the two tables) == scale_gat_dim (TransE adds relation rows to the
+    # final embeddings, model_bce.py:351-354)
+    small = dict(embed_dim=16, relation_dim=16, scale_gat_dim=16, num_lit_dim=2, txt_lit_dim=8, conv_dim=8,
+                 n_conv_layers=2, mess_dropout=0.0)
+    run_head_case("bce_small_bi", OracleConfig(aggregation_type="bi-interaction", **small), 57, 4, 240, 21, "bce")
+    run_head_case("bce_small_gcn", OracleConfig(aggregation_type="gcn", use_residual=False, **small), 57, 4, 240, 22, "bce")
+    run_head_case("mlp_small_sage", OracleConfig(aggregation_type="graphsage", **small), 57, 4, 240, 23, "mlp")
+
+
 def main():
+    if "--heads" in sys.argv:
+        return main_heads()
     small = dict(embed_dim=12, relation_dim=12, scale_gat_dim=16, num_lit_dim=2, txt_lit_dim=8,
                  conv_dim=8, n_conv_layers=2, mess_dropout=0.0)
     for agg in ("bi-interaction", "gcn", "graphsage"):

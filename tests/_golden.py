@@ -12,9 +12,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+HEADS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_heads")
+HEAD_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(HEADS_DIR, "*.npz")))
+
+
 class Golden:
-    def __init__(self, name):
-        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    def __init__(self, name, directory=GOLDEN_DIR):
+        z = np.load(os.path.join(directory, name + ".npz"))
         self.name = name
         raw = json.loads(bytes(z["config"]).decode())
         self.n = raw.pop("n_entities")
