@@ -49,7 +49,7 @@ inline int stages_for(int bn_cta, int groups) {
     return s > kStages ? kStages : s;
 }
 
-enum EpiKind { kEpiLinear = 0, kEpiGate = 1, kEpiScore = 2 };
+enum EpiKind { kEpiLinear = 0, kEpiGate = 1, kEpiScore = 2, kEpiRank = 3 };
 
 struct TcParams {
     CUtensorMap a_map[LKG_MAX_SEGMENTS];
@@ -80,6 +80,13 @@ struct TcParams {
     float* gz_out;                      // gate, training: activated (tanh g, sigmoid z) pairs [m, n] (nullable)
     int64_t ld_gz;
     int accumulate;                     // linear: out += result
+    // rank epilogue (lkg_score_rank): no score is stored.  Per head row the columns whose score is certainly above the
+    // target's are counted; the ones inside the error band around it are listed for an exact re-score
+    const float* rank_thr;              // [m][2] {lo, hi} = exact target score -/+ the error bound of the 3-product GEMM
+    int* rank_above;                    // [m]   += columns with score > hi
+    int* rank_band_cnt;                 // [m]   += columns with lo <= score <= hi
+    int* rank_band;                     // [m][rank_band_cap] those columns (first rank_band_cap of them)
+    int rank_band_cap;
 };
 
 __device__ __forceinline__ uint32_t order_enc(float f) {
@@ -434,6 +441,10 @@ __global__ void __launch_bounds__(threads_for(G), 1) tc_gemm_kernel(const __grid
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
+            float2 rthr = make_float2(INFINITY, INFINITY);
+            int rank_cnt = 0;
+            if (EPI == kEpiRank && row0 + lane < p.m)
+                rthr = __ldg(reinterpret_cast<const float2*>(p.rank_thr) + row0 + lane);
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t raw[32];
                 // the accumulator buffers are kMaxBN columns apart: a 32-column read that starts inside the tile
@@ -449,23 +460,38 @@ __global__ void __launch_bounds__(threads_for(G), 1) tc_gemm_kernel(const __grid
                         else mbar_arrive(&acc_empty[acc]);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * kStagePitch + j] = __uint_as_float(raw[j]) * acc_scale;
-                __syncwarp();
                 const int col0 = nb * p.bn + c0;
-                if (EPI == kEpiGate) {
-                    float4 e_next[4];      // the next block's x_ent rows travel while this block is computed
-                    if (!last) gate_prefetch(p, al, row0, col0 + 32, col_end, lane, e_next);
-                    gate_block(p, al, st, row0, col0, col_end, lane, out_scale, e);
-                    if (!last) {
+                if (EPI == kEpiRank) {     // thread = head row: nothing to store, no transpose
+                    const int64_t row = row0 + lane;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) e[i] = e_next[i];
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(raw[j]) * acc_scale;
+                        const bool in = col0 + j < col_end;
+                        rank_cnt += (in && v > rthr.y) ? 1 : 0;
+                        if (in && v >= rthr.x && v <= rthr.y) {
+                            const int slot = atomicAdd(p.rank_band_cnt + row, 1);
+                            if (slot < p.rank_band_cap) p.rank_band[row * p.rank_band_cap + slot] = col0 + j;
+                        }
                     }
                 } else {
-                    epilogue_block<EPI>(p, al, st, row0, col0, col_end, lane, out_scale, lo, hi);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) st[lane * kStagePitch + j] = __uint_as_float(raw[j]) * acc_scale;
+                    __syncwarp();
+                    if (EPI == kEpiGate) {
+                        float4 e_next[4];      // the next block's x_ent rows travel while this block is computed
+                        if (!last) gate_prefetch(p, al, row0, col0 + 32, col_end, lane, e_next);
+                        gate_block(p, al, st, row0, col0, col_end, lane, out_scale, e);
+                        if (!last) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) e[i] = e_next[i];
+                        }
+                    } else {
+                        epilogue_block<EPI>(p, al, st, row0, col0, col_end, lane, out_scale, lo, hi);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
+            if (EPI == kEpiRank && rank_cnt > 0) atomicAdd(p.rank_above + row0 + lane, rank_cnt);
             if (c_begin >= c_end) {        // a group without columns in this launch still owes its arrival
                 tc_fence_before();
                 __syncwarp();
@@ -589,7 +615,7 @@ int launch_tc(TcParams& p, const lkg_planes* a, int64_t m, const lkg_planes* b, 
     p.n_segments = a->n_segments;
     LKG_REQUIRE(b->scale[0] != nullptr, "the B operand needs a scale record");
     p.mul_b = b->scale[0];
-    if (EPI == kEpiScore) {
+    if (EPI == kEpiScore || EPI == kEpiRank) {
         LKG_REQUIRE(a->scale[0] != nullptr, "the heads operand needs a scale record");
         p.mul_a = a->scale[0];
     }
@@ -920,6 +946,25 @@ extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_
     p.gz_out = gz_out;
     p.ld_gz = ld_gz;
     return launch_tc<kEpiGate>(p, x, m, w_pair, 2 * dim, (cudaStream_t)stream_);
+}
+
+extern "C" int lkg_score_rank(const lkg_planes* heads, int64_t n_heads, const lkg_planes* tails, int64_t n_tails,
+                              const float* thr, int32_t* above, int32_t* band_cnt, int32_t* band, int32_t band_cap,
+                              void* stream_) {
+    LKG_REQUIRE(n_heads >= 0 && n_tails >= 0 && n_tails < (1ll << 31), "bad rank shape");
+    if (n_heads == 0 || n_tails == 0) return LKG_OK;
+    LKG_REQUIRE(thr && above && band_cnt && band && band_cap > 0 && aligned16(thr) == aligned16(thr), "null argument");
+    LKG_REQUIRE((reinterpret_cast<uintptr_t>(thr) & 7u) == 0, "thr must be 8-byte aligned");
+    LKG_REQUIRE(heads && tails && heads->n_segments == 1 && tails->n_segments == 1 && heads->k[0] == tails->k[0],
+                "rank operands must be single-segment planes of equal width");
+    TcParams p{};
+    p.rank_thr = thr;
+    p.rank_above = above;
+    p.rank_band_cnt = band_cnt;
+    p.rank_band = band;
+    p.rank_band_cap = band_cap;
+    p.m_fastest = 1;    // all head tiles of one tail tile run together: the tails stream through L2 once
+    return launch_tc<kEpiRank>(p, heads, n_heads, tails, (int)n_tails, (cudaStream_t)stream_);
 }
 
 extern "C" int lkg_score(const lkg_planes* heads, int64_t n_heads, const lkg_planes* tails, int64_t n_tails,

@@ -524,6 +524,88 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
     }
 }
 
+// ---- rank of a given tail per head (north star (d): "top-k and rank epilogue") -----------------------------------
+// rank_i = #{ j : s_ij > s_it  or  (s_ij == s_it and j < t_i) } with s the EXACT scores (fp32 products summed in fp64,
+// one rounding -- the values the fused top-k returns) and t_i the position of head i's target in the tail list.
+//   1. lkg_rank_prepare   tau_i = exact score of (head i, target i); band tau_i -/+ E_i with E_i a bound of the
+//                         3-product fp16 hi/lo GEMM's error: representation 3 * 2^-22 |h||t| + fp32 accumulation of
+//                         48 MMAs <= 2^-22 |h||t| each -> 1.2e-5 |h||t|; kRankErr doubles it;
+//   2. lkg_score_rank     (gemm_tc.cu) the score GEMM with a counting epilogue: columns certainly above tau are counted,
+//                         the ones inside the band are listed; no score leaves the SM;
+//   3. lkg_rank_finalize  the listed columns re-scored exactly and compared with tau under the tie rule.
+constexpr float kRankErr = 2.5e-5f;
+
+__global__ void rank_prepare_kernel(const float* __restrict__ emb, int64_t ld, const int64_t* __restrict__ tail_rows,
+                                    const float* __restrict__ head_emb, int64_t ld_h,
+                                    const int64_t* __restrict__ head_rows, const int64_t* __restrict__ target_pos,
+                                    int n_heads, int dim, const float* __restrict__ tail_max_norm,
+                                    const float* __restrict__ rec, float* __restrict__ tau, float* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const int head = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (head >= n_heads) return;
+    const float* hrow = head_emb + (head_rows ? head_rows[head] : head) * ld_h;
+    const int64_t tp = target_pos[head];
+    const float* trow = emb + (tail_rows ? tail_rows[tp] : tp) * ld;
+    double acc = 0.0, nh = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+        const float a = __ldg(hrow + c), b = __ldg(trow + c);
+        acc = fma((double)a, (double)b, acc);
+        nh = fma((double)a, (double)a, nh);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(kFull, acc, o);
+        nh += __shfl_xor_sync(kFull, nh, o);
+    }
+    if (lane == 0) {
+        const float t = (float)acc;
+        const float e = kRankErr * (float)sqrt(nh) * (*tail_max_norm) * rec[2] * 1.0001f + 1e-30f;   // norms: scaled units
+        tau[head] = t;
+        thr[2 * head] = t - e - fabsf(t) * 2e-7f;
+        thr[2 * head + 1] = t + e + fabsf(t) * 2e-7f;
+    }
+}
+
+__global__ void __launch_bounds__(256) rank_finalize_kernel(const float* __restrict__ emb, int64_t ld,
+                                                            const int64_t* __restrict__ tail_rows,
+                                                            const float* __restrict__ head_emb, int64_t ld_h,
+                                                            const int64_t* __restrict__ head_rows,
+                                                            const int64_t* __restrict__ target_pos,
+                                                            const float* __restrict__ tau, const int* __restrict__ above,
+                                                            const int* __restrict__ band_cnt, const int* __restrict__ band,
+                                                            int cap, int n_tails, int dim, int64_t* __restrict__ ranks) {
+    __shared__ __align__(16) float s_head[kMaxChunks * kBK];
+    __shared__ int s_better[8];
+    const int head = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int grp = lane >> 3, q = lane & 7;
+    const float* hrow = head_emb + (head_rows ? head_rows[head] : head) * ld_h;
+    for (int i = threadIdx.x; i < kMaxChunks * kBK; i += blockDim.x) s_head[i] = i < dim ? __ldg(hrow + i) : 0.f;
+    __syncthreads();
+    const float t = tau[head];
+    const int64_t tp = target_pos[head];
+    const int n_band = band_cnt[head];
+    const bool overflow = n_band > cap;            // the band held more columns than the list: exact scan of every tail
+    const int n = overflow ? n_tails : n_band;
+    int better = 0;
+    for (int c0 = 4 * warp; c0 < n; c0 += 4 * nwarps) {
+        const int c = c0 + grp;
+        const bool live = c < n;
+        const int col = live ? (overflow ? c : band[(int64_t)head * cap + c]) : 0;
+        const float* trow = emb + (tail_rows ? tail_rows[col] : col) * ld;
+        const float s = exact_dot8(s_head, trow, dim, q, live);
+        if (live && q == 0 && (s > t || (s == t && col < tp))) ++better;
+    }
+    better = (int)warp_sum((float)better);          // < 2^24 per warp
+    if (lane == 0) s_better[warp] = better;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t tot = overflow ? 0 : above[head];
+        for (int w = 0; w < nwarps; ++w) tot += s_better[w];
+        ranks[head] = tot;
+    }
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -544,6 +626,39 @@ extern "C" int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows
     score_index_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, stream>>>(emb, ld, rows, m, dim, rec, (__half*)hi,
                                                                               ld_hi, norms, max_norm);
     LKG_LAUNCH_CHECK("score_index_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_rank_prepare(const float* emb, int64_t ld_emb, const int64_t* tail_rows, const float* head_emb,
+                                int64_t ld_head_emb, const int64_t* head_rows, const int64_t* target_pos, int64_t n_heads,
+                                int32_t dim, const float* tail_max_norm, const float* rec, float* tau, float* thr,
+                                void* stream_) {
+    LKG_REQUIRE(emb && head_emb && target_pos && tail_max_norm && rec && tau && thr && n_heads >= 0 && dim > 0,
+                "bad rank arguments");
+    if (n_heads == 0) return LKG_OK;
+    const int64_t blocks = (n_heads * 32 + 255) / 256;
+    rank_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(emb, ld_emb, tail_rows, head_emb, ld_head_emb,
+                                                                             head_rows, target_pos, (int)n_heads, dim,
+                                                                             tail_max_norm, rec, tau, thr);
+    LKG_LAUNCH_CHECK("rank_prepare_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_rank_finalize(const float* emb, int64_t ld_emb, const int64_t* tail_rows, const float* head_emb,
+                                 int64_t ld_head_emb, const int64_t* head_rows, const int64_t* target_pos,
+                                 const float* tau, const int32_t* above, const int32_t* band_cnt, const int32_t* band,
+                                 int32_t band_cap, int64_t n_heads, int64_t n_tails, int32_t dim, int64_t* ranks,
+                                 void* stream_) {
+    LKG_REQUIRE(emb && head_emb && target_pos && tau && above && band_cnt && band && ranks && band_cap > 0,
+                "bad rank arguments");
+    LKG_REQUIRE(dim >= 4 && dim % 4 == 0 && dim <= kMaxChunks * kBK && ld_emb % 4 == 0 && ld_head_emb % 4 == 0 &&
+                    aligned16(emb) && aligned16(head_emb) && n_tails < (1ll << 31),
+                "the rank path supports dim %% 4 == 0, dim <= %d, 16-byte aligned rows", kMaxChunks * kBK);
+    if (n_heads == 0) return LKG_OK;
+    rank_finalize_kernel<<<(unsigned)n_heads, 256, 0, (cudaStream_t)stream_>>>(emb, ld_emb, tail_rows, head_emb, ld_head_emb,
+                                                                               head_rows, target_pos, tau, above, band_cnt,
+                                                                               band, band_cap, (int)n_tails, dim, ranks);
+    LKG_LAUNCH_CHECK("rank_finalize_kernel");
     return LKG_OK;
 }
 

@@ -1079,10 +1079,14 @@ class LiteralKG(nn.Module):
             with torch.no_grad():
                 all_embed = self.gat_embeddings()
         n_tails = tail_index.m if tail_index is not None else len(tail_ids)
-        fused = target_tails is None and ops.fused_topk_applicable(n_tails, all_embed.shape[1], k)
-        if fused:
+        if ops.fused_topk_applicable(n_tails, all_embed.shape[1], k):
+            if tail_index is None:
+                tail_index = ops.ScoreIndex(all_embed, tail_ids)
             vals, pos = ops.score_topk(all_embed, head_ids, tail_ids, k, tail_index=tail_index)
-            return vals, pos, None
+            # ranks of the given target positions: the scoring GEMM again with a counting epilogue + exact re-score of
+            # the few columns inside the error band -- no B x Nt matrix either
+            ranks = None if target_tails is None else ops.score_rank(all_embed, head_ids, target_tails, tail_index)
+            return vals, pos, ranks
         scores = ops.score(all_embed, head_ids, tail_ids)
         return ops.topk_rows(scores, k, target_tails)
 

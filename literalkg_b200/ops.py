@@ -295,6 +295,50 @@ class ScoreIndex:
                                                    self.norms.data_ptr(), self.max_norm.data_ptr(), _lib.stream()))
 
 
+    def planes(self) -> _lib.Planes:
+        """fp16 hi/lo planes of the same rows under the same scale record (the 3-product operand of the rank GEMM);
+        built on first use, kept with the index."""
+        if getattr(self, "_planes", None) is None:
+            self._planes = split_planes(self.emb, self.rows, rec=self.rec)
+        return self._planes
+
+
+def score_rank(emb: torch.Tensor, heads: Optional[torch.Tensor], target_pos: torch.Tensor, tail_index: ScoreIndex,
+               head_emb: Optional[torch.Tensor] = None, band_cap: int = 2048) -> torch.Tensor:
+    """Rank (0 = best) of tail position ``target_pos[i]`` for head i among the tails of ``tail_index`` under "larger
+    exact score first, ties -> lower position", without the B x Nt score matrix (lkg_rank_prepare / lkg_score_rank /
+    lkg_rank_finalize).  ``heads`` index ``head_emb`` (default ``emb``), None = every row."""
+    ti = tail_index
+    hsrc = emb if head_emb is None else head_emb
+    assert hsrc.dtype == torch.float32 and hsrc.stride(1) == 1 and hsrc.shape[1] == emb.shape[1]
+    hrows = None if heads is None else heads.to(device=emb.device, dtype=torch.int64).contiguous()
+    hp = split_planes(hsrc, hrows, rec=ti.rec)
+    nh = hp.rows
+    tgt = target_pos.to(device=emb.device, dtype=torch.int64).contiguous()
+    assert tgt.numel() == nh
+    ranks = torch.empty(nh, dtype=torch.int64, device=emb.device)
+    if nh == 0:
+        return ranks
+    tp = ti.planes()
+    tau = torch.empty(nh, dtype=torch.float32, device=emb.device)
+    thr = torch.empty((nh, 2), dtype=torch.float32, device=emb.device)
+    counters = torch.zeros((2, nh), dtype=torch.int32, device=emb.device)
+    band = torch.empty((nh, band_cap), dtype=torch.int32, device=emb.device)
+    a, b = _lib.planes_operand([hp]), _lib.planes_operand([tp])
+    with _dev_guard(emb, "score_rank", 3):
+        lib = _lib.load()
+        _lib.check(lib.lkg_rank_prepare(emb.data_ptr(), emb.stride(0), _lib.ptr(ti.rows), hsrc.data_ptr(), hsrc.stride(0),
+                                        _lib.ptr(hrows), tgt.data_ptr(), nh, emb.shape[1], ti.max_norm.data_ptr(),
+                                        ti.rec.data_ptr(), tau.data_ptr(), thr.data_ptr(), _lib.stream()))
+        _lib.check(lib.lkg_score_rank(C.byref(a), nh, C.byref(b), ti.m, thr.data_ptr(), counters[0].data_ptr(),
+                                      counters[1].data_ptr(), band.data_ptr(), band_cap, _lib.stream()))
+        _lib.check(lib.lkg_rank_finalize(emb.data_ptr(), emb.stride(0), _lib.ptr(ti.rows), hsrc.data_ptr(), hsrc.stride(0),
+                                         _lib.ptr(hrows), tgt.data_ptr(), tau.data_ptr(), counters[0].data_ptr(),
+                                         counters[1].data_ptr(), band.data_ptr(), band_cap, nh, ti.m, emb.shape[1],
+                                         ranks.data_ptr(), _lib.stream()))
+    return ranks
+
+
 def fused_topk_applicable(n_tails: int, dim: int, k: int) -> bool:
     """The fused path needs enough 128-tail tiles to bound the k-th best score from tile maxima."""
     return (dim <= FUSED_TOPK_MAX_DIM and dim % 4 == 0 and n_tails >= max(FUSED_TOPK_MIN_TAILS, 512 * k)

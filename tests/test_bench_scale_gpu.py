@@ -183,3 +183,33 @@ def test_cfg3_layer1_on_sampled_rows(cfg3):
     floor = ((ref32.double() - ref64).abs().max() / ref64.abs().max()).item()
     print(f"cfg3 layer 1, {len(rows)} rows (max degree {deg[rows].max()}): CUDA vs fp64 {err:.2e}; fp32 torch vs fp64 {floor:.2e}")
     assert err < REL and err < max(4 * floor, 2e-5)
+
+
+def test_cfg4_rank_epilogue_bit_exact_at_1m_tails():
+    """Ranks of given positive tails for 2 048 heads against 1 M tails (the MRR / Hits@k evaluation of configs[3]):
+    bit exact against chunked float64 scoring, targets drawn from the top, the middle and the bottom of the ranking."""
+    from literalkg_b200 import ops
+    n, dim, nh = 1_000_000, 256, 2048
+    g = torch.Generator(device="cuda").manual_seed(77)
+    base = torch.randn(n, dim, generator=g, device="cuda") + 0.5 * torch.randn(1, dim, generator=g, device="cuda")
+    emb = torch.nn.functional.leaky_relu(base, 0.01) * 0.21
+    emb[1000:1016] = emb[17]
+    heads = (torch.arange(nh, device="cuda") * 487 + 7919) % n
+    target = torch.randint(0, n, (nh,), generator=g, device="cuda")
+    target[:4] = torch.tensor([17, 1000, 1015, 1003], device="cuda")
+    heads[:4] = 17
+    ti = ops.ScoreIndex(emb, None)
+    vals, pos = ops.score_topk(emb, heads[64:128], None, 10, tail_index=ti)
+    target[64:128] = pos[:, 3]                                     # known rank 3
+    got = ops.score_rank(emb, heads, target, ti)
+    e64 = emb.double()
+    ref = []
+    posn = torch.arange(n, device="cuda").unsqueeze(0)
+    for i in range(0, nh, 64):
+        s = (e64[heads[i:i + 64]] @ e64.t()).float()
+        tp = target[i:i + 64].unsqueeze(1)
+        tgt = torch.gather(s, 1, tp)
+        ref.append(((s > tgt) | ((s == tgt) & (posn < tp))).sum(1))
+    ref = torch.cat(ref)
+    assert torch.equal(got, ref)
+    assert torch.equal(got[64:128], torch.full((64,), 3, dtype=torch.int64, device="cuda"))

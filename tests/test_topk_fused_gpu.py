@@ -108,3 +108,69 @@ def test_fused_topk_vs_generic_path_and_model_api():
     assert ((v - gv).abs().max() / gv.abs().max()).item() < 1e-5
     rv, rp = ref_topk(emb, heads, tails, 10)
     assert torch.equal(p, rp) and torch.equal(v, rv)
+
+
+# ---- rank epilogue: lkg_rank_prepare / lkg_score_rank / lkg_rank_finalize ---------------------------------------
+def ref_ranks(emb, heads, tails, target_pos, chunk=128):
+    """O.rank_of's rule on the exact scores (fp64 dot products rounded once to fp32), chunked over the heads."""
+    e64 = emb.double()
+    t64 = e64 if tails is None else e64[tails]
+    pos = torch.arange(t64.shape[0], device=emb.device).unsqueeze(0)
+    out = []
+    for i in range(0, heads.numel(), chunk):
+        s = (e64[heads[i:i + chunk]] @ t64.t()).float()
+        tp = target_pos[i:i + chunk].unsqueeze(1)
+        tgt = torch.gather(s, 1, tp)
+        out.append(((s > tgt) | ((s == tgt) & (pos < tp))).sum(1))
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("n,dim,nh", [(40_000, 256, 300), (70_001, 256, 129), (25_000, 200, 513), (9_000, 64, 77)])
+def test_rank_epilogue_bit_exact(n, dim, nh):
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n + nh)
+    emb = torch.nn.functional.leaky_relu(torch.randn(n, dim, generator=g, device="cuda"), 0.01) * 0.37
+    emb[500:520] = emb[7]                                           # exact ties: resolved by position
+    heads = torch.randint(0, n, (nh,), generator=g, device="cuda")
+    heads[:4] = torch.tensor([7, 505, 7, 519], device="cuda")
+    tails = torch.randperm(n, generator=g, device="cuda")[: n - 5]
+    target = torch.randint(0, n - 5, (nh,), generator=g, device="cuda")
+    where = {int(t): i for i, t in enumerate(tails.tolist())} if n < 10_000 else None
+    if where is not None:                                           # make some targets members of the tie group
+        target[0], target[1] = where[505], where[7]
+    ti = ops.ScoreIndex(emb, tails)
+    got = ops.score_rank(emb, heads, target, ti)
+    assert torch.equal(got, ref_ranks(emb, heads, tails, target))
+    # identity tail list; the best and the worst tail of every head get ranks 0 and n - 1
+    ti2 = ops.ScoreIndex(emb, None)
+    s = (emb[heads[:16]].double() @ emb.double().t()).float()
+    best = torch.sort(s, dim=1, descending=True, stable=True).indices
+    assert torch.equal(ops.score_rank(emb, heads[:16], best[:, 0], ti2), torch.zeros(16, dtype=torch.int64, device="cuda"))
+    # a tiny band capacity forces the overflow path (exact scan): same answer
+    got3 = ops.score_rank(emb, heads[:32], target[:32], ti, band_cap=1)
+    assert torch.equal(got3, got[:32])
+
+
+def test_model_topk_returns_ranks_without_score_matrix():
+    """LiteralKG.topk(target_tails=...) on a large candidate set goes through the fused kernels for values, positions
+    AND ranks; identical to the dense path (score matrix + lkg_topk_rows) on the same embeddings."""
+    import argparse
+    import literalkg_b200 as L
+    import literalkg_oracle as O
+    from literalkg_b200 import ops
+    cfg = O.OracleConfig(n_conv_layers=1, mess_dropout=0.0)
+    n = 30_000
+    kg = L.synthetic.make_kg(n, 120_000, 4, seed=1, max_out_degree=100)
+    num, txt = L.synthetic.make_literals(n, seed=1)
+    args = argparse.Namespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+    kt = L.KGTensors(kg.h, kg.t, kg.r, n_entities=n)
+    torch.manual_seed(0)
+    m = L.LiteralKG(args, n, 4, kt.A_in, num, txt).cuda().eval()
+    heads = torch.arange(0, 200, device="cuda") * 37 % n
+    tails = torch.arange(n, device="cuda")
+    target = (heads * 11 + 3) % n
+    vals, pos, ranks = m.topk(heads, tails, 10, target_tails=target)
+    emb = m.gat_embeddings()
+    assert torch.equal(ranks, ref_ranks(emb, heads, None, target))
+    rv, rp = ref_topk(emb, heads, tails, 10)
+    assert torch.equal(pos, rp) and torch.equal(vals, rv)
