@@ -359,6 +359,12 @@ int lkg_topk_rows(const float* scores, int64_t ld_scores, int64_t n_rows, int64_
                   int64_t* ranks_out, void* stream);
 
 
+/* k-way merge of `parts` per-rank survivor lists (sharded scoring): vals / ids [parts][n_rows][k], ids = global tail
+ * positions (-1 = padding), every list ordered (score desc, position asc); parts * k <= 1024.  Output: the k best per
+ * row under the same order. */
+int lkg_topk_merge(const float* vals, const int64_t* ids, int32_t parts, int64_t n_rows, int32_t k, float* top_values,
+                   int64_t* top_ids, void* stream);
+
 /* ---- fused all-entity scoring + top-k: the B x Nt score matrix is never materialised --------------
  * Index of a set of embedding rows (heads of a batch, or the candidate tails): the scaled fp16 "hi" plane
  * [m, ld_hi] the filter GEMM reads, the rows' norms (scaled units) and their maximum (device scalar, reset by

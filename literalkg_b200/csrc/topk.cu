@@ -162,10 +162,66 @@ topk_rows_kernel(const float* __restrict__ scores, int64_t ld, int64_t n_cols, i
     }
 }
 
+// ---- k-way merge of per-rank survivor lists (sharded scoring) ---------------------------------------
+// vals / ids [parts][n_rows][k]: every rank's k best (score, global tail position) per head, -inf / -1 padded.  One warp
+// per head sorts the parts * k <= 1024 keys (score desc, position asc) in shared memory and writes the first k.
+constexpr int kMergeMax = 1024;
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ ids,
+                                                         int parts, int64_t n_rows, int k, float* __restrict__ top_val,
+                                                         int64_t* __restrict__ top_id) {
+    __shared__ unsigned long long keys[kMergeMax];
+    const int64_t row = blockIdx.x;
+    const int w = parts * k;
+    int p2 = 1;
+    while (p2 < w) p2 <<= 1;
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < w) {
+            const int part = i / k, j = i - part * k;
+            const int64_t src = ((int64_t)part * n_rows + row) * k + j;
+            const int64_t id = ids[src];
+            if (id >= 0) key = ((unsigned long long)enc(vals[src]) << 32) | (uint32_t)(~(uint32_t)id);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= p2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long a = keys[i], b = keys[j];
+                    if ((a < b) == desc) {
+                        keys[i] = b;
+                        keys[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const unsigned long long key = i < p2 ? keys[i] : 0ull;
+        const bool ok = key != 0ull;
+        top_val[row * k + i] = ok ? dec((uint32_t)(key >> 32)) : -INFINITY;
+        top_id[row * k + i] = ok ? (int64_t)(~(uint32_t)(key & 0xffffffffu)) : -1;
+    }
+}
+
 }  // namespace
 }  // namespace lkg
 
 using namespace lkg;
+
+extern "C" int lkg_topk_merge(const float* vals, const int64_t* ids, int32_t parts, int64_t n_rows, int32_t k,
+                              float* top_values, int64_t* top_ids, void* stream_) {
+    LKG_REQUIRE(vals && ids && top_values && top_ids && parts >= 1 && k >= 1 && n_rows >= 0, "bad merge arguments");
+    LKG_REQUIRE((int64_t)parts * k <= kMergeMax, "parts * k must be <= %d (got %d x %d)", kMergeMax, parts, k);
+    if (n_rows == 0) return LKG_OK;
+    topk_merge_kernel<<<(unsigned)n_rows, 128, 0, (cudaStream_t)stream_>>>(vals, ids, parts, n_rows, k, top_values, top_ids);
+    LKG_LAUNCH_CHECK("topk_merge_kernel");
+    return LKG_OK;
+}
 
 extern "C" int lkg_topk_rows(const float* scores, int64_t ld_scores, int64_t n_rows, int64_t n_cols, int32_t k,
                              float* top_values, int64_t* top_cols, const int64_t* target_cols,

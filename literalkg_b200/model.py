@@ -1109,23 +1109,25 @@ class LiteralKG(nn.Module):
         part.all_reduce(hmat)
         if tail_index is None:
             tail_index = self.sharded_index(local_embed)
-        fused = ops.fused_topk_applicable(tail_index.m, local_embed.shape[1], k)
-        vals_l, ids_l, off = [], [], 0
-        for nb in sizes:
-            hm = hmat[off:off + nb]
-            off += nb
-            if fused:
-                vals, pos = ops.score_topk(local_embed, None, None, k, tail_index=tail_index, head_emb=hm)
-            else:
-                both = torch.cat([local_embed, hm])
-                scores = ops.score(both, torch.arange(nb, device=dev) + local_embed.shape[0],
-                                   torch.arange(local_embed.shape[0], device=dev), rec=tail_index.rec)
-                vals, pos, _ = ops.topk_rows(scores, k)
-            vals_l.append(vals)
-            ids_l.append(torch.where(pos >= 0, pos + part.begin, pos))
-        from .parallel import merge_topk
-        top_v, top_i = merge_topk(part.all_gather_stack(torch.cat(vals_l)), part.all_gather_stack(torch.cat(ids_l)), k,
-                                  lambda sc, kk: ops.topk_rows(sc, kk)[:2])
+        # every head of every batch in ONE scoring call (the per-call sampling / threshold / finalize launches and the
+        # resident head blocks are amortised over all of them), then one exchange of the survivors and one merge
+        if ops.fused_topk_applicable(tail_index.m, local_embed.shape[1], k):
+            vals, pos = ops.score_topk(local_embed, None, None, k, tail_index=tail_index, head_emb=hmat)
+        else:               # small shards: score matrix + row top-k, 2 048 heads at a time
+            both = torch.cat([local_embed, hmat])
+            tails_all = torch.arange(local_embed.shape[0], device=dev)
+            chunks = []
+            for c0 in range(0, hmat.shape[0], 2048):
+                rows = torch.arange(c0, min(c0 + 2048, hmat.shape[0]), device=dev) + local_embed.shape[0]
+                chunks.append(ops.topk_rows(ops.score(both, rows, tails_all, rec=tail_index.rec), k)[:2])
+            vals, pos = torch.cat([c[0] for c in chunks]), torch.cat([c[1] for c in chunks])
+        ids = torch.where(pos >= 0, pos + part.begin, pos)
+        all_v, all_i = part.all_gather_stack(vals), part.all_gather_stack(ids)
+        if part.world * k <= 1024:
+            top_v, top_i = ops.topk_merge(all_v, all_i, k)
+        else:
+            from .parallel import merge_topk
+            top_v, top_i = merge_topk(all_v, all_i, k, lambda sc, kk: ops.topk_rows(sc, kk)[:2])
         if not many:
             return top_v, top_i
         return list(zip(torch.split(top_v, sizes), torch.split(top_i, sizes)))

@@ -269,6 +269,19 @@ def topk_rows(scores: torch.Tensor, k: int, target_cols: Optional[torch.Tensor] 
     return vals, idx, ranks
 
 
+def topk_merge(vals: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """vals / ids [parts, B, k] (per-rank survivors, ids = global positions, -1 pads) -> the k best per row."""
+    parts, b, kk = vals.shape
+    assert kk == k and ids.shape == vals.shape and vals.dtype == torch.float32 and ids.dtype == torch.int64
+    vals, ids = vals.contiguous(), ids.contiguous()
+    top_v = torch.empty((b, k), dtype=torch.float32, device=vals.device)
+    top_i = torch.empty((b, k), dtype=torch.int64, device=vals.device)
+    with _dev_guard(vals, "topk_merge"):
+        _lib.check(_lib.load().lkg_topk_merge(vals.data_ptr(), ids.data_ptr(), parts, b, k, top_v.data_ptr(),
+                                              top_i.data_ptr(), _lib.stream()))
+    return top_v, top_i
+
+
 # ---- fused all-entity scoring + top-k ---------------------------------------------------------------------
 FUSED_TOPK_MIN_TAILS = 16384      # below this the score matrix is small: score() + topk_rows()
 FUSED_TOPK_MAX_DIM = 256

@@ -199,6 +199,10 @@ class PeerTable:
         self.t = symm_mem.empty((self.slots, self.rows, self.d), dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.t, group)
         self.stream = torch.cuda.Stream(device=device)
+        # large row blocks go out on several streams at once: one device-to-device copy keeps ONE copy engine busy,
+        # well below what the 18 NVLinks of the GPU carry; small blocks are launch-latency bound and stay on one stream
+        n_copy = min(4, max(1, part.world - 1)) if self.rows * self.d * 4 >= (64 << 20) else 1
+        self.copy_streams = [self.stream] + [torch.cuda.Stream(device=device) for _ in range(n_copy - 1)]
         self.calls = 0
 
     def begin(self):
@@ -217,18 +221,29 @@ class _PeerHandle:
     def start(self):
         o, part = self.owner, self.owner.part
         main = torch.cuda.current_stream()
-        o.stream.wait_stream(main)                      # the rows are written, earlier readers of the slot are queued
-        with torch.cuda.stream(o.stream):
-            b, e = part.begin, part.end
-            if e > b:
-                rows = o.t[self.slot, b:e]
-                off = (self.slot * o.rows + b) * o.d
-                for step in range(1, part.world):       # staggered destinations: no two ranks start on the same peer
-                    r = (part.rank + step) % part.world
+        for cs in o.copy_streams:
+            cs.wait_stream(main)                        # the rows are written, earlier readers of the slot are queued
+        from . import ops
+        timed = ops.PROFILE is not None and ops.PROFILE.only is None
+        if timed:                                       # bench.py's per-call breakdown: transfer + barrier time
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(o.stream)
+        b, e = part.begin, part.end
+        if e > b:
+            rows = o.t[self.slot, b:e]
+            off = (self.slot * o.rows + b) * o.d
+            for step in range(1, part.world):           # staggered destinations: no two ranks start on the same peer
+                r = (part.rank + step) % part.world
+                with torch.cuda.stream(o.copy_streams[step % len(o.copy_streams)]):
                     o.hdl.get_buffer(r, (e - b, o.d), torch.float32, off).copy_(rows, non_blocking=True)
+        for cs in o.copy_streams[1:]:
+            o.stream.wait_stream(cs)
+        with torch.cuda.stream(o.stream):
             o.hdl.barrier()                             # stream ordered: every rank's pushes have landed
-            self.done = torch.cuda.Event()
+            self.done = torch.cuda.Event(enable_timing=timed)
             self.done.record(o.stream)
+        if timed:
+            ops.PROFILE.events.append((f"peer_push_{o.rows * o.d * 4 / 1e6:.0f}MB", t0, self.done))
         return self
 
     def wait(self):
