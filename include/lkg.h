@@ -103,6 +103,7 @@ typedef struct {
 typedef enum {
     LKG_ACT_NONE = 0,
     LKG_ACT_LEAKY_RELU = 1,
+    LKG_ACT_TANH = 2,
     LKG_ACT_ACCUMULATE = 256 /* flag, OR-ed in: out += act(result) (gradient accumulation of the backward pass) */
 } lkg_activation;
 typedef enum { LKG_AGG_GCN = 0, LKG_AGG_GRAPHSAGE = 1, LKG_AGG_BI_INTERACTION = 2 } lkg_aggregator;
@@ -153,6 +154,21 @@ int lkg_attn_workspace_bytes(int32_t n_relations, int32_t dim, size_t* bytes /*h
 int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t ld_entity,
                     const float* relation, int64_t ld_relation, int32_t dim,
                     float* values, void* workspace, void* stream);
+
+/* ---- relation-projected attention (north star (b); the formula the reference keeps commented out, model.py:436-439):
+ *      v(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r).  Because the tanh factor only depends on (h, r), v = e_t . u_{h,r}
+ *      with u_{h,r} = W_r tanh(W_r^T e_h + e_r): the two projections run once per (head, relation) RUN of the att
+ *      order, bucketed by relation, as two chained tensor-core GEMMs (lkg_split_planes with the run heads as row
+ *      gather -> lkg_linear_fwd with LKG_ACT_TANH writing planes -> lkg_linear_fwd), and the per-triple work is the
+ *      same 1 200-byte tail-row gather as lkg_attn_update:
+ *   lkg_attn_run_logits  logits[e] = entity[att_tail[e]] . run_w[run_slot[run]] for every triple e of every run
+ *                        (run_ptr [n_runs + 1]: the runs' triple ranges in att order; run_w [n_runs, dim] fp32);
+ *   lkg_row_softmax      in-place max-subtracted softmax of values[rowptr[i] : rowptr[i + 1]] for every row (after the
+ *                        duplicate (h,t) logits were summed with lkg_segment_scatter_add). */
+int lkg_attn_run_logits(const int32_t* run_ptr, const int32_t* run_slot, int64_t n_runs, const int32_t* att_tail,
+                        const float* entity, int64_t ld_entity, int32_t dim, const float* run_w, int64_t ld_w,
+                        float* logits, void* stream);
+int lkg_row_softmax(const int32_t* rowptr, int64_t n_rows, float* values, void* stream);
 
 /* ---- dense: C[M,N] = epilogue(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores, three fp16 products per
  *      k-step (hi*hi + lo*hi + hi*lo) accumulated in fp32 TMEM (torch Linear layout: B is [out, in]) ---- */

@@ -15,7 +15,7 @@ LKG_MAX_SEGMENTS = 4
 LKG_SCALE_FLOATS = 8
 ABI_VERSION = 5
 SOLO_DEGREE, SEG_DEGREE, MAX_SEGS, SEG_STRIDE = 256, 512, 8, 576
-ACT_NONE, ACT_LEAKY_RELU, ACT_ACCUMULATE = 0, 1, 256
+ACT_NONE, ACT_LEAKY_RELU, ACT_TANH, ACT_ACCUMULATE = 0, 1, 2, 256
 
 i32, i64, f32p, vp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 
@@ -46,6 +46,8 @@ SIGNATURES = {
     "lkg_laplacian_init": (C.c_int, [C.POINTER(LkgGraph), C.c_int, vp, vp, vp]),
     "lkg_attn_workspace_bytes": (C.c_int, [i32, i32, C.POINTER(C.c_size_t)]),
     "lkg_attn_update": (C.c_int, [C.POINTER(LkgGraph), vp, i64, vp, i64, i32, vp, vp, vp]),
+    "lkg_attn_run_logits": (C.c_int, [vp, vp, i64, vp, vp, i64, i32, vp, i64, vp, vp]),
+    "lkg_row_softmax": (C.c_int, [vp, i64, vp, vp]),
     "lkg_scale_from_data": (C.c_int, [vp, i64, vp, i64, i32, C.c_float, vp, vp]),
     "lkg_scale_from_bound": (C.c_int, [C.c_float, vp, vp, vp]),
     "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, vp, i64, i64, vp]),

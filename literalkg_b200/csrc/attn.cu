@@ -293,6 +293,80 @@ attn_update_kernel(lkg_graph g, const float* __restrict__ ent, int64_t ld_ent,
     }
 }
 
+// ---- relation-projected attention: logits per (head, relation) run -------------------------------------------------
+// One warp per run: its weight vector u (run_w row, coalesced) stays in registers, the run's tail rows are gathered with
+// streaming 128-bit loads (4 rows in flight), one warp reduction per triple.
+template <int S>
+__global__ void __launch_bounds__(256) attn_run_logits_kernel(const int* __restrict__ run_ptr,
+                                                              const int* __restrict__ run_slot, int64_t n_runs,
+                                                              const int* __restrict__ att_tail,
+                                                              const float* __restrict__ ent, int64_t ld_ent, int nvec,
+                                                              const float* __restrict__ run_w, int64_t ld_w,
+                                                              float* __restrict__ logits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t run = warp; run < n_runs; run += nwarps) {
+        const int e0 = __ldg(run_ptr + run), e1 = __ldg(run_ptr + run + 1);
+        const float4* wrow = reinterpret_cast<const float4*>(run_w + (int64_t)__ldg(run_slot + run) * ld_w);
+        float4 w[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int v = lane + 32 * s;
+            w[s] = v < nvec ? __ldg(wrow + v) : make_float4(0, 0, 0, 0);
+        }
+        for (int c0 = e0; c0 < e1; c0 += 4) {
+            float4 t[4][S];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool live = c0 + j < e1;
+                const float* trow = ent + (int64_t)(live ? __ldg(att_tail + c0 + j) : 0) * ld_ent;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const int v = lane + 32 * s;
+                    t[j][s] = (live && v < nvec) ? ldg_stream4(trow + 4 * v) : make_float4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float p = 0.f;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    p = fmaf(t[j][s].x, w[s].x, p);
+                    p = fmaf(t[j][s].y, w[s].y, p);
+                    p = fmaf(t[j][s].z, w[s].z, p);
+                    p = fmaf(t[j][s].w, w[s].w, p);
+                }
+                p = warp_sum(p);
+                if (lane == 0 && c0 + j < e1) logits[c0 + j] = p;
+            }
+        }
+    }
+}
+
+// in-place softmax of every CSR row: one warp per row, three passes over the row's slots
+__global__ void __launch_bounds__(256) row_softmax_kernel(const int* __restrict__ rowptr, int64_t n_rows,
+                                                          float* __restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n_rows; row += nwarps) {
+        const int u0 = __ldg(rowptr + row), u1 = __ldg(rowptr + row + 1);
+        float m = -INFINITY;
+        for (int i = u0 + lane; i < u1; i += 32) m = fmaxf(m, val[i]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int i = u0 + lane; i < u1; i += 32) {
+            const float ex = __expf(val[i] - m);
+            val[i] = ex;
+            sum += ex;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        for (int i = u0 + lane; i < u1; i += 32) val[i] *= inv;
+    }
+}
+
 inline size_t attn_smem_bytes(int nvec, int ring) {
     return (size_t)kWarps * ring * nvec * 16 + kWarps * ring * 8 + kWarps * kSegCap * 4;
 }
@@ -357,5 +431,44 @@ extern "C" int lkg_attn_update(const lkg_graph* g, const float* entity, int64_t 
     }
     if (rc) return rc;
     LKG_LAUNCH_CHECK("attn_update_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_attn_run_logits(const int32_t* run_ptr, const int32_t* run_slot, int64_t n_runs, const int32_t* att_tail,
+                                   const float* entity, int64_t ld_entity, int32_t dim, const float* run_w, int64_t ld_w,
+                                   float* logits, void* stream_) {
+    LKG_REQUIRE(run_ptr && run_slot && att_tail && entity && run_w && logits && n_runs >= 0, "null argument");
+    LKG_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512 && ld_entity % 4 == 0 && ld_w % 4 == 0 && aligned16(entity) &&
+                    aligned16(run_w), "projected attention needs dim %% 4 == 0, dim <= 512, 16-byte aligned rows");
+    if (n_runs == 0) return LKG_OK;
+    const int nvec = dim / 4;
+    int64_t blocks = (n_runs * 32 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nvec <= 32)
+        attn_run_logits_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(run_ptr, run_slot, n_runs, att_tail, entity, ld_entity,
+                                                                        nvec, run_w, ld_w, logits);
+    else if (nvec <= 64)
+        attn_run_logits_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(run_ptr, run_slot, n_runs, att_tail, entity, ld_entity,
+                                                                        nvec, run_w, ld_w, logits);
+    else if (nvec <= 96)
+        attn_run_logits_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(run_ptr, run_slot, n_runs, att_tail, entity, ld_entity,
+                                                                        nvec, run_w, ld_w, logits);
+    else
+        attn_run_logits_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(run_ptr, run_slot, n_runs, att_tail, entity, ld_entity,
+                                                                        nvec, run_w, ld_w, logits);
+    LKG_LAUNCH_CHECK("attn_run_logits_kernel");
+    return LKG_OK;
+}
+
+extern "C" int lkg_row_softmax(const int32_t* rowptr, int64_t n_rows, float* values, void* stream_) {
+    LKG_REQUIRE(rowptr && values && n_rows >= 0, "null argument");
+    if (n_rows == 0) return LKG_OK;
+    int64_t blocks = (n_rows * 32 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    row_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(rowptr, n_rows, values);
+    LKG_LAUNCH_CHECK("row_softmax_kernel");
     return LKG_OK;
 }

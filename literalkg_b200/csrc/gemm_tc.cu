@@ -184,6 +184,8 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, const EpiAlign
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             if (p.act == LKG_ACT_LEAKY_RELU) {
                 v.x = leaky(v.x); v.y = leaky(v.y); v.z = leaky(v.z); v.w = leaky(v.w);
+            } else if (p.act == LKG_ACT_TANH) {
+                v.x = tanh_acc(v.x); v.y = tanh_acc(v.y); v.z = tanh_acc(v.z); v.w = tanh_acc(v.w);
             }
             if (p.accumulate) {
                 v.x += old[it].x; v.y += old[it].y; v.z += old[it].z; v.w += old[it].w;

@@ -208,6 +208,32 @@ class GraphPlan:
             self._transposed = tuple(x[:self.nnz] for x in (t_tail, t_head, t_perm))
         return self._transposed
 
+    def runs(self):
+        """The (head, relation) RUNS of the att order (triples sorted by (h, r, t)): what the relation-projected
+        attention projects once each.  -> dict(run_ptr int32 [n_runs + 1], run_head int64 [n_runs], run_rel int64
+        [n_runs], order int64 [n_runs] = run ids bucketed by relation (stable), run_slot int32 [n_runs] = position of
+        a run in that bucket order, offsets = host list [R + 1] of the buckets).  Built on first use (integer
+        bookkeeping with torch ops on the device, one read-back of R + 1 counts), cached with the plan."""
+        if getattr(self, "_runs", None) is None:
+            dev, e = self.device, self.n_edges
+            counts = (self.att_rowptr[1:] - self.att_rowptr[:-1]).long()
+            heads = torch.repeat_interleave(torch.arange(self.n_entities, device=dev), counts)
+            rel = self.att_rel.long()
+            new = torch.ones(e, dtype=torch.bool, device=dev)
+            if e > 1:
+                new[1:] = (heads[1:] != heads[:-1]) | (rel[1:] != rel[:-1])
+            start = torch.nonzero(new).reshape(-1)
+            n_runs = int(start.numel())
+            run_ptr = torch.cat([start, torch.tensor([e], device=dev)]).to(torch.int32)
+            run_head, run_rel = heads[start], rel[start]
+            order = torch.sort(run_rel, stable=True).indices
+            run_slot = torch.empty(n_runs, dtype=torch.int32, device=dev)
+            run_slot[order] = torch.arange(n_runs, dtype=torch.int32, device=dev)
+            offsets = [0] + torch.cumsum(torch.bincount(run_rel, minlength=self.n_relations), 0).tolist()
+            self._runs = dict(run_ptr=run_ptr, run_head=run_head, run_rel=run_rel, order=order, run_slot=run_slot,
+                              offsets=offsets, n_runs=n_runs)
+        return self._runs
+
     def attn_workspace(self, dim: int) -> int:
         """Workspace of lkg_attn_update: row counter + the exp(2 e_r) table."""
         nbytes = C.c_size_t(0)

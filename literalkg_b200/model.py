@@ -978,6 +978,19 @@ class LiteralKG(nn.Module):
     # ---- attention update ------------------------------------------------------------------------
     def update_attention(self, h_list, t_list, r_list, relations):
         """model.py:444-471.  Entirely on device: no host round trip, no per-relation Python loop."""
+        plan = self._edge_plan(h_list, t_list, r_list, relations)
+        return self._apply_attention(plan, None)
+
+    def update_attention_projected(self, h_list, t_list, r_list, relations, w_rel):
+        """Extension (BASELINE.json north star (b)): the relation-PROJECTED attention the reference keeps commented
+        out (model.py:436-439), v = (e_t W_r) . tanh(e_h W_r + e_r) with an explicit ``w_rel`` [R, embed_dim,
+        relation_dim]; same duplicate merge, row softmax and ``A_in`` side effect as ``update_att``."""
+        if self._part is not None and self._part.world > 1:
+            raise NotImplementedError("the projected attention extension runs on one GPU")
+        plan = self._edge_plan(h_list, t_list, r_list, relations)
+        return self._apply_attention(plan, w_rel)
+
+    def _edge_plan(self, h_list, t_list, r_list, relations) -> GraphPlan:
         dev = self._param_device()
         # the CSR plan only depends on the edge list.  The very same tensors (address, length, in-place version) as
         # last time need no look at all; otherwise an unchanged list is recognised by content (one small kernel + a
@@ -994,10 +1007,16 @@ class LiteralKG(nn.Module):
                 self._att_key = key
             self._att_ident = ident
             self._att_refs = (h_list, t_list, r_list)   # keeps the addresses from being reused by other tensors
-        plan = self._att_plan
+        return self._att_plan
+
+    def _apply_attention(self, plan: GraphPlan, w_rel) -> None:
+        dev = self._param_device()
         part = self._part if (self._part is not None and self._part.world > 1) else None
         with torch.no_grad():
-            if part is None:
+            if w_rel is not None:
+                values = ops.attn_update_projected(plan, self.entity_embed.weight.detach(),
+                                                   self.relation_embed.weight.detach(), w_rel.detach().to(dev))
+            elif part is None:
                 values = ops.attn_update(plan, self.entity_embed.weight.detach(), self.relation_embed.weight.detach())
             else:   # rows are independent: every rank fills the values of its own head rows
                 if self.prefetch_gate:
@@ -1183,6 +1202,8 @@ class LiteralKG(nn.Module):
             return self.calc_triplet_loss(*input)
         if mode == 'update_att':
             return self.update_attention(*input)
+        if mode == 'update_att_projected':               # extension, see update_attention_projected
+            return self.update_attention_projected(*input)
         if mode == 'predict':
             return self.predict_links(*input)
         if mode == 'mlp':

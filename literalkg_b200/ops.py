@@ -75,6 +75,46 @@ def attn_update(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor,
     return out
 
 
+def attn_update_projected(plan: GraphPlan, entity: torch.Tensor, relation: torch.Tensor, w_rel: torch.Tensor,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A_in values of the relation-PROJECTED attention (north star (b); the formula commented out at model.py:436-439):
+    v(h,r,t) = (e_t W_r) . tanh(e_h W_r + e_r), duplicate (h,t) logits summed, row softmax.  ``w_rel`` [R, D, D_rel].
+    v = e_t . u_{h,r} with u_{h,r} = W_r tanh(W_r^T e_h + e_r): two chained tensor-core GEMMs per relation bucket over
+    the (head, relation) runs of the plan, then one gather + dot per triple (csrc/attn.cu)."""
+    entity, relation, w_rel = _lib.f32c(entity), _lib.f32c(relation), _lib.f32c(w_rel)
+    n_rel, d, d_rel = w_rel.shape
+    if entity.shape[1] != d or relation.shape[1] != d_rel or relation.shape[0] != n_rel:
+        raise ValueError("w_rel must be [n_relations, embed_dim, relation_dim]")
+    dev = entity.device
+    runs = plan.runs()
+    n_runs = runs["n_runs"]
+    u_all = torch.empty((max(n_runs, 1), d), dtype=torch.float32, device=dev)        # bucket order
+    unit = scale_from_bound(1.0, dev)
+    for r in range(n_rel):
+        lo, hi = runs["offsets"][r], runs["offsets"][r + 1]
+        if hi == lo:
+            continue
+        heads = runs["run_head"][runs["order"][lo:hi]]
+        hp = split_planes(entity, heads)                                              # gathered head rows as planes
+        q = _lib.Planes(hi - lo, d_rel, dev, rec=unit)                                # |tanh| <= 1
+        linear([hp], w_rel[r].t().contiguous(), relation[r], _lib.ACT_TANH, out_planes=q)      # tanh(e_h W_r + e_r)
+        linear([q], w_rel[r].contiguous(), None, _lib.ACT_NONE, out=u_all[lo:hi])     # u = W_r q
+    logits = torch.empty(max(plan.n_edges, 1), dtype=torch.float32, device=dev)
+    with _dev_guard(entity, "attn_run_logits"):
+        _lib.check(_lib.load().lkg_attn_run_logits(runs["run_ptr"].data_ptr(), runs["run_slot"].data_ptr(), n_runs,
+                                                   plan.att_tail.data_ptr(), entity.data_ptr(), entity.stride(0), d,
+                                                   u_all.data_ptr(), u_all.stride(0), logits.data_ptr(), _lib.stream()))
+    if out is None:
+        out = torch.empty(max(plan.nnz, 1), dtype=torch.float32, device=dev)[:plan.nnz]
+    seg = (plan.att_seg & 0x7fffffff).contiguous()
+    with _dev_guard(entity, "attn_merge_softmax", 2):
+        lib = _lib.load()
+        _lib.check(lib.lkg_segment_scatter_add(logits.data_ptr(), seg.data_ptr(), plan.n_edges, out.data_ptr(), plan.nnz,
+                                               _lib.stream()))
+        _lib.check(lib.lkg_row_softmax(plan.rowptr.data_ptr(), plan.n_entities, out.data_ptr(), _lib.stream()))
+    return out
+
+
 def scale_from_data(src: torch.Tensor, rows: Optional[torch.Tensor] = None, floor: float = 0.0,
                     rec: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Device scale record (float[8]) of max(|src[rows]|, floor); no host sync."""

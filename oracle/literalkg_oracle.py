@@ -307,6 +307,25 @@ def update_attention(ent_w, rel_w, h, t, r, relations: Iterable[int], n: int):
     return a.indices(), a.values()
 
 
+def update_attention_projected(ent_w, rel_w, w_rel, h, t, r, relations: Iterable[int], n: int):
+    """The relation-projected attention the reference keeps commented out (model.py:436-439), with the rest of
+    update_attention (model.py:444-471) unchanged:  r_mul_h = h_embed @ W_r;  r_mul_t = t_embed @ W_r;
+    v = sum(r_mul_t * tanh(r_mul_h + r_embed), dim=1).  ``w_rel`` [R, embed_dim, relation_dim]."""
+    rows, cols, vals = [], [], []
+    for rel in relations:
+        sel = torch.where(r == rel)
+        bh, bt = h[sel], t[sel]
+        rows.append(bh)
+        cols.append(bt)
+        r_mul_h = ent_w[bh] @ w_rel[rel]
+        r_mul_t = ent_w[bt] @ w_rel[rel]
+        vals.append(torch.sum(r_mul_t * torch.tanh(r_mul_h + rel_w[rel]), dim=1))
+    idx = torch.stack([torch.cat(rows), torch.cat(cols)])
+    a = torch.sparse_coo_tensor(idx, torch.cat(vals), (n, n))
+    a = torch.sparse.softmax(a, dim=1).coalesce()
+    return a.indices(), a.values()
+
+
 def update_attention_segments(ent_w, rel_w, h, t, r, relations: Iterable[int], n: int):
     """Independent numpy restatement of the same semantics (sort by (h,t), sum duplicate logits,
     max-subtracted softmax per head row) used to cross-check ``update_attention`` and to spell
