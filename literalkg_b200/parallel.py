@@ -199,9 +199,11 @@ class PeerTable:
         self.t = symm_mem.empty((self.slots, self.rows, self.d), dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.t, group)
         self.stream = torch.cuda.Stream(device=device)
-        # large row blocks go out on several streams at once: one device-to-device copy keeps ONE copy engine busy,
-        # well below what the 18 NVLinks of the GPU carry; small blocks are launch-latency bound and stay on one stream
-        n_copy = min(4, max(1, part.world - 1)) if self.rows * self.d * 4 >= (64 << 20) else 1
+        # the row blocks go out as device-to-device copies (copy engines), one peer at a time on one stream
+        # (measured at 8 GPUs, r02j: 4 concurrent streams made the 1.2 GB exchange SLOWER -- pass 5.0 ms against 4.1 ms
+        # with one stream; the staggered destinations only keep the ingress links disjoint when every rank sends to one
+        # peer at a time.  LKG_PUSH_STREAMS overrides for experiments.)
+        n_copy = max(1, min(int(os.environ.get("LKG_PUSH_STREAMS", "1")), max(1, part.world - 1)))
         self.copy_streams = [self.stream] + [torch.cuda.Stream(device=device) for _ in range(n_copy - 1)]
         self.calls = 0
 
