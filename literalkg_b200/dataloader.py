@@ -81,6 +81,58 @@ def read_numeric_literals(paths: Sequence[str], n_entities: Optional[int], numer
     return table, max_id
 
 
+NUMERIC_FILES = ("age_dict.txt", "weight_dict.txt")                                     # dataloader.py:29-30
+TEXT_FILES = ("cc_dict.pickle", "disease_dict.pickle", "memo_dict.pickle", "prescription_dict.pickle",
+              "treatment_dict.pickle")                                                   # dataloader.py:31-32
+
+
+def read_text_literals(paths: Sequence[str]) -> Dict[int, np.ndarray]:
+    """The text-literal pickles (dataloader.py:139-152): each holds ``{entity id: vector}``; a later file overrides an
+    earlier one for the same entity (dict assignment in file order)."""
+    text: Dict[int, np.ndarray] = {}
+    for p in paths:
+        with open(p, "rb") as fh:
+            for k, v in pickle.load(fh).items():
+                text[int(k)] = np.asarray(v, dtype=np.float32)
+    return text
+
+
+def read_data_dir(data_dir: str, kg_file: str = "pre_training_train.txt", numeric_dim: int = 2, text_dim: int = 300,
+                  numeric_files=NUMERIC_FILES, text_files=TEXT_FILES, use_num_lit: bool = True,
+                  use_txt_lit: bool = True):
+    """Host side of ``DataLoader.__init__`` for the tensors on the path (dataloader.py:111-152, 186-190, 405-438):
+    -> (triples int64 [E, 3] as (h, r, t), numeric table or None, text table or None), both tables [n, dim] float32
+    with n = max(KG ids, literal ids) + 1.  An entity that appears in a text pickle has its numeric row zeroed and an
+    entity of a numeric file gets a zero text row unless a pickle sets it (load_attributes, :133-150)."""
+    trip = read_triples(os.path.join(data_dir, kg_file))
+    n_kg = int(max(trip[:, 0].max(), trip[:, 2].max()) + 1)
+    num_paths = [os.path.join(data_dir, f) for f in numeric_files if os.path.exists(os.path.join(data_dir, f))]
+    txt_paths = [os.path.join(data_dir, f) for f in text_files if os.path.exists(os.path.join(data_dir, f))]
+    text = read_text_literals(txt_paths) if use_txt_lit else {}
+    num_table = text_table = None
+    num_max = -1
+    if num_paths and (use_num_lit or use_txt_lit):
+        table, num_max = read_numeric_literals(num_paths, n_kg, numeric_dim)
+        if use_num_lit:
+            if text:                                                  # dataloader.py:147-150
+                n_all = max(table.shape[0], max(text) + 1)
+                if n_all > table.shape[0]:
+                    table = np.concatenate([table, np.zeros((n_all - table.shape[0], numeric_dim), np.float32)])
+                table[np.fromiter(text.keys(), dtype=np.int64)] = 0
+            num_table = table
+    if use_txt_lit and (text or num_max >= 0):
+        n_txt = max([n_kg, num_max + 1] + ([max(text) + 1] if text else []))
+        if num_table is not None:
+            n_txt = max(n_txt, num_table.shape[0])
+        tt = np.zeros((n_txt, text_dim), dtype=np.float32)
+        for k, v in text.items():
+            tt[k] = v
+        text_table = tt
+        if num_table is not None and num_table.shape[0] < n_txt:
+            num_table = np.concatenate([num_table, np.zeros((n_txt - num_table.shape[0], numeric_dim), np.float32)])
+    return trip, num_table, text_table
+
+
 class KGTensors:
     """Device tensors with the attribute names the reference's training loop reads from its DataLoader
     (main.py:42-43,147-151): ``A_in``, ``h_list``, ``t_list``, ``r_list``, ``laplacian_dict`` (keys only),
@@ -123,37 +175,12 @@ class KGTensors:
 
     @classmethod
     def from_dir(cls, data_dir: str, kg_file: str = "pre_training_train.txt", numeric_dim: int = 2,
-                 text_dim: int = 300, numeric_files=("age_dict.txt", "weight_dict.txt"),
-                 text_files=("cc_dict.pickle", "disease_dict.pickle", "memo_dict.pickle",
-                             "prescription_dict.pickle", "treatment_dict.pickle"),
+                 text_dim: int = 300, numeric_files=NUMERIC_FILES, text_files=TEXT_FILES,
                  use_num_lit: bool = True, use_txt_lit: bool = True, **kw) -> "KGTensors":
         """Reads a reference data directory (dataloader.py:24-32).  Missing literal files are skipped
         (the Drive-hosted pickles are not bundled with the reference)."""
-        trip = read_triples(os.path.join(data_dir, kg_file))
-        num_paths = [os.path.join(data_dir, f) for f in numeric_files if os.path.exists(os.path.join(data_dir, f))]
-        n_kg = int(max(trip[:, 0].max(), trip[:, 2].max()) + 1)
-        num_table = text_table = None
-        text: Dict[int, np.ndarray] = {}
-        if use_txt_lit:
-            for f in text_files:
-                p = os.path.join(data_dir, f)
-                if os.path.exists(p):
-                    with open(p, "rb") as fh:
-                        text.update(pickle.load(fh))
-        if use_num_lit and num_paths:
-            table, _ = read_numeric_literals(num_paths, n_kg, numeric_dim)
-            if text:                                                  # dataloader.py:147-150
-                ids = np.fromiter((k for k in text if k < table.shape[0]), dtype=np.int64)
-                table[ids] = 0
-            num_table = table
-        if use_txt_lit:
-            n_txt = max([n_kg] + [k + 1 for k in text]) if text else n_kg
-            if num_table is not None:
-                n_txt = max(n_txt, num_table.shape[0])
-            tt = np.zeros((n_txt, text_dim), dtype=np.float32)
-            for k, v in text.items():
-                tt[k] = np.asarray(v, dtype=np.float32)
-            text_table = tt
+        trip, num_table, text_table = read_data_dir(data_dir, kg_file, numeric_dim, text_dim, numeric_files, text_files,
+                                                    use_num_lit, use_txt_lit)
         return cls(trip[:, 0], trip[:, 2], trip[:, 1], num_table=num_table, text_table=text_table, **kw)
 
 
