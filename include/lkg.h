@@ -351,7 +351,8 @@ int lkg_sigmoid_bwd(const float* dy, const float* y, int64_t m, float* dz, void*
  *      a CSR over heads whose rows are sorted by (relation, tail) (lkg_graph att_rowptr / att_tail / att_rel).
  *      Outputs are [n_heads * neg_rate], head / relation / positive repeated neg_rate times like
  *      generate_batch_by_neg_rate (dataloader.py:320-333).  Counter-based generator: the same seed gives the same
- *      batch.  n_failed (device int32, accumulated): draws that found no admissible tail in max_tries (output -1). */
+ *      batch.  n_failed (device int32, accumulated): draws that found no admissible tail in max_tries (the last candidate
+ *      drawn is emitted, so ids always stay valid) or heads without triples; callers must treat n_failed > 0 as an error. */
 int lkg_sample_batch(const int32_t* rowptr, const int32_t* tails, const int32_t* rels, const int64_t* heads,
                      int64_t n_heads, const int64_t* candidates, int64_t n_candidates, int32_t neg_rate,
                      int32_t use_relation, uint64_t seed, int32_t max_tries, int64_t* out_h,

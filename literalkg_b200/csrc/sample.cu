@@ -58,7 +58,11 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ rowptr, const in
         pos_t = __ldg(tails + e);
         pos_r = __ldg(rels + e);
     } else {
-        atomicAdd(n_failed, 1);                      // a head without triples cannot be sampled (KeyError upstream)
+        // a head without triples cannot be sampled (KeyError upstream): flagged, and the ids that are emitted stay
+        // inside the tables (the loss kernels do no range checks)
+        atomicAdd(n_failed, 1);
+        pos_t = cand[0];
+        pos_r = 0;
     }
     const int rel = use_relation ? (int)pos_r : -1;
     for (int k = 0; k < neg_rate; ++k) {
@@ -67,9 +71,10 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ rowptr, const in
         out_pos[i * neg_rate + k] = pos_t;
     }
     for (int k = 0; k < neg_rate; ++k) {
-        int64_t pick = -1;
+        int64_t pick = -1, last = cand[0];
         for (int tries = 0; tries < max_tries && pick < 0; ++tries) {
             const int64_t c = cand[rng.below((uint64_t)n_cand)];
+            last = c;
             // binary search for (rel, c) in the sorted row
             int lo = u0, hi = u1;
             while (lo < hi) {
@@ -82,7 +87,10 @@ __global__ void sample_batch_kernel(const int32_t* __restrict__ rowptr, const in
             for (int q = 0; q < k && !bad; ++q) bad = out_neg[i * neg_rate + q] == c;
             if (!bad) pick = c;
         }
-        if (pick < 0) atomicAdd(n_failed, 1);        // the reference would loop forever here
+        if (pick < 0) {                              // the reference would loop forever here: flagged (n_failed), and the
+            atomicAdd(n_failed, 1);                  // last candidate drawn is emitted so that the id stays valid
+            pick = last;
+        }
         out_neg[i * neg_rate + k] = pick;
     }
 }

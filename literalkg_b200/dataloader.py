@@ -197,6 +197,10 @@ class BatchSampler:
     def __init__(self, plan: GraphPlan, candidates, neg_rate: int, use_relation: bool, seed: int = 2022,
                  max_tries: int = 10_000):
         self.plan, self.neg_rate, self.use_relation = plan, int(neg_rate), bool(use_relation)
+        if not self.use_relation and plan.n_relations > 1:
+            # the rejection test is a binary search by tail in a row sorted by (relation, tail)
+            raise ValueError("use_relation=False needs a single-relation plan (build the (head, tail) plan with "
+                             "relation 0, like head_dict of the reference)")
         self.device = plan.device
         self.candidates = torch.as_tensor(candidates, dtype=torch.int64).to(self.device).contiguous()
         deg = plan.att_rowptr[1:] - plan.att_rowptr[:-1]
@@ -204,6 +208,15 @@ class BatchSampler:
         self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
         self.seed, self.calls, self.max_tries = int(seed), 0, int(max_tries)
         self.n_failed = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.check_every = 256          # calls between two looks at n_failed (one host sync each)
+
+    def check(self) -> None:
+        """Raises when a draw found no admissible negative within ``max_tries`` or a head had no triple (the reference
+        loops forever / raises KeyError there); ``sample`` calls it every ``check_every`` batches, callers at epoch end."""
+        n = int(self.n_failed.item())
+        if n:
+            raise RuntimeError(f"BatchSampler: {n} draws failed (no admissible negative tail within {self.max_tries} tries, "
+                               "or a head without triples)")
 
     def sample(self, batch_size: int):
         """-> (head, relation or None, pos_tail, neg_tail), int64 [n * neg_rate] with n = batch_size // neg_rate
@@ -220,6 +233,8 @@ class BatchSampler:
         out_h, out_pos, out_neg = torch.empty(m, **i64), torch.empty(m, **i64), torch.empty(m, **i64)
         out_r = torch.empty(m, **i64) if self.use_relation else None
         self.calls += 1
+        if self.check_every and self.calls % self.check_every == 0:
+            self.check()
         p = self.plan
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().lkg_sample_batch(

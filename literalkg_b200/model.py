@@ -228,10 +228,19 @@ class _GatEmbeddingsFn(torch.autograd.Function):
             model._debug_keep = keep
         ctx.model, ctx.pre, ctx.keep = model, pre, keep
         ctx.present = [t is not None for t in leaves]
+        # the backward reads the live parameters (detached): remember their in-place versions so that an optimizer
+        # step between this forward and its backward is an error, not a silently wrong gradient
+        ctx.versions = _param_key(model)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
+        if ctx.keep is None:
+            raise RuntimeError("the saved activations of this gat_embeddings() pass were freed by its first backward; "
+                               "run the forward again (retain_graph is not supported by the fused pass)")
+        if _param_key(ctx.model) != ctx.versions:
+            raise RuntimeError("a parameter of the model was modified in place (optimizer step / load_state_dict) between "
+                               "gat_embeddings() and its backward: the fused backward reads the live parameters")
         with torch.no_grad():
             grads = ctx.model._gat_backward(ctx.keep, ctx.pre, g_out)
         ctx.keep = None
@@ -558,12 +567,15 @@ class LiteralKG(nn.Module):
             # it is kept until one of them changes (in-place version counters; update_att bumps the A_in epoch).
             key = None
             if self.cache_embeddings and not self.training:
+                self._gate_module()                # normalise the state the key is built from first: the literal tables
+                self._current_plan()               # move to the device, A_in is re-expressed in plan order
+                vals = self.A_in.data._values()
                 key = (tuple((p.data_ptr(), p._version) for n_, p in self.named_parameters() if n_ != "A_in"),
                        tuple(None if t is None else (t.data_ptr(), t._version)
                              for t in (self.numerical_literals_embed, self.text_literals_embed)),
-                       self._a_in_epoch, self.A_in.data._values().data_ptr(), id(self._part), bool(gather))
+                       self._a_in_epoch, vals.data_ptr(), vals._version, id(self._part), bool(gather))
                 if self._embed_cache is not None and self._embed_cache[0] == key:
-                    return self._embed_cache[1]
+                    return self._embed_cache[1]     # shared with every caller until an input changes: treat as read-only
             out = self._gat_embeddings_native()
             part = self._part
             if not (part is None or part.world == 1 or not gather):

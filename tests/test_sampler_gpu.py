@@ -62,14 +62,24 @@ def test_prediction_batch_and_oversampling():
     assert r is None
     h, p, ng = h.cpu().numpy(), p.cpu().numpy(), ng.cpu().numpy()
     assert len(h) == 600 and set(h.tolist()) <= set(pos)
+    failed = 0
+    assert ng.min() >= 400 and ng.max() < 420                 # emitted ids are always valid candidates (no -1 sentinel)
     for i in range(0, 600, 3):
         assert int(p[i]) in pos[int(h[i])]
         negs = [int(x) for x in ng[i:i + 3]]
-        ok = [x for x in negs if x >= 0]
-        assert len(set(ok)) == len(ok) and all(x not in pos[int(h[i])] for x in ok)
-        # a head whose positives leave fewer than 3 admissible tails cannot be served (the reference loops forever)
+        ok = list(dict.fromkeys(x for x in negs if x not in pos[int(h[i])]))          # admissible and distinct
+        # a head whose positives leave fewer than 3 admissible tails cannot be served (the reference loops forever):
+        # such draws are flagged in n_failed and repeat / reuse a candidate
         assert len(ok) == min(3, 20 - len(pos[int(h[i])])) or len(ok) == 3
-    assert int(s.n_failed.item()) == int((ng < 0).sum())
+        failed += 3 - len(ok)
+    assert int(s.n_failed.item()) >= failed
+    if failed:
+        with pytest.raises(RuntimeError):
+            s.check()
+    with pytest.raises(ValueError):                           # rows sorted by (relation, tail): no tail-only search
+        kg3 = L.GraphPlan(torch.from_numpy(pairs[:, 0]).cuda(), torch.from_numpy(pairs[:, 1]).cuda(),
+                          (torch.arange(len(pairs)) % 3).cuda(), n, 3)
+        L.BatchSampler(kg3, np.arange(400, 420), neg_rate=3, use_relation=False)
 
 
 def test_positive_draw_is_uniform():
