@@ -33,6 +33,11 @@ def _param_key(module: nn.Module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
+def _dense_param_key(module: nn.Module):
+    """``_param_key`` without the sparse ``A_in`` entry of LiteralKG (a sparse tensor has no data pointer)."""
+    return tuple((p.data_ptr(), p._version) for n_, p in module.named_parameters() if n_ != "A_in")
+
+
 _EYE = {}
 
 
@@ -230,7 +235,7 @@ class _GatEmbeddingsFn(torch.autograd.Function):
         ctx.present = [t is not None for t in leaves]
         # the backward reads the live parameters (detached): remember their in-place versions so that an optimizer
         # step between this forward and its backward is an error, not a silently wrong gradient
-        ctx.versions = _param_key(model)
+        ctx.versions = _dense_param_key(model)
         return out
 
     @staticmethod
@@ -238,7 +243,7 @@ class _GatEmbeddingsFn(torch.autograd.Function):
         if ctx.keep is None:
             raise RuntimeError("the saved activations of this gat_embeddings() pass were freed by its first backward; "
                                "run the forward again (retain_graph is not supported by the fused pass)")
-        if _param_key(ctx.model) != ctx.versions:
+        if _dense_param_key(ctx.model) != ctx.versions:
             raise RuntimeError("a parameter of the model was modified in place (optimizer step / load_state_dict) between "
                                "gat_embeddings() and its backward: the fused backward reads the live parameters")
         with torch.no_grad():
