@@ -13,14 +13,20 @@ import torch
 from . import ops
 
 
-def _needs_grad(*tensors) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+def require_no_grad(module, tensors, what: str) -> None:
+    """The standalone modules run the forward kernels only.  The reference's modules are differentiable, so a caller
+    that trains through one of them must not get a silently detached result: fail loudly instead."""
+    if torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                    or any(t is not None and t.requires_grad for t in tensors)):
+        raise RuntimeError(f"{what} is a forward (inference) module of literalkg_b200: call it under torch.no_grad(); "
+                           "gradients of the path flow through LiteralKG.gat_embeddings() (one fused autograd node)")
 
 
 def gate_apply(module, inputs, out=None, out_planes=None, ent_planes=None, lit_planes=None, packed=None, gz_out=None):
     """Fused literal gate forward for ``Gate`` / ``GateMul`` (gate.py:22-28, 45-51).  The A operand is the K
     concatenation (entity | literals); ``ent_planes`` / ``lit_planes`` let the caller reuse cached fp16 planes."""
     x_ent = inputs[0]
+    require_no_grad(module, inputs, type(module).__name__)
     with torch.no_grad():
         w_pair, b_pair = module.packed() if packed is None else packed
         if ent_planes is None:

@@ -190,6 +190,8 @@ class Aggregator(nn.Module):
     def forward(self, ego_embeddings, A_in, all_layers, lamda, alpha, l):
         """Reference signature (model.py:101): ``A_in`` is a sparse COO tensor, ``all_layers[0]`` the gate
         output used by the residual connection, ``l`` the 1-based layer index."""
+        from .autograd import require_no_grad
+        require_no_grad(self, [ego_embeddings] + list(all_layers[:1]), "Aggregator")
         with torch.no_grad():
             ego = _lib.f32c(ego_embeddings)
             _lib.require_cuda(ego, "ego_embeddings")

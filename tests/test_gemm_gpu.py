@@ -74,8 +74,11 @@ def test_gate(m, dim, lits):
         mod.gate_bias.add_(torch.randn(dim, generator=g) * 0.2)
     mod = mod.cuda()
     xs = [torch.randn(m, dim, generator=g).cuda()] + [torch.randn(m, k, generator=g).cuda() for k in lits]
-    out = mod(*xs)
-    d = lambda t: t.double()
+    with pytest.raises(RuntimeError):          # standalone modules are inference modules: no silent detach under grad
+        mod(*xs)
+    with torch.no_grad():
+        out = mod(*xs)
+    d = lambda t: t.detach().double()
     x = torch.cat([d(t) for t in xs], 1)
     gg = torch.tanh(x @ d(mod.g.weight).t() + d(mod.g.bias))
     if len(lits) == 2:
@@ -155,8 +158,9 @@ def test_cta_pair_gate_and_score(cta_group):
     res = []
     for cg in (1, 2):
         cta_group(cg)
-        res.append(mod(*xs))
-    d = lambda t: t.double()
+        with torch.no_grad():
+            res.append(mod(*xs))
+    d = lambda t: t.detach().double()
     x = torch.cat([d(t) for t in xs], 1)
     gg = torch.tanh(x @ d(mod.g.weight).t() + d(mod.g.bias))
     z = torch.sigmoid(d(xs[0]) @ d(mod.gate_ent.weight).t() + d(xs[1]) @ d(mod.gate_num_lit.weight).t()
