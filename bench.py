@@ -504,6 +504,62 @@ def run_ours(a):
                    "dtype": "f16 filter GEMM (1 product) + exact fp64-accumulated re-score of the candidates",
                    "calls": {k_: round(v["ms_avg"], 4) for k_, v in sprof.items()}}
 
+    ranking = None
+    if not a.no_scoring and part is None:
+        # north star (d): rank of a given (positive) tail per head, fused -- the 3-product scoring GEMM with a counting
+        # epilogue + exact re-score of the few columns inside the error band; no B x N score matrix
+        ti = ops.ScoreIndex(emb, None)
+        ti.planes()
+        hb = batches[0]
+        tgt = (hb * 31 + 17) % n
+        for _ in range(2):
+            ops.score_rank(emb, hb, tgt, ti)
+        sync()
+        start.record()
+        for _ in range(3):
+            ranks = ops.score_rank(emb, hb, tgt, ti)
+        end.record()
+        sync()
+        rms = start.elapsed_time(end) / 3
+        flops3 = 3 * 2.0 * a.score_heads * n * emb.shape[1]
+        ranking = {"metric": f"triples/s, rank of a given tail per head, {a.score_heads} heads x {n} tails, fused (no score matrix)",
+                   "value": a.score_heads * n / (rms / 1e3), "unit": "triples/s", "ms_per_batch": rms,
+                   "issued_tflops": flops3 / (rms / 1e3) / 1e12,
+                   "frac_of_tensor_peak_issued": flops3 / (rms / 1e3) / 1e12 / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+                   "mean_rank": float(ranks.float().mean())}
+
+    projected = None
+    if not a.no_scoring and part is None and a.entities <= 2_000_000:
+        # north star (b), extension: relation-projected attention v = (e_t W_r) . tanh(e_h W_r + e_r) with an explicit
+        # W [R, D, D]: two chained tensor-core GEMMs per relation bucket over the (head, relation) runs + one gather per triple
+        gw = torch.Generator(device=dev).manual_seed(1)
+        w_rel = torch.randn(n_rel, cfg.embed_dim, cfg.relation_dim, generator=gw, device=dev) / cfg.embed_dim ** 0.5
+        keep_a = (model._agg_plan, model._agg_values, model.A_in.data)
+        model(h_dev, t_dev, r_dev, rels, w_rel, device=dev, mode="update_att_projected")      # warm-up: run bookkeeping
+        sync()
+        ops.PROFILE = ops.Profile()
+        start.record()
+        for _ in range(2):
+            model(h_dev, t_dev, r_dev, rels, w_rel, device=dev, mode="update_att_projected")
+        end.record()
+        sync()
+        pprof = ops.PROFILE.summary()
+        ops.PROFILE = None
+        pms = start.elapsed_time(end) / 2
+        n_runs = model._att_plan.runs()["n_runs"]
+        gemm_ms = sum(v["ms_total"] for k_, v in pprof.items() if k_.startswith("linear_")) / 2
+        pflops = 3 * 2 * 2.0 * n_runs * cfg.embed_dim * cfg.relation_dim                      # two GEMMs, three products
+        projected = {"metric": "edges/s, relation-projected attention update (extension)", "value": e / (pms / 1e3),
+                     "unit": UNIT, "ms_per_update": pms, "head_relation_runs": n_runs,
+                     "gemm_ms": gemm_ms, "gemm_issued_tflops": pflops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None,
+                     "calls_ms_per_update": {k_: round(v["ms_total"] / 2, 3) for k_, v in
+                                             sorted(pprof.items(), key=lambda kv: -kv[1]["ms_total"])}}
+        model._agg_plan, model._agg_values = keep_a[0], keep_a[1]
+        model.A_in.data = keep_a[2]
+        model._a_in_epoch += 1
+        del w_rel
+        torch.cuda.empty_cache()
+
     training = None
     if not a.no_training:
         # one optimisation step's worth of kernels: fine-tuning (BPR) loss on the reference's effective minibatch of
@@ -573,7 +629,8 @@ def run_ours(a):
                            "cache": "inputs (entity tables 1.2 GB each, 25 GB gathered per kernel) "
                            "are far larger than the 126 MB L2; no explicit flush"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks.result(), "scoring": scoring, "training": training}
+                "clocks": clocks.result(), "scoring": scoring, "ranking": ranking, "projected_attention": projected,
+                "training": training}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
