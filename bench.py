@@ -509,7 +509,7 @@ def run_ours(a):
         # north star (d): rank of a given (positive) tail per head, fused -- the 3-product scoring GEMM with a counting
         # epilogue + exact re-score of the few columns inside the error band; no B x N score matrix
         ti = ops.ScoreIndex(emb, None)
-        ti.planes()
+        ti.centered()
         hb = batches[0]
         tgt = (hb * 31 + 17) % n
         for _ in range(2):

@@ -393,15 +393,21 @@ int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows /*nullable
  * rank_i = #{ j : s_ij > s_it or (s_ij == s_it and j < t_i) }, s = the exact scores the fused top-k returns, t_i =
  * target_pos[i] (a position in the tail list).  Three calls on one stream:
  *   lkg_rank_prepare  tau [n_heads] = exact target scores, thr [n_heads][2] = tau -/+ a rigorous bound of the
- *                     3-product GEMM's error (tail_max_norm / rec: the tails' score index);
+ *                     3-product GEMM's error (tail_max_norm / rec: the score index of the tails the GEMM multiplies).
+ *                     center (nullable): the GEMM's tails are t_j - center -- a common shift leaves every head's
+ *                     ranking unchanged and shrinks the bound from |h| max|t| to |h| max|t - center|; the thresholds
+ *                     are then taken around tau - h . center;
  *   lkg_score_rank    the scoring GEMM (heads / tails as hi/lo planes sharing one scale record) with a counting
  *                     epilogue: above[i] += columns certainly better, band_cnt[i] += columns inside the band, the first
  *                     band_cap of them listed in band [n_heads][band_cap] (zero above / band_cnt first);
  *   lkg_rank_finalize the listed columns re-scored exactly; a head whose band overflowed is re-scanned exactly. */
+/* out[r, :] = src[rows ? rows[r] : r, :] - center: the shifted tails of the rank GEMM (center = their mean). */
+int lkg_shift_rows(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
+                   const float* center, float* out, int64_t ld_out, void* stream);
 int lkg_rank_prepare(const float* emb, int64_t ld_emb, const int64_t* tail_rows /*nullable*/, const float* head_emb,
                      int64_t ld_head_emb, const int64_t* head_rows /*nullable*/, const int64_t* target_pos,
-                     int64_t n_heads, int32_t dim, const float* tail_max_norm, const float* rec, float* tau, float* thr,
-                     void* stream);
+                     int64_t n_heads, int32_t dim, const float* tail_max_norm, const float* rec,
+                     const float* center /*nullable [dim]*/, float* tau, float* thr, void* stream);
 int lkg_score_rank(const lkg_planes* heads, int64_t n_heads, const lkg_planes* tails, int64_t n_tails, const float* thr,
                    int32_t* above, int32_t* band_cnt, int32_t* band, int32_t band_cap, void* stream);
 int lkg_rank_finalize(const float* emb, int64_t ld_emb, const int64_t* tail_rows, const float* head_emb,

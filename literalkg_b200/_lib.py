@@ -86,7 +86,8 @@ SIGNATURES = {
     "lkg_minmax_reset": (C.c_int, [vp, vp]),
     "lkg_predict_threshold": (C.c_int, [vp, i64, i64, i64, vp, C.c_float, vp, i64, vp]),
     "lkg_topk_rows": (C.c_int, [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp]),
-    "lkg_rank_prepare": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp, vp]),
+    "lkg_shift_rows": (C.c_int, [vp, i64, vp, i64, i32, vp, vp, i64, vp]),
+    "lkg_rank_prepare": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
     "lkg_score_rank": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i64, vp, vp, vp, vp, i32, vp]),
     "lkg_rank_finalize": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, i64, i64, i32, vp, vp]),
     "lkg_topk_merge": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp]),

@@ -535,34 +535,55 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
 //   3. lkg_rank_finalize  the listed columns re-scored exactly and compared with tau under the tie rule.
 constexpr float kRankErr = 2.5e-5f;
 
+// center (nullable, [dim]): the GEMM's tails are t_j - center (a common shift moves every score of a head by the same
+// h . center, so the ranking is unchanged while the error bound shrinks from |h| max|t| to |h| max|t - center| -- the
+// embeddings of a trained or freshly initialised model are tightly clustered around their mean, and a band relative
+// to |t| would hold tens of thousands of tails); the thresholds are then taken around tau - h . center.
+// out[r, :] = src[rows ? rows[r] : r, :] - center  (the shifted tails of the rank GEMM)
+__global__ void shift_rows_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows, int64_t m,
+                                  int k, const float* __restrict__ center, float* __restrict__ out, int64_t ldo) {
+    const int64_t total = m * k;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / k;
+        const int c = (int)(i - r * k);
+        out[r * ldo + c] = src[(rows ? rows[r] : r) * ld + c] - __ldg(center + c);
+    }
+}
+
 __global__ void rank_prepare_kernel(const float* __restrict__ emb, int64_t ld, const int64_t* __restrict__ tail_rows,
                                     const float* __restrict__ head_emb, int64_t ld_h,
                                     const int64_t* __restrict__ head_rows, const int64_t* __restrict__ target_pos,
                                     int n_heads, int dim, const float* __restrict__ tail_max_norm,
-                                    const float* __restrict__ rec, float* __restrict__ tau, float* __restrict__ thr) {
+                                    const float* __restrict__ rec, const float* __restrict__ center,
+                                    float* __restrict__ tau, float* __restrict__ thr) {
     const int lane = threadIdx.x & 31;
     const int head = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (head >= n_heads) return;
     const float* hrow = head_emb + (head_rows ? head_rows[head] : head) * ld_h;
     const int64_t tp = target_pos[head];
     const float* trow = emb + (tail_rows ? tail_rows[tp] : tp) * ld;
-    double acc = 0.0, nh = 0.0;
+    double acc = 0.0, nh = 0.0, hc = 0.0;
     for (int c = lane; c < dim; c += 32) {
         const float a = __ldg(hrow + c), b = __ldg(trow + c);
         acc = fma((double)a, (double)b, acc);
         nh = fma((double)a, (double)a, nh);
+        if (center) hc = fma((double)a, (double)__ldg(center + c), hc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         acc += __shfl_xor_sync(kFull, acc, o);
         nh += __shfl_xor_sync(kFull, nh, o);
+        hc += __shfl_xor_sync(kFull, hc, o);
     }
     if (lane == 0) {
-        const float t = (float)acc;
-        const float e = kRankErr * (float)sqrt(nh) * (*tail_max_norm) * rec[2] * 1.0001f + 1e-30f;   // norms: scaled units
+        const float t = (float)acc;                          // exact target score, rounded once (what finalize compares)
+        const float ts = (float)(acc - hc);                  // the same in the GEMM's (shifted) frame
+        // bound of the GEMM's error (norms of the tails: scaled units) + the rounding of the two fp32 numbers above
+        const float e = kRankErr * (float)sqrt(nh) * (*tail_max_norm) * rec[2] * 1.0001f +
+                        (fabsf(t) + fabsf(ts) + (float)fabs(hc)) * 2e-7f + 1e-30f;
         tau[head] = t;
-        thr[2 * head] = t - e - fabsf(t) * 2e-7f;
-        thr[2 * head + 1] = t + e + fabsf(t) * 2e-7f;
+        thr[2 * head] = ts - e;
+        thr[2 * head + 1] = ts + e;
     }
 }
 
@@ -629,17 +650,29 @@ extern "C" int lkg_score_index(const float* emb, int64_t ld, const int64_t* rows
     return LKG_OK;
 }
 
+extern "C" int lkg_shift_rows(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k, const float* center,
+                              float* out, int64_t ld_out, void* stream_) {
+    LKG_REQUIRE(src && center && out && m >= 0 && k > 0 && ld_out >= k, "bad shift arguments");
+    if (m == 0) return LKG_OK;
+    int64_t blocks = (m * k + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    shift_rows_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream_>>>(src, ld, rows, m, k, center,
+                                                                                            out, ld_out);
+    LKG_LAUNCH_CHECK("shift_rows_kernel");
+    return LKG_OK;
+}
+
 extern "C" int lkg_rank_prepare(const float* emb, int64_t ld_emb, const int64_t* tail_rows, const float* head_emb,
                                 int64_t ld_head_emb, const int64_t* head_rows, const int64_t* target_pos, int64_t n_heads,
-                                int32_t dim, const float* tail_max_norm, const float* rec, float* tau, float* thr,
-                                void* stream_) {
+                                int32_t dim, const float* tail_max_norm, const float* rec, const float* center,
+                                float* tau, float* thr, void* stream_) {
     LKG_REQUIRE(emb && head_emb && target_pos && tail_max_norm && rec && tau && thr && n_heads >= 0 && dim > 0,
                 "bad rank arguments");
     if (n_heads == 0) return LKG_OK;
     const int64_t blocks = (n_heads * 32 + 255) / 256;
     rank_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(emb, ld_emb, tail_rows, head_emb, ld_head_emb,
                                                                              head_rows, target_pos, (int)n_heads, dim,
-                                                                             tail_max_norm, rec, tau, thr);
+                                                                             tail_max_norm, rec, center, tau, thr);
     LKG_LAUNCH_CHECK("rank_prepare_kernel");
     return LKG_OK;
 }

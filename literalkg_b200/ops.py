@@ -348,12 +348,26 @@ class ScoreIndex:
                                                    self.norms.data_ptr(), self.max_norm.data_ptr(), _lib.stream()))
 
 
-    def planes(self) -> _lib.Planes:
-        """fp16 hi/lo planes of the same rows under the same scale record (the 3-product operand of the rank GEMM);
-        built on first use, kept with the index."""
-        if getattr(self, "_planes", None) is None:
-            self._planes = split_planes(self.emb, self.rows, rec=self.rec)
-        return self._planes
+    def centered(self):
+        """-> (center [dim], ScoreIndex of the rows minus their mean, its hi/lo planes): the operand of the rank GEMM.
+        A common shift of the tails changes no head's ranking, and the error band of the GEMM is relative to
+        max|t - center| instead of max|t| (model embeddings are tightly clustered).  Built on first use."""
+        if getattr(self, "_centered", None) is None:
+            if self.rows is None:
+                center = colsum(self.emb)
+            else:                                        # a gathered tail list: its own column sums
+                center = torch.zeros(self.dim, dtype=torch.float32, device=self.emb.device)
+                for c0 in range(0, self.m, 1 << 20):
+                    colsum(self.emb[self.rows[c0:c0 + (1 << 20)]], out=center)
+            center = (center / float(max(self.m, 1))).contiguous()
+            shifted = torch.empty((max(self.m, 1), self.dim), dtype=torch.float32, device=self.emb.device)[:self.m]
+            with _dev_guard(self.emb, "shift_rows"):
+                _lib.check(_lib.load().lkg_shift_rows(self.emb.data_ptr(), self.emb.stride(0), _lib.ptr(self.rows), self.m,
+                                                      self.dim, center.data_ptr(), shifted.data_ptr(), shifted.stride(0),
+                                                      _lib.stream()))
+            ci = ScoreIndex(shifted, None)
+            self._centered = (center.contiguous(), ci, split_planes(shifted, None, rec=ci.rec))
+        return self._centered
 
 
 def score_rank(emb: torch.Tensor, heads: Optional[torch.Tensor], target_pos: torch.Tensor, tail_index: ScoreIndex,
@@ -365,14 +379,14 @@ def score_rank(emb: torch.Tensor, heads: Optional[torch.Tensor], target_pos: tor
     hsrc = emb if head_emb is None else head_emb
     assert hsrc.dtype == torch.float32 and hsrc.stride(1) == 1 and hsrc.shape[1] == emb.shape[1]
     hrows = None if heads is None else heads.to(device=emb.device, dtype=torch.int64).contiguous()
-    hp = split_planes(hsrc, hrows, rec=ti.rec)
+    hp = split_planes(hsrc, hrows)                       # own scale record: the two operands' factors multiply
     nh = hp.rows
     tgt = target_pos.to(device=emb.device, dtype=torch.int64).contiguous()
     assert tgt.numel() == nh
     ranks = torch.empty(nh, dtype=torch.int64, device=emb.device)
     if nh == 0:
         return ranks
-    tp = ti.planes()
+    center, ci, tp = ti.centered()
     tau = torch.empty(nh, dtype=torch.float32, device=emb.device)
     thr = torch.empty((nh, 2), dtype=torch.float32, device=emb.device)
     counters = torch.zeros((2, nh), dtype=torch.int32, device=emb.device)
@@ -381,8 +395,9 @@ def score_rank(emb: torch.Tensor, heads: Optional[torch.Tensor], target_pos: tor
     with _dev_guard(emb, "score_rank", 3):
         lib = _lib.load()
         _lib.check(lib.lkg_rank_prepare(emb.data_ptr(), emb.stride(0), _lib.ptr(ti.rows), hsrc.data_ptr(), hsrc.stride(0),
-                                        _lib.ptr(hrows), tgt.data_ptr(), nh, emb.shape[1], ti.max_norm.data_ptr(),
-                                        ti.rec.data_ptr(), tau.data_ptr(), thr.data_ptr(), _lib.stream()))
+                                        _lib.ptr(hrows), tgt.data_ptr(), nh, emb.shape[1], ci.max_norm.data_ptr(),
+                                        ci.rec.data_ptr(), center.data_ptr(), tau.data_ptr(), thr.data_ptr(),
+                                        _lib.stream()))
         _lib.check(lib.lkg_score_rank(C.byref(a), nh, C.byref(b), ti.m, thr.data_ptr(), counters[0].data_ptr(),
                                       counters[1].data_ptr(), band.data_ptr(), band_cap, _lib.stream()))
         _lib.check(lib.lkg_rank_finalize(emb.data_ptr(), emb.stride(0), _lib.ptr(ti.rows), hsrc.data_ptr(), hsrc.stride(0),
