@@ -521,12 +521,20 @@ def run_ours(a):
         end.record()
         sync()
         rms = start.elapsed_time(end) / 3
+        # checker: the first 32 heads against float64 scoring (exact fp32 products, fp64 sums, one rounding, ties by position)
+        e64 = emb.double()
+        s64 = (e64[hb[:32]] @ e64.t()).float()
+        tg = torch.gather(s64, 1, tgt[:32].unsqueeze(1))
+        posn = torch.arange(n, device=dev).unsqueeze(0)
+        ref_rank = ((s64 > tg) | ((s64 == tg) & (posn < tgt[:32].unsqueeze(1)))).sum(1)
+        rank_exact = bool(torch.equal(ranks[:32], ref_rank))
+        del e64, s64
         flops3 = 3 * 2.0 * a.score_heads * n * emb.shape[1]
         ranking = {"metric": f"triples/s, rank of a given tail per head, {a.score_heads} heads x {n} tails, fused (no score matrix)",
                    "value": a.score_heads * n / (rms / 1e3), "unit": "triples/s", "ms_per_batch": rms,
                    "issued_tflops": flops3 / (rms / 1e3) / 1e12,
                    "frac_of_tensor_peak_issued": flops3 / (rms / 1e3) / 1e12 / float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                   "mean_rank": float(ranks.float().mean())}
+                   "mean_rank": float(ranks.float().mean()), "first_32_heads_equal_float64_ranking": rank_exact}
 
     projected = None
     if not a.no_scoring and part is None and a.entities <= 2_000_000:

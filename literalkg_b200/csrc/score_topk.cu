@@ -528,12 +528,13 @@ __global__ void __launch_bounds__(kFinalThreads) score_finalize_kernel(FinalPara
 // rank_i = #{ j : s_ij > s_it  or  (s_ij == s_it and j < t_i) } with s the EXACT scores (fp32 products summed in fp64,
 // one rounding -- the values the fused top-k returns) and t_i the position of head i's target in the tail list.
 //   1. lkg_rank_prepare   tau_i = exact score of (head i, target i); band tau_i -/+ E_i with E_i a bound of the
-//                         3-product fp16 hi/lo GEMM's error: representation 3 * 2^-22 |h||t| + fp32 accumulation of
-//                         48 MMAs <= 2^-22 |h||t| each -> 1.2e-5 |h||t|; kRankErr doubles it;
+//                         3-product fp16 hi/lo GEMM's error for K <= 256: representation (operands kept to 2^-22, the
+//                         lo * lo product dropped) 3 * 2^-22 |h||t| = 0.7e-6, fp32 accumulation of 48 MMAs at <= 2^-23
+//                         of the running magnitude each = 5.7e-6; kRankErr = 1e-5 leaves a factor 1.5 on top;
 //   2. lkg_score_rank     (gemm_tc.cu) the score GEMM with a counting epilogue: columns certainly above tau are counted,
 //                         the ones inside the band are listed; no score leaves the SM;
 //   3. lkg_rank_finalize  the listed columns re-scored exactly and compared with tau under the tie rule.
-constexpr float kRankErr = 2.5e-5f;
+constexpr float kRankErr = 1.0e-5f;
 
 // center (nullable, [dim]): the GEMM's tails are t_j - center (a common shift moves every score of a head by the same
 // h . center, so the ranking is unchanged while the error bound shrinks from |h| max|t| to |h| max|t - center| -- the

@@ -371,7 +371,7 @@ class ScoreIndex:
 
 
 def score_rank(emb: torch.Tensor, heads: Optional[torch.Tensor], target_pos: torch.Tensor, tail_index: ScoreIndex,
-               head_emb: Optional[torch.Tensor] = None, band_cap: int = 2048) -> torch.Tensor:
+               head_emb: Optional[torch.Tensor] = None, band_cap: int = 8192) -> torch.Tensor:
     """Rank (0 = best) of tail position ``target_pos[i]`` for head i among the tails of ``tail_index`` under "larger
     exact score first, ties -> lower position", without the B x Nt score matrix (lkg_rank_prepare / lkg_score_rank /
     lkg_rank_finalize).  ``heads`` index ``head_emb`` (default ``emb``), None = every row."""
