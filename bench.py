@@ -506,35 +506,43 @@ def run_ours(a):
 
     ranking = None
     if not a.no_scoring and part is None:
-        # north star (d): rank of a given (positive) tail per head, fused -- the 3-product scoring GEMM with a counting
-        # epilogue + exact re-score of the few columns inside the error band; no B x N score matrix
+        # north star (d): rank of a given tail per head, fused -- the 3-product scoring GEMM with a counting epilogue +
+        # exact re-score of the few columns inside the error band; no B x N score matrix.  Two target sets: the tail
+        # that is 38th best for its head (what a link-prediction evaluation ranks: positives sit near the top; doubles
+        # as an exactness check, every rank must come out as 37) and arbitrary tails (mid-ranked: the densest part of
+        # the score distribution, the worst case for the band).
         ti = ops.ScoreIndex(emb, None)
         ti.centered()
         hb = batches[0]
-        tgt = (hb * 31 + 17) % n
-        for _ in range(2):
-            ops.score_rank(emb, hb, tgt, ti)
-        sync()
-        start.record()
-        for _ in range(3):
-            ranks = ops.score_rank(emb, hb, tgt, ti)
-        end.record()
-        sync()
-        rms = start.elapsed_time(end) / 3
-        # checker: the first 32 heads against float64 scoring (exact fp32 products, fp64 sums, one rounding, ties by position)
-        e64 = emb.double()
-        s64 = (e64[hb[:32]] @ e64.t()).float()
-        tg = torch.gather(s64, 1, tgt[:32].unsqueeze(1))
-        posn = torch.arange(n, device=dev).unsqueeze(0)
-        ref_rank = ((s64 > tg) | ((s64 == tg) & (posn < tgt[:32].unsqueeze(1)))).sum(1)
-        rank_exact = bool(torch.equal(ranks[:32], ref_rank))
-        del e64, s64
-        flops3 = 3 * 2.0 * a.score_heads * n * emb.shape[1]
+        _, top_pos = ops.score_topk(emb, hb, None, 100, tail_index=ti)
+        targets = {"top": top_pos[:, 37].contiguous(), "arbitrary": (hb * 31 + 17) % n}
         ranking = {"metric": f"triples/s, rank of a given tail per head, {a.score_heads} heads x {n} tails, fused (no score matrix)",
-                   "value": a.score_heads * n / (rms / 1e3), "unit": "triples/s", "ms_per_batch": rms,
-                   "issued_tflops": flops3 / (rms / 1e3) / 1e12,
-                   "frac_of_tensor_peak_issued": flops3 / (rms / 1e3) / 1e12 / float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                   "mean_rank": float(ranks.float().mean()), "first_32_heads_equal_float64_ranking": rank_exact}
+                   "unit": "triples/s"}
+        for name, tgt in targets.items():
+            for _ in range(2):
+                ops.score_rank(emb, hb, tgt, ti)
+            sync()
+            start.record()
+            for _ in range(3):
+                ranks = ops.score_rank(emb, hb, tgt, ti)
+            end.record()
+            sync()
+            rms = start.elapsed_time(end) / 3
+            if name == "top":
+                ranking.update(value=a.score_heads * n / (rms / 1e3), ms_per_batch=rms,
+                               issued_tflops=3 * 2.0 * a.score_heads * n * emb.shape[1] / (rms / 1e3) / 1e12,
+                               all_ranks_equal_37=bool((ranks == 37).all()))
+            else:
+                # checker: the first 32 heads against float64 scoring (exact products, fp64 sums, one rounding, ties by position)
+                e64 = emb.double()
+                s64 = (e64[hb[:32]] @ e64.t()).float()
+                tg = torch.gather(s64, 1, tgt[:32].unsqueeze(1))
+                posn = torch.arange(n, device=dev).unsqueeze(0)
+                ref_rank = ((s64 > tg) | ((s64 == tg) & (posn < tgt[:32].unsqueeze(1)))).sum(1)
+                ranking.update(arbitrary_targets_ms_per_batch=rms, arbitrary_targets_mean_rank=float(ranks.float().mean()),
+                               arbitrary_first_32_heads_equal_float64_ranking=bool(torch.equal(ranks[:32], ref_rank)))
+                del e64, s64
+        ranking["frac_of_tensor_peak_issued"] = ranking["issued_tflops"] / float(peaks.get("bf16_tflops_sustained", 1400.0))
 
     projected = None
     if not a.no_scoring and part is None and a.entities <= 2_000_000:
