@@ -15,7 +15,9 @@
  *   - buffers are borrowed for the duration of the call: the library never allocates, frees or
  *     retains device memory (callers size scratch with the *_workspace_bytes queries);
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host unless
- *     documented otherwise, re-entrant, and keep no global mutable state;
+ *     documented otherwise.  A graph plan (lkg_graph) carries device scratch its kernels mutate during a
+ *     launch (row counter, seg_tickets, seg_scratch): ONE plan may be used by ONE stream at a time.  The only
+ *     process-wide state is the error string (thread local) and the lkg_gemm_set_cta_group tuning knob;
  *   - row-major matrices; `ld*` arguments are leading dimensions in ELEMENTS;
  *   - sm_100 only: there is no CPU or other-architecture fallback by design.
  */
