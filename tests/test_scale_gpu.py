@@ -58,10 +58,24 @@ def test_default_dims_vs_oracle(agg, res):
     assert np.array_equal(a.indices().cpu().numpy(), oi.numpy())
     assert rel_err(a.values(), ov) < REL
     assert oi.shape[1] < kg.n_edges                       # the duplicate-merge path was exercised
-    # full embedding pass
+    # full embedding pass: the yardstick is the oracle evaluated in FLOAT64 (two fp32 evaluations of the same formula
+    # already differ by up to 5e-4 for graphsage + residual, so "within 1e-3 of an fp32 oracle" would not bound the
+    # distance to the reference); the oracle's own fp32 evaluation is measured against it beside ours
     out = m.gat_embeddings()
     ref, st = O.gat_embeddings(p, cfg, oi, ov, num if cfg.use_num_lit else None, txt if cfg.use_txt_lit else None,
                                return_stages=True)
+    p64 = O.cast_params(p, torch.float64)
+    oi64, ov64 = O.update_attention(p64["entity_embed.weight"], p64["relation_embed.weight"], h, t, r, kt.relations, n)
+    ref64 = O.gat_embeddings(p64, cfg, oi64, ov64, num.double() if cfg.use_num_lit else None,
+                             txt.double() if cfg.use_txt_lit else None)
+    e_cuda, e_fp32 = rel_err(out, ref64), rel_err(ref, ref64)
+    big = ref64.abs() > 0.1 * ref64.abs().max()                 # element-wise on the top decade of magnitudes
+    el_cuda = ((out.cpu().double() - ref64).abs()[big] / ref64.abs()[big]).max().item()
+    el_fp32 = ((ref.double() - ref64).abs()[big] / ref64.abs()[big]).max().item()
+    print(f"{agg} residual={res}: CUDA vs fp64 {e_cuda:.2e} (element-wise {el_cuda:.2e}); fp32 oracle vs fp64 {e_fp32:.2e} "
+          f"(element-wise {el_fp32:.2e})")
+    assert rel_err(a.values(), ov64) < REL
+    assert e_cuda < REL and el_cuda < 5 * REL
     assert rel_err(out, ref) < REL
     # scoring + top-k against torch.topk of the oracle's calc_score (near-ties excluded by margin)
     heads = torch.arange(0, 64) * 7 % n
