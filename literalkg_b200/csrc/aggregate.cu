@@ -578,9 +578,14 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) aggregate_stream_kernel(
     float4* stage = reinterpret_cast<float4*>(warp_base + (size_t)kRing * slot_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NT * nvec * cpad * 16 +
                                                  (size_t)kStreamWarps * warp_bytes) + warp * kRing;
+    // [ego row | z row] stored back to back in one table (model.py lays the gate output and its projection out like
+    // that): ONE bulk copy per neighbour instead of two, and the 128-byte z row rides in the DRAM page of its ego row
+    const bool zcontig = Z && p.z == p.ego + d_in && p.ld_z == p.ld_ego;
     auto issue = [&](uint32_t slot, int col) {                   // one elected lane: row copy (+ z copy), one barrier
         uint8_t* dst = ring + slot * slot_bytes;
-        if (Z) {
+        if (Z && zcontig) {
+            ring_issue(dst, p.ego + (int64_t)col * p.ld_ego, slot_bytes, &bars[slot]);
+        } else if (Z) {
             ring_expect(&bars[slot], slot_bytes);
             ring_copy(dst, p.ego + (int64_t)col * p.ld_ego, row_bytes, &bars[slot]);
             ring_copy(dst + row_bytes, p.z + (int64_t)col * p.ld_z, z_bytes, &bars[slot]);

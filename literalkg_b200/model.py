@@ -639,7 +639,25 @@ class LiteralKG(nn.Module):
         gate_mod, tables = self._gate_module()
         ent = self.entity_embed.weight
         return ((ent.data_ptr(), ent._version), None if gate_mod is None else _param_key(gate_mod),
-                tuple((t.data_ptr(), t._version) for t in tables), None if part is None else (part.begin, part.end))
+                tuple((t.data_ptr(), t._version) for t in tables), None if part is None else (part.begin, part.end),
+                tuple(_param_key(layer) for layer in self.aggregator_layers), float(self.lamda), float(self.alpha))
+
+    def _combined_table(self, keep, pre) -> bool:
+        """Inference pass of the bi-interaction model with the pre-projected sum term: the gate output h0 and
+        z = h0 @ Pb live side by side in ONE table [rows, d + C] -- layer 1 fetches a neighbour's (h0 | z) row with one
+        bulk copy, and the row partition exchanges one table instead of two."""
+        d = self.embed_dim
+        return (keep is None and pre is None and self.scale_gat_dim is not None and self.n_layers > 0
+                and self.use_residual and self.aggregation_type == 'bi-interaction' and d >= 128 and d % 4 == 0
+                and self.aggregator_layers[0].out_dim % 4 == 0)
+
+    def _residual_gemm(self, h0_planes, folds):
+        """h0 @ Q for all layers (+ layer 1's ego @ Pa and the z columns) as one GEMM -> (h0q, offsets, zoff)."""
+        qkey = tuple(id(f) for f in folds)                 # the fold dicts are cached per parameter version
+        if self._h0q_cache is None or self._h0q_cache[0] != qkey:
+            self._h0q_cache = (qkey, *self._stack_q(folds), folds)
+        _, wq, cq, offsets, zoff, _ = self._h0q_cache
+        return ops.linear([h0_planes], wq, cq), offsets, zoff
 
     def _gate_stage(self, part, keep=None, pre=None) -> dict:
         """First stage of the embedding pass: buffers, the literal gate on this rank's rows and -- row partitioned,
@@ -651,14 +669,28 @@ class LiteralKG(nn.Module):
         rb, re = (0, n) if part is None else (part.begin, part.end)
         rows = None if part is None else (rb, re)
         n_own, n_tab = re - rb, (n if part is None else part.padded)
-        cat = torch.empty((n_own, total), dtype=torch.float32, device=dev)   # concat buffer, this rank's rows
+        combined = self._combined_table(keep, pre)
+        width = d + (self.aggregator_layers[0].out_dim if combined else 0)
+        # concat buffer, this rank's rows (fp32 copy of what linear_gat reads as planes; not needed by the combined
+        # inference layout, whose fp32 consumers are the gathers of layer 1 only)
+        cat = None if combined else torch.empty((n_own, total), dtype=torch.float32, device=dev)
         gather_h0 = False
         if part is not None and self.n_layers > 0:
             c0 = self.aggregator_layers[0].out_dim
             z_path = self.use_residual and d >= 128 and c0 % 4 == 0      # see _stack_q
             gather_h0 = not z_path or self.aggregation_type == 'bi-interaction'
         peer = None
-        if part is None:
+        if combined:
+            if part is None:
+                h0_tab = torch.empty((n, width), dtype=torch.float32, device=dev)
+            else:
+                tab = self._exchange_table(part, "h0z", width, False)
+                if tab is not None:
+                    h0_tab, peer = tab.begin()
+                else:
+                    h0_tab = torch.empty((n_tab, width), dtype=torch.float32, device=dev)
+            h0 = h0_tab[rb:re, :d]
+        elif part is None:
             h0_tab = h0 = cat[:, :d]                      # gate output lives in the concat buffer
         else:
             tab = self._exchange_table(part, "h0", d, keep is not None) if gather_h0 else None
@@ -677,11 +709,18 @@ class LiteralKG(nn.Module):
             gz = torch.empty((n_own, 2 * d), dtype=torch.float32, device=dev)      # activated (g, z) pairs
         _, h0_planes = self.gate_embeddings(out=h0, planes_window=(cat_planes, 0, d), rows=rows,
                                             packed=None if pre is None else pre["packed"], gz_out=gz)
+        extra = {}
+        if combined:                                      # z = h0 @ Pb next to h0 (the residual GEMM only needs parameters)
+            folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
+            h0q, offsets, zoff = self._residual_gemm(h0_planes, folds)
+            c0 = self.aggregator_layers[0].out_dim
+            h0_tab[rb:re, d:].copy_(h0q[:, zoff:zoff + c0])
+            extra = dict(combined=True, folds=folds, h0q=h0q, offsets=offsets, zoff=zoff)
         work = None
         if gather_h0:
             work = peer.start() if peer is not None else part.all_gather_rows(h0_tab, async_op=True)
         return dict(cat=cat, h0_tab=h0_tab, h0=h0, cat_planes=cat_planes, h0_planes=h0_planes, xcol=xcol, gz=gz,
-                    work=work)
+                    work=work, **extra)
 
     def _gat_embeddings_native(self, keep: Optional[dict] = None, pre: Optional[dict] = None) -> torch.Tensor:
         """``pre`` (training): {folds, wq, cq, offsets, zcol, packed} built under autograd by the caller (detached
@@ -710,22 +749,23 @@ class LiteralKG(nn.Module):
         h0q = None
         offsets: List[int] = []
         zoff = -1                                         # column of the pre-projected layer-1 sum term in h0q
-        if pre is not None:
+        combined = bool(st.get("combined", False))
+        if combined:
+            folds, h0q, offsets, zoff = st["folds"], st["h0q"], st["offsets"], st["zoff"]
+        elif pre is not None:
             folds, wq, cq, offsets, zoff = pre["folds"], pre["wq"], pre["cq"], pre["offsets"], pre["zcol"]
             if wq is not None:
                 h0q = ops.linear([h0_planes], wq, cq)
         else:
             folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
             if self.use_residual and self.n_layers > 0:
-                qkey = tuple(id(f) for f in folds)                 # the fold dicts are cached per parameter version
-                if self._h0q_cache is None or self._h0q_cache[0] != qkey:
-                    self._h0q_cache = (qkey, *self._stack_q(folds), folds)
-                _, wq, cq, offsets, zoff, _ = self._h0q_cache
-                h0q = ops.linear([h0_planes], wq, cq)              # this rank's rows
+                h0q, offsets, zoff = self._residual_gemm(h0_planes, folds)     # this rank's rows
 
         c0 = self.aggregator_layers[0].out_dim if self.n_layers > 0 else 0
         z_tab = None
-        if zoff >= 0:
+        if combined:
+            z_tab = h0_tab[:, d:d + c0]                            # travels with h0: nothing to exchange
+        elif zoff >= 0:
             if part is None:
                 z_tab = h0q[:, zoff:zoff + c0]                     # [N, C] view, row index == entity id
             else:
@@ -736,7 +776,7 @@ class LiteralKG(nn.Module):
             if self.scale_gat_dim is None:
                 cat[:, :d] = h0
 
-        x = h0_tab
+        x = h0_tab[:, :d] if combined else h0_tab
         col = d
         for k, (layer, f) in enumerate(zip(self.aggregator_layers, folds)):
             c = layer.out_dim
@@ -756,7 +796,8 @@ class LiteralKG(nn.Module):
                 saved = {}
                 keep.setdefault("layers", []).append(saved)
                 saved.update(x=x, y=x_out)
-            layer.run(plan, a_values, x, f, r1, r2, x_out, cat[:, col:col + c], fold_ego=(h0q is not None and k == 0),
+            layer.run(plan, a_values, x, f, r1, r2, x_out, None if cat is None else cat[:, col:col + c],
+                      fold_ego=(h0q is not None and k == 0),
                       xn_planes=_lib.PlanesView(cat_planes, xcol + col - d, c, rec=xn_all.rec), rows=rows,
                       z=z_tab if k == 0 else None, saved=saved)
             if exchange:
