@@ -116,6 +116,13 @@ const char* lkg_last_error(void);
 /* LKG_OK iff `device` is an sm_100 GPU (B200).  Host call. */
 int lkg_device_check(int device);
 
+/* Stores `nbytes` (multiple of 16) of local device memory into n_dst <= 8 destinations that are PEER-mapped device
+ * pointers (the same block of every peer's copy of a symmetric-memory exchange table) with one kernel on n_ctas CTAs:
+ * every 16-byte vector is loaded once and stored over NVLink to all destinations.  dst: HOST array of device pointers.
+ * Completion is stream ordered; visibility at the peers needs the caller's cross-rank barrier afterwards. */
+int lkg_peer_push(const void* src, int64_t nbytes, void* const* dst /*host array*/, int32_t n_dst, int32_t n_ctas,
+                  void* stream);
+
 /* ---- graph plan: replaces DataLoader.construct_data's tensor products + the coalesce/sort that
  *      torch.sparse.softmax performs inside update_attention (dataloader.py:369-424,
  *      model.py:462-470) ------------------------------------------------------------------------ */

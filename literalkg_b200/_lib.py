@@ -38,6 +38,7 @@ SIGNATURES = {
     "lkg_abi_version": (C.c_int, []),
     "lkg_last_error": (C.c_char_p, []),
     "lkg_device_check": (C.c_int, [C.c_int]),
+    "lkg_peer_push": (C.c_int, [vp, i64, C.POINTER(vp), i32, i32, vp]),
     "lkg_plan_workspace_bytes": (C.c_int, [i64, i64, C.POINTER(C.c_size_t)]),
     "lkg_plan_build": (C.c_int, [vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                  C.c_size_t, vp]),

@@ -205,6 +205,14 @@ class PeerTable:
         # peer at a time.  LKG_PUSH_STREAMS overrides for experiments.)
         n_copy = max(1, min(int(os.environ.get("LKG_PUSH_STREAMS", "1")), max(1, part.world - 1)))
         self.copy_streams = [self.stream] + [torch.cuda.Stream(device=device) for _ in range(n_copy - 1)]
+        # Large tables: a fraction of the row block goes out through lkg_peer_push -- a kernel on a few SMs that stores
+        # straight into the peers' copies -- at the same time as the copy engines move the rest, so that both paths
+        # load the NVLinks together.  (LKG_PUSH_SM_FRACTION / LKG_PUSH_SM_CTAS for experiments; 0 = copy engines only.)
+        big = self.rows * self.d * 4 >= (256 << 20) and part.world > 2
+        self.sm_fraction = float(os.environ.get("LKG_PUSH_SM_FRACTION", "0.4" if big else "0"))
+        self.sm_ctas = int(os.environ.get("LKG_PUSH_SM_CTAS", "24"))
+        self.sm_stream = torch.cuda.Stream(device=device) if self.sm_fraction > 0 else None
+        self.peer_ptrs = list(self.hdl.buffer_ptrs)
         self.calls = 0
 
     def begin(self):
@@ -231,6 +239,20 @@ class _PeerHandle:
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record(o.stream)
         b, e = part.begin, part.end
+        if e > b and o.sm_stream is not None:            # the tail of the block: pushed by SMs, concurrently
+            import ctypes as C
+            from . import _lib
+            m = b + int((e - b) * (1.0 - o.sm_fraction))
+            o.sm_stream.wait_stream(main)
+            nbytes = (e - m) * o.d * 4
+            if nbytes > 0 and nbytes % 16 == 0:
+                offb = (self.slot * o.rows + m) * o.d * 4
+                peers = [r for r in range(part.world) if r != part.rank]
+                arr = (C.c_void_p * len(peers))(*[o.peer_ptrs[r] + offb for r in peers])
+                with torch.cuda.stream(o.sm_stream):
+                    _lib.check(_lib.load().lkg_peer_push(o.t[self.slot, m:e].data_ptr(), nbytes, arr, len(peers), o.sm_ctas,
+                                                         o.sm_stream.cuda_stream))
+                e = m
         if e > b:
             rows = o.t[self.slot, b:e]
             off = (self.slot * o.rows + b) * o.d
@@ -240,6 +262,8 @@ class _PeerHandle:
                     o.hdl.get_buffer(r, (e - b, o.d), torch.float32, off).copy_(rows, non_blocking=True)
         for cs in o.copy_streams[1:]:
             o.stream.wait_stream(cs)
+        if o.sm_stream is not None:
+            o.stream.wait_stream(o.sm_stream)
         with torch.cuda.stream(o.stream):
             o.hdl.barrier()                             # stream ordered: every rank's pushes have landed
             self.done = torch.cuda.Event(enable_timing=timed)
