@@ -205,11 +205,11 @@ class PeerTable:
         # peer at a time.  LKG_PUSH_STREAMS overrides for experiments.)
         n_copy = max(1, min(int(os.environ.get("LKG_PUSH_STREAMS", "1")), max(1, part.world - 1)))
         self.copy_streams = [self.stream] + [torch.cuda.Stream(device=device) for _ in range(n_copy - 1)]
-        # Large tables: a fraction of the row block goes out through lkg_peer_push -- a kernel on a few SMs that stores
-        # straight into the peers' copies -- at the same time as the copy engines move the rest, so that both paths
-        # load the NVLinks together.  (LKG_PUSH_SM_FRACTION / LKG_PUSH_SM_CTAS for experiments; 0 = copy engines only.)
-        big = self.rows * self.d * 4 >= (256 << 20) and part.world > 2
-        self.sm_fraction = float(os.environ.get("LKG_PUSH_SM_FRACTION", "0.4" if big else "0"))
+        # Optional (LKG_PUSH_SM_FRACTION > 0): a fraction of the row block goes out through lkg_peer_push -- a kernel on
+        # LKG_PUSH_SM_CTAS CTAs that stores straight into the peers' copies -- at the same time as the copy engines move
+        # the rest.  Measured at 8 GPUs (r02t, 1.33 GB table): pass 4.03 ms with the copy engines alone, 4.28 ms with
+        # 40 % on 24 CTAs, 4.51 ms with 70 % -- the SM stores do not add NVLink throughput here, so the default is off.
+        self.sm_fraction = float(os.environ.get("LKG_PUSH_SM_FRACTION", "0"))
         self.sm_ctas = int(os.environ.get("LKG_PUSH_SM_CTAS", "24"))
         self.sm_stream = torch.cuda.Stream(device=device) if self.sm_fraction > 0 else None
         self.peer_ptrs = list(self.hdl.buffer_ptrs)
