@@ -184,6 +184,14 @@ int lkg_row_softmax(const int32_t* rowptr, int64_t n_rows, float* values, void* 
 /* rec <- record of max(|src[rows or all, 0:k]|, floor).  src fp32 [*, ld], optional int64 row gather. */
 int lkg_scale_from_data(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
                         float floor, float* rec, void* stream);
+/* Records built by the kernels that PRODUCE a matrix (no pass re-reads it): zero a float[LKG_SCALE_FLOATS], hand it to
+ * the producers' `amax` arguments (lkg_leaky_bwd, lkg_layer_bwd_rows, lkg_bi_bwd_rows, lkg_gate_bwd) and / or raise it
+ * with lkg_absmax_accumulate for the parts other kernels wrote, then lkg_scale_finish(floor, rec) turns element 0 into
+ * the record of max(element 0, floor).  A record only has to BOUND its data: every factor of two of slack costs one of
+ * the 36 bits the hi/lo pair resolves below the bound. */
+int lkg_absmax_accumulate(const float* src, int64_t ld, const int64_t* rows /*nullable*/, int64_t m, int32_t k,
+                          float* rec, void* stream);
+int lkg_scale_finish(float floor, float* rec, void* stream);
 /* rec <- record of max(bound, other[0]) where `other` is an optional existing record (e.g. the gate output
  * is bounded by max(1, max|entity|): a convex mix of the entity row and a tanh). */
 int lkg_scale_from_bound(float bound, const float* other /*nullable*/, float* rec, void* stream);
@@ -265,16 +273,20 @@ int lkg_spmm_coo(const int32_t* seg, const int32_t* src, const int32_t* perm /*n
 /* Row-local backward of one aggregator layer (model.py:108-130, 161-164 and F.normalize of :305):
  *   dy = dy_in + d normalize(y)^T dyn;  dropout mask;  LayerNorm backward;  LeakyReLU backward of both paths.
  * y: the layer output, o: the pre-activations saved by lkg_aggregate_fwd ([o1 | o2], has_o2 for
- * bi-interaction).  Writes d_o = [do1 | do2] and ACCUMULATES dgamma_dbeta[2*c] (LayerNorm weight / bias). */
+ * bi-interaction).  Writes d_o = [do1 | do2] and ACCUMULATES dgamma_dbeta[2*c] (LayerNorm weight / bias).
+ * amax / amax2 (nullable): scale records under construction (zeroed float[LKG_SCALE_FLOATS]) whose element 0 is raised
+ * to max|d_o| -- see lkg_scale_finish. */
 int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const float* y, int64_t ld_y, const float* o,
                        int64_t ld_o, const float* mask /*nullable [n, c]*/, const float* dy_in /*nullable*/,
                        int64_t ld_dy, const float* dyn /*nullable*/, int64_t ld_dyn, const float* ln_weight,
-                       float* d_o, int64_t ld_do, float* dgamma_dbeta, void* stream);
+                       float* d_o, int64_t ld_do, float* dgamma_dbeta, float* amax, float* amax2, void* stream);
 /* Product path of bi-interaction (model.py:127-128): V = do2 @ P2^T;  w_out = V * x (the operand of the
- * A^T gather);  dx (+)= V * side;  xs_out (nullable) = x * side, the row operand of d P2 = (x * side)^T do2. */
+ * A^T gather);  dx (+)= V * side;  xs_out (nullable) = x * side, the row operand of d P2 = (x * side)^T do2;
+ * xs_amax (nullable): record under construction raised to max|xs_out|. */
 int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o2, int64_t ld_do, const float* p2 /*[d, c]*/,
                     const float* x, int64_t ld_x, const float* side, int64_t ld_side, float* w_out, int64_t ld_w,
-                    float* dx, int64_t ld_dx, int32_t accumulate, float* xs_out, int64_t ld_xs, void* stream);
+                    float* dx, int64_t ld_dx, int32_t accumulate, float* xs_out, int64_t ld_xs, float* xs_amax,
+                    void* stream);
 /* Parameter gradients: out[i, j] += sum_rows x[row, i] * (x2 ? x2[row, i] : 1) * y[row, j]; x == NULL with dx == 1
  * gives the column sums of y (bias gradients).  out [dx, cy] is accumulated into (zero it first). */
 int lkg_xt_y(const float* x /*nullable*/, int64_t ld_x, const float* x2 /*nullable*/, int64_t ld_x2, int32_t dx,
@@ -286,12 +298,15 @@ int lkg_xt_y_planes(const lkg_planes* x, const lkg_planes* y, int64_t n_rows, fl
 /* out[j] += sum_rows y[row, j]  (bias gradients). */
 int lkg_colsum(const float* y, int64_t ld_y, int64_t n, int32_t c, float* out, void* stream);
 /* Literal gate backward, elementwise part (gate.py:22-28): from dh = d loss / d out and the saved (g, z) pairs:
- * d_pre (interleaved like w_pair's rows) and the direct entity term d_ent = dh * (1 - z). */
+ * d_pre (interleaved like w_pair's rows) and the direct entity term d_ent = dh * (1 - z); pre_amax (nullable):
+ * record under construction raised to max|d_pre|. */
 int lkg_gate_bwd(const float* dh, int64_t ld_dh, const float* gz, int64_t ld_gz, const float* ent, int64_t ld_ent,
-                 int64_t n, int32_t dim, float* d_pre, int64_t ld_pre, float* d_ent, int64_t ld_de, void* stream);
-/* d_pre = grad * LeakyReLU'(out) from the activated output (model.py:311). */
+                 int64_t n, int32_t dim, float* d_pre, int64_t ld_pre, float* d_ent, int64_t ld_de, float* pre_amax,
+                 void* stream);
+/* d_pre = grad * LeakyReLU'(out) from the activated output (model.py:311); amax (nullable): record under
+ * construction raised to max|d_pre|. */
 int lkg_leaky_bwd(const float* grad, int64_t ld_g, const float* out, int64_t ld_out, int64_t n, int32_t c,
-                  float* d_pre, int64_t ld_d, void* stream);
+                  float* d_pre, int64_t ld_d, float* amax, void* stream);
 
 /* ---- loss heads of the training modes: value and gradients over one minibatch ---------------------------------
  * Both losses are batch means (+ l2_lambda * the reference's _L2_loss_mean terms).  `loss` (nullable) is a device

@@ -50,6 +50,8 @@ SIGNATURES = {
     "lkg_attn_run_logits": (C.c_int, [vp, vp, i64, vp, vp, i64, i32, vp, i64, vp, vp]),
     "lkg_row_softmax": (C.c_int, [vp, i64, vp, vp]),
     "lkg_scale_from_data": (C.c_int, [vp, i64, vp, i64, i32, C.c_float, vp, vp]),
+    "lkg_absmax_accumulate": (C.c_int, [vp, i64, vp, i64, i32, vp, vp]),
+    "lkg_scale_finish": (C.c_int, [C.c_float, vp, vp]),
     "lkg_scale_from_bound": (C.c_int, [C.c_float, vp, vp, vp]),
     "lkg_split_planes": (C.c_int, [vp, i64, vp, i64, i32, vp, vp, i64, i64, vp]),
     "lkg_packed_weight_cols": (C.c_int, [C.POINTER(i32), i32, C.POINTER(i32)]),
@@ -65,13 +67,13 @@ SIGNATURES = {
     "lkg_plan_transpose_workspace_bytes": (C.c_int, [i64, C.POINTER(C.c_size_t)]),
     "lkg_plan_transpose": (C.c_int, [C.POINTER(LkgGraph), vp, vp, vp, vp, C.c_size_t, vp]),
     "lkg_spmm_coo": (C.c_int, [vp, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp]),
-    "lkg_layer_bwd_rows": (C.c_int, [i64, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, i64, vp, vp]),
-    "lkg_bi_bwd_rows": (C.c_int, [i64, i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp]),
+    "lkg_layer_bwd_rows": (C.c_int, [i64, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp]),
+    "lkg_bi_bwd_rows": (C.c_int, [i64, i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp, vp]),
     "lkg_xt_y": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, i32, i64, vp, i64, vp]),
     "lkg_xt_y_planes": (C.c_int, [C.POINTER(LkgPlanes), C.POINTER(LkgPlanes), i64, vp, i64, vp]),
     "lkg_colsum": (C.c_int, [vp, i64, i64, i32, vp, vp]),
-    "lkg_gate_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, i64, vp, i64, vp]),
-    "lkg_leaky_bwd": (C.c_int, [vp, i64, vp, i64, i64, i32, vp, i64, vp]),
+    "lkg_gate_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, i64, vp, i64, vp, vp]),
+    "lkg_leaky_bwd": (C.c_int, [vp, i64, vp, i64, i64, i32, vp, i64, vp, vp]),
     "lkg_sample_batch": (C.c_int, [vp, vp, vp, vp, i64, vp, i64, i32, i32, C.c_uint64, i32, vp, vp, vp, vp, vp, vp]),
     "lkg_bpr_loss": (C.c_int, [vp, i64, i32, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp]),
     "lkg_transr_loss": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp, i64, C.c_float, vp, vp, vp, i64, vp, vp,

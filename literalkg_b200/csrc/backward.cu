@@ -159,6 +159,14 @@ int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
     return LKG_OK;
 }
 
+// Producer-side scale records: a kernel that writes a gradient matrix raises rec[0] (the bits of a non-negative
+// float order like unsigned integers) so that no separate absmax pass has to re-read what it wrote; lkg_scale_finish
+// completes the record.  NaNs are dropped by fmaxf like in the absmax pass.
+__device__ __forceinline__ void raise_absmax(float* rec, float mx) {
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<uint32_t*>(rec), __float_as_uint(mx));
+}
+
 // ---- row backward of one aggregator layer ----------------------------------------------------------------------
 struct LayerBwdParams {
     int64_t n;
@@ -171,6 +179,8 @@ struct LayerBwdParams {
     const float* ln_w;
     float* d_o;          int64_t ld_do;      // out: [do1 | do2]
     float* dgb;                              // out (accumulated): [dgamma (c) | dbeta (c)]
+    float* amax;                             // nullable: raw absmax of d_o (scale record under construction)
+    float* amax2;                            // nullable: a second record that covers d_o (the buffer it is a part of)
 };
 
 template <int NC>
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(256) layer_bwd_rows_kernel(LayerBwdParams p) {
         const int ch = lane + 32 * c;
         lw[c] = ch < C ? __ldg(p.ln_w + ch) : 0.f;
     }
+    float amax = 0.f;
     const int64_t stride = (int64_t)gridDim.x * 8;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n; row += stride) {
         float o1[NC], o2[NC], e[NC], y[NC], g[NC];
@@ -241,9 +252,22 @@ __global__ void __launch_bounds__(256) layer_bwd_rows_kernel(LayerBwdParams p) {
             const int ch = lane + 32 * c;
             if (ch < C) {
                 const float de = (dhat[c] - m1 - ehat[c] * m2) * rstd;
-                p.d_o[row * p.ld_do + ch] = de * (o1[c] > 0.f ? 1.f : 0.01f);
-                if (p.has_o2) p.d_o[row * p.ld_do + C + ch] = de * (o2[c] > 0.f ? 1.f : 0.01f);
+                const float d1 = de * (o1[c] > 0.f ? 1.f : 0.01f);
+                p.d_o[row * p.ld_do + ch] = d1;
+                amax = fmaxf(amax, fabsf(d1));
+                if (p.has_o2) {
+                    const float d2 = de * (o2[c] > 0.f ? 1.f : 0.01f);
+                    p.d_o[row * p.ld_do + C + ch] = d2;
+                    amax = fmaxf(amax, fabsf(d2));
+                }
             }
+        }
+    }
+    if (p.amax || p.amax2) {
+        amax = warp_max(amax);
+        if (lane == 0 && amax > 0.f) {
+            if (p.amax) atomicMax(reinterpret_cast<uint32_t*>(p.amax), __float_as_uint(amax));
+            if (p.amax2) atomicMax(reinterpret_cast<uint32_t*>(p.amax2), __float_as_uint(amax));
         }
     }
 #pragma unroll
@@ -274,6 +298,7 @@ struct BiBwdParams {
     float* xs_out;       int64_t ld_xs;      // nullable: x * side, the row operand of d P2 = (x * side)^T do2
     int accumulate;
     int ps;                                  // padded row stride of P2 in shared memory (floats), = 4 * odd
+    float* xs_amax;                          // nullable: raw absmax of xs_out
 };
 
 // One warp per row.  The row's do2 (<= 64 values) is broadcast from shared memory into registers once; lane i then
@@ -291,6 +316,7 @@ __global__ void __launch_bounds__(256) bi_bwd_rows_kernel(BiBwdParams p) {
         sp[i] = c < p.c ? p.p2[r * p.c + c] : 0.f;
     }
     __syncthreads();
+    float amax = 0.f;
     const int64_t stride = (int64_t)gridDim.x * 8;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n; row += stride) {
         for (int c = lane; c < 4 * CQ; c += 32) sdo[c] = c < p.c ? __ldg(p.d_o2 + row * p.ld_do + c) : 0.f;
@@ -328,12 +354,17 @@ __global__ void __launch_bounds__(256) bi_bwd_rows_kernel(BiBwdParams p) {
                     }
                     const float v = v0 + v1;
                     p.w_out[row * p.ld_w + i] = v * xv[u];
-                    if (p.xs_out) p.xs_out[row * p.ld_xs + i] = xv[u] * sv[u];
+                    if (p.xs_out) {
+                        const float xsv = xv[u] * sv[u];
+                        p.xs_out[row * p.ld_xs + i] = xsv;
+                        amax = fmaxf(amax, fabsf(xsv));
+                    }
                     p.dx[row * p.ld_dx + i] = fmaf(v, sv[u], dv[u]);
                 }
             }
         }
     }
+    if (p.xs_amax) raise_absmax(p.xs_amax, amax);
 }
 
 // ---- parameter gradients: out[i, j] += sum_rows x[row, i] (* x2[row, i]) * y[row, j] ------------------------------
@@ -414,8 +445,10 @@ __global__ void __launch_bounds__(256) xt_y_kernel(XtyParams p) {
 //   d_pre[2j] = dh z (1 - g^2)   d_pre[2j+1] = dh (g - e) z (1 - z)   d_ent = dh (1 - z)
 __global__ void gate_bwd_kernel(const float* __restrict__ dh, int64_t ld_dh, const float* __restrict__ gz, int64_t ld_gz,
                                 const float* __restrict__ ent, int64_t ld_ent, int64_t n, int dim,
-                                float* __restrict__ d_pre, int64_t ld_pre, float* __restrict__ d_ent, int64_t ld_de) {
+                                float* __restrict__ d_pre, int64_t ld_pre, float* __restrict__ d_ent, int64_t ld_de,
+                                float* __restrict__ pre_amax) {
     const int64_t total = n * dim;
+    float amax = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / dim;
         const int j = (int)(i - row * dim);
@@ -423,20 +456,27 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dh, int64_t ld_dh, con
         const float g = a.x, z = a.y;
         const float d = __ldg(dh + row * ld_dh + j);
         const float e = __ldg(ent + row * ld_ent + j);
-        reinterpret_cast<float2*>(d_pre + row * ld_pre)[j] = make_float2(d * z * (1.f - g * g), d * (g - e) * z * (1.f - z));
+        const float2 dp = make_float2(d * z * (1.f - g * g), d * (g - e) * z * (1.f - z));
+        reinterpret_cast<float2*>(d_pre + row * ld_pre)[j] = dp;
+        amax = fmaxf(amax, fmaxf(fabsf(dp.x), fabsf(dp.y)));
         d_ent[row * ld_de + j] = d * (1.f - z);
     }
+    if (pre_amax) raise_absmax(pre_amax, amax);
 }
 
 // dpre = g * leaky'(out)   (sign(out) == sign of the pre-activation)
 __global__ void leaky_bwd_kernel(const float* __restrict__ g, int64_t ld_g, const float* __restrict__ out, int64_t ld_out,
-                                 int64_t n, int c, float* __restrict__ d, int64_t ld_d) {
+                                 int64_t n, int c, float* __restrict__ d, int64_t ld_d, float* __restrict__ d_amax) {
     const int64_t total = n * c;
+    float amax = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / c;
         const int j = (int)(i - row * c);
-        d[row * ld_d + j] = __ldg(g + row * ld_g + j) * (__ldg(out + row * ld_out + j) > 0.f ? 1.f : 0.01f);
+        const float v = __ldg(g + row * ld_g + j) * (__ldg(out + row * ld_out + j) > 0.f ? 1.f : 0.01f);
+        d[row * ld_d + j] = v;
+        amax = fmaxf(amax, fabsf(v));
     }
+    if (d_amax) raise_absmax(d_amax, amax);
 }
 
 }  // namespace
@@ -501,12 +541,13 @@ extern "C" int lkg_spmm_coo(const int32_t* seg, const int32_t* src, const int32_
 extern "C" int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const float* y, int64_t ld_y, const float* o,
                                   int64_t ld_o, const float* mask, const float* dy_in, int64_t ld_dy,
                                   const float* dyn, int64_t ld_dyn, const float* ln_weight, float* d_o, int64_t ld_do,
-                                  float* dgamma_dbeta, void* stream_) {
+                                  float* dgamma_dbeta, float* amax, float* amax2, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(y && o && ln_weight && d_o && dgamma_dbeta && c > 0, "null argument");
     if (c > 64) LKG_FAIL(LKG_ERR_UNSUPPORTED, "layer backward: d_out %d > 64", c);
-    LayerBwdParams p{n, c, has_o2, y, ld_y, o, ld_o, mask, dy_in, ld_dy, dyn, ld_dyn, ln_weight, d_o, ld_do, dgamma_dbeta};
+    LayerBwdParams p{n, c, has_o2, y, ld_y, o, ld_o, mask, dy_in, ld_dy, dyn, ld_dyn, ln_weight, d_o, ld_do, dgamma_dbeta,
+                     amax, amax2};
     const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8);
     if (c <= 32) layer_bwd_rows_kernel<1><<<grid, 256, 0, stream>>>(p);
     else layer_bwd_rows_kernel<2><<<grid, 256, 0, stream>>>(p);
@@ -517,7 +558,7 @@ extern "C" int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const fl
 extern "C" int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o2, int64_t ld_do, const float* p2,
                                const float* x, int64_t ld_x, const float* side, int64_t ld_side, float* w_out,
                                int64_t ld_w, float* dx, int64_t ld_dx, int32_t accumulate, float* xs_out, int64_t ld_xs,
-                               void* stream_) {
+                               float* xs_amax, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(d_o2 && p2 && x && side && w_out && dx && d > 0 && c > 0, "null argument");
@@ -527,7 +568,8 @@ extern "C" int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o
     if ((ps / 4) % 2 == 0) ps += 4;                           // 4 * odd
     const size_t smem = ((size_t)d * ps + 8 * 64) * sizeof(float);
     if (smem > 227 * 1024) LKG_FAIL(LKG_ERR_UNSUPPORTED, "bi backward: d_in %d x d_out %d does not fit shared memory", d, c);
-    BiBwdParams p{n, d, c, d_o2, ld_do, p2, x, ld_x, side, ld_side, w_out, ld_w, dx, ld_dx, xs_out, ld_xs, accumulate, ps};
+    BiBwdParams p{n, d, c, d_o2, ld_do, p2, x, ld_x, side, ld_side, w_out, ld_w, dx, ld_dx, xs_out, ld_xs, accumulate, ps,
+                  xs_out ? xs_amax : nullptr};
     const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
     const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * per_sm);
 #define LKG_BI_CASE(Q)                                                                                              \
@@ -563,23 +605,24 @@ extern "C" int lkg_xt_y(const float* x, int64_t ld_x, const float* x2, int64_t l
 
 extern "C" int lkg_gate_bwd(const float* dh, int64_t ld_dh, const float* gz, int64_t ld_gz, const float* ent,
                             int64_t ld_ent, int64_t n, int32_t dim, float* d_pre, int64_t ld_pre, float* d_ent,
-                            int64_t ld_de, void* stream_) {
+                            int64_t ld_de, float* pre_amax, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(dh && gz && ent && d_pre && d_ent && dim > 0, "null argument");
     LKG_REQUIRE(ld_gz % 2 == 0 && ld_pre % 2 == 0 && (reinterpret_cast<uintptr_t>(gz) & 7u) == 0 &&
                     (reinterpret_cast<uintptr_t>(d_pre) & 7u) == 0, "gate backward: (g, z) pairs must be 8-byte aligned");
-    gate_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(dh, ld_dh, gz, ld_gz, ent, ld_ent, n, dim, d_pre, ld_pre, d_ent, ld_de);
+    gate_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(dh, ld_dh, gz, ld_gz, ent, ld_ent, n, dim, d_pre, ld_pre, d_ent, ld_de,
+                                                            pre_amax);
     LKG_LAUNCH_CHECK("gate_bwd_kernel");
     return LKG_OK;
 }
 
 extern "C" int lkg_leaky_bwd(const float* grad, int64_t ld_g, const float* out, int64_t ld_out, int64_t n, int32_t c,
-                             float* d_pre, int64_t ld_d, void* stream_) {
+                             float* d_pre, int64_t ld_d, float* amax, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(grad && out && d_pre && c > 0, "null argument");
-    leaky_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(grad, ld_g, out, ld_out, n, c, d_pre, ld_d);
+    leaky_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(grad, ld_g, out, ld_out, n, c, d_pre, ld_d, amax);
     LKG_LAUNCH_CHECK("leaky_bwd_kernel");
     return LKG_OK;
 }

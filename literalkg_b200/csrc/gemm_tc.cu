@@ -646,35 +646,59 @@ __device__ __forceinline__ void write_record(float* rec, float amax) {
     rec[2] = ldexpf(1.f, -e);
 }
 
-// VEC: rows are 16-byte aligned -> one warp per row, float4 loads; otherwise a flat scalar grid-stride loop
-template <bool VEC>
-__global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows, int64_t m,
-                              int k, float floor_, float* __restrict__ rec) {
+// VEC: rows are 16-byte aligned -> the [m, k / 4] matrix of float4 units is walked flat (narrow matrices keep every
+// lane busy), four independent loads per thread and step; the k % 4 tail columns and the unaligned case go through
+// a scalar loop.  I: index type (uint32 while 4 strides past the end still fit).
+// FINISH: the last block to leave turns the absmax into the record (rec was zeroed by the caller); otherwise the
+// kernel only raises rec[0] (atomic max on the bits of a non-negative float) and lkg_scale_finish completes it.
+template <typename I>
+__device__ __forceinline__ float absmax_units(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
+                                              int64_t m, int k) {
+    constexpr int U = 4;
+    const I kv = (I)(k >> 2);
+    const I total = (I)m * kv;
+    const I stride = (I)gridDim.x * blockDim.x;
     float mx = 0.f;
-    if (VEC) {
-        const int lane = threadIdx.x & 31;
-        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        const int kv = k >> 2;
-        for (int64_t r = warp; r < m; r += nwarps) {
-            const float* row = src + (rows ? rows[r] : r) * ld;
-            for (int v = lane; v < kv; v += 32) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(row) + v);
-                // fmaxf drops a NaN operand: NaNs do not poison the scale
-                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const I j = i + (I)u * stride;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < total) {
+                const I r = j / kv;
+                const I v = j - r * kv;
+                x[u] = __ldg(reinterpret_cast<const float4*>(src + (rows ? rows[r] : (int64_t)r) * ld) + v);
             }
-            for (int c = 4 * kv + lane; c < k; c += 32) mx = fmaxf(mx, fabsf(__ldg(row + c)));
         }
-    } else {
-        const int64_t total = m * k;
+#pragma unroll
+        for (int u = 0; u < U; ++u)   // fmaxf drops a NaN operand: NaNs do not poison the scale
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x[u].x), fabsf(x[u].y))), fmaxf(fabsf(x[u].z), fabsf(x[u].w)));
+    }
+    return mx;
+}
+
+template <bool VEC, bool FINISH>
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t ld,
+                                                     const int64_t* __restrict__ rows, int64_t m, int k, float floor_,
+                                                     float* __restrict__ rec) {
+    float mx = 0.f;
+    const int c_begin = VEC ? (k & ~3) : 0;             // columns the scalar loop covers
+    if (VEC)
+        mx = (m * (int64_t)(k >> 2) < (int64_t)1 << 30) ? absmax_units<uint32_t>(src, ld, rows, m, k)
+                                                        : absmax_units<uint64_t>(src, ld, rows, m, k);
+    const int kt = k - c_begin;
+    if (kt > 0) {
+        const int64_t total = m * kt;
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / k;
-            mx = fmaxf(mx, fabsf(src[(rows ? rows[r] : r) * ld + (i - r * k)]));
+            const int64_t r = i / kt;
+            mx = fmaxf(mx, fabsf(src[(rows ? rows[r] : r) * ld + c_begin + (i - r * kt)]));
         }
     }
     mx = warp_max(mx);
     uint32_t* bits = reinterpret_cast<uint32_t*>(rec);
     if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(bits, __float_as_uint(mx));   // non-negative floats order like uints
+    if (!FINISH) return;
     // the last block to finish turns the absmax into the record
     __shared__ bool last;
     __syncthreads();
@@ -691,41 +715,78 @@ __global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, const i
     }
 }
 
+// rec[0] holds a raw absmax (producer kernels raise it with atomic max): complete the record in place
+__global__ void finish_record_kernel(float floor_, float* rec) {
+    float amax = rec[0];
+    if (!(amax < 3.0e38f)) amax = amax != amax ? 0.f : 3.0e38f;
+    write_record(rec, fmaxf(amax, floor_));
+}
+
 __global__ void bound_record_kernel(float bound, const float* __restrict__ other, float* __restrict__ rec) {
     write_record(rec, other ? fmaxf(bound, other[0]) : bound);
 }
 
-template <bool VEC>
-__global__ void split_planes_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
-                                    int64_t m, int k, const float* __restrict__ rec, __half* __restrict__ dst,
-                                    int64_t ldp, int64_t plane_stride) {
-    const float scale = __ldg(rec + 1);
-    if (VEC) {   // one warp per row, 8 columns per lane and step: two float4 in, one 16-byte store per plane
-        const int lane = threadIdx.x & 31;
-        const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        const int groups = (int)(ldp >> 3);
-        for (int64_t r = warp; r < m; r += nwarps) {
-            const float* row = src + (rows ? rows[r] : r) * ld;
-            __half* hrow = dst + r * ldp;
-            for (int gq = lane; gq < groups; gq += 32) {
-                const int c0 = 8 * gq;
-                float x[8];
+// VEC: 16-byte aligned rows and planes -> the [m, ld_planes / 8] matrix of 8-column groups is walked flat: two float4
+// in, one 16-byte store per plane, two groups per thread and step in flight (narrow operands keep every lane busy;
+// a group that lies in the zero padding only stores).
+template <typename I>
+__device__ __forceinline__ void split_groups(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ rows,
+                                             int64_t m, int k, float scale, __half* __restrict__ dst, int64_t ldp,
+                                             int64_t plane_stride) {
+    constexpr int U = 2;
+    const I groups = (I)(ldp >> 3);
+    const I total = (I)m * groups;
+    const I stride = (I)gridDim.x * blockDim.x;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+        float x[U][8];
+        I row[U];
+        int col[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const I j = i + (I)u * stride;
+            const bool ok = j < total;
+            const I r = ok ? j / groups : 0;
+            const int c0 = 8 * (int)(j - r * groups);
+            row[u] = r;
+            col[u] = ok ? c0 : -1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[u][q] = 0.f;
+            if (ok && c0 < k) {
+                const float* s = src + (rows ? rows[r] : (int64_t)r) * ld + c0;
                 if (c0 + 8 <= k) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(row + c0));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(row + c0) + 1);
-                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(s));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+                    x[u][0] = a.x; x[u][1] = a.y; x[u][2] = a.z; x[u][3] = a.w;
+                    x[u][4] = b.x; x[u][5] = b.y; x[u][6] = b.z; x[u][7] = b.w;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = c0 + j < k ? __ldg(row + c0 + j) : 0.f;
+                    for (int q = 0; q < 8; ++q)
+                        if (c0 + q < k) x[u][q] = __ldg(s + q);
                 }
-                __align__(16) __half h[8], l[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) split_f16(x[j] * scale, h[j], l[j]);
-                *reinterpret_cast<uint4*>(hrow + c0) = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(hrow + plane_stride + c0) = *reinterpret_cast<const uint4*>(l);
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (col[u] < 0) continue;
+            __align__(16) __half h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_f16(x[u][q] * scale, h[q], l[q]);
+            __half* hrow = dst + (int64_t)row[u] * ldp + col[u];
+            *reinterpret_cast<uint4*>(hrow) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(hrow + plane_stride) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, int64_t ld,
+                                                           const int64_t* __restrict__ rows, int64_t m, int k,
+                                                           const float* __restrict__ rec, __half* __restrict__ dst,
+                                                           int64_t ldp, int64_t plane_stride) {
+    const float scale = __ldg(rec + 1);
+    if (VEC) {
+        if (m * (ldp >> 3) < (int64_t)1 << 30) split_groups<uint32_t>(src, ld, rows, m, k, scale, dst, ldp, plane_stride);
+        else split_groups<uint64_t>(src, ld, rows, m, k, scale, dst, ldp, plane_stride);
     } else {
         const int64_t total = m * ldp;
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -827,16 +888,40 @@ inline int grid_1d(int64_t n) {
 
 using namespace lkg;
 
+namespace lkg {
+namespace {
+template <bool FINISH>
+int launch_absmax(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k, float floor_, float* rec,
+                  cudaStream_t stream) {
+    if (m > 0 && aligned16(src) && ld % 4 == 0 && k >= 4)
+        absmax_kernel<true, FINISH><<<grid_1d(m * (k / 4 + 3) / 4), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
+    else
+        absmax_kernel<false, FINISH><<<grid_1d(m * k), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
+    LKG_LAUNCH_CHECK("absmax_kernel");
+    return LKG_OK;
+}
+}  // namespace
+}  // namespace lkg
+
 extern "C" int lkg_scale_from_data(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
                                    float floor_, float* rec, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LKG_REQUIRE(rec && m >= 0 && k > 0 && (m == 0 || src) && floor_ >= 0.f, "bad scale arguments");
     LKG_CUDA(cudaMemsetAsync(rec, 0, LKG_SCALE_FLOATS * sizeof(float), stream));
-    if (m > 0 && aligned16(src) && ld % 4 == 0 && k >= 4)
-        absmax_kernel<true><<<grid_1d(m * 32), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
-    else
-        absmax_kernel<false><<<grid_1d(m * k), 256, 0, stream>>>(src, ld, rows, m, k, floor_, rec);
-    LKG_LAUNCH_CHECK("absmax_kernel");
+    return launch_absmax<true>(src, ld, rows, m, k, floor_, rec, stream);
+}
+
+extern "C" int lkg_absmax_accumulate(const float* src, int64_t ld, const int64_t* rows, int64_t m, int32_t k,
+                                     float* rec, void* stream_) {
+    LKG_REQUIRE(rec && m >= 0 && k > 0 && (m == 0 || src), "bad scale arguments");
+    if (m == 0) return LKG_OK;
+    return launch_absmax<false>(src, ld, rows, m, k, 0.f, rec, (cudaStream_t)stream_);
+}
+
+extern "C" int lkg_scale_finish(float floor_, float* rec, void* stream_) {
+    LKG_REQUIRE(rec && floor_ >= 0.f, "bad scale arguments");
+    finish_record_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(floor_, rec);
+    LKG_LAUNCH_CHECK("finish_record_kernel");
     return LKG_OK;
 }
 
@@ -855,8 +940,8 @@ extern "C" int lkg_split_planes(const float* src, int64_t ld, const int64_t* row
                 "bad split arguments");
     if (m == 0) return LKG_OK;
     if (aligned16(src) && ld % 4 == 0 && aligned16(planes) && ld_planes % 8 == 0 && plane_stride % 8 == 0)
-        split_planes_kernel<true><<<grid_1d(m * 32), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
-                                                                       ld_planes, plane_stride);
+        split_planes_kernel<true><<<grid_1d(m * (ld_planes / 8 + 1) / 2), 256, 0, stream>>>(
+            src, ld, rows, m, k, rec, (__half*)planes, ld_planes, plane_stride);
     else
         split_planes_kernel<false><<<grid_1d(m * ld_planes), 256, 0, stream>>>(src, ld, rows, m, k, rec, (__half*)planes,
                                                                             ld_planes, plane_stride);

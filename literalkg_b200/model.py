@@ -886,12 +886,15 @@ class LiteralKG(nn.Module):
         h0_planes = keep["h0_planes"]
         grads: List[Optional[torch.Tensor]] = []
         g_out = g_out if (g_out.dtype == torch.float32 and g_out.stride(1) == 1) else _lib.f32c(g_out)
+        # scale records of the gradient matrices: raised by the kernels that write them, no absmax pass re-reads them
+        recs = torch.zeros((2 * L + 3, _lib.LKG_SCALE_FLOATS), **dict(dtype=torch.float32, device=dev))
+        dpre_rec, pre_rec, dmat_rec = recs[0], recs[1], recs[2]
 
         # ---- linear_gat + LeakyReLU (model.py:311) ----
         g_wg = g_bg = None
         if self.scale_gat_dim is not None:
-            dpre = ops.leaky_bwd(g_out, keep["out"])
-            dpre_pl = ops.split_planes(dpre)
+            dpre = ops.leaky_bwd(g_out, keep["out"], amax=dpre_rec)
+            dpre_pl = ops.split_planes(dpre, rec=ops.scale_finish(dpre_rec))
             g_wg = torch.zeros_like(self.linear_gat.weight)                     # [G, T] = dpre^T [h0 | xn_1 | ...]
             ops.xt_y_planes(dpre_pl, h0_planes, out=g_wg[:, :d])
             if total > d:
@@ -922,8 +925,11 @@ class LiteralKG(nn.Module):
             nt = 2 if has_o2 else 1
             d_o = dmat[:, offsets[k]:offsets[k] + nt * c] if residual else torch.empty((n, nt * c), **f32)
             dgb = torch.zeros(2 * c, **f32)
+            do_rec, xs_rec = recs[3 + 2 * k], recs[4 + 2 * k]
             ops.layer_bwd_rows(y_k, sv["o"], has_o2, sv["mask"], dy_in, dcat[:, col:col + c],
-                               layer.layer_normalize.weight.detach(), d_o, dgb)
+                               layer.layer_normalize.weight.detach(), d_o, dgb, amax=do_rec,
+                               amax2=dmat_rec if residual else None)
+            ops.scale_finish(do_rec)                           # bounds do1 and do2 alike
             do1 = d_o[:, :c]
             do2 = d_o[:, c:] if has_o2 else None
             fold_ego = residual and k == 0                     # ego @ Pa lives inside h0 @ Q
@@ -931,10 +937,12 @@ class LiteralKG(nn.Module):
             t1 = dmat[:, zcol:zcol + c] if z_path else torch.empty((n, c), **f32)
             t1.zero_()
             spmm_t(do1, t1)                                    # A^T do1: (A x) Pb backward without the wide gather
+            if z_path:
+                ops.absmax_accumulate(t1, dmat_rec)
             g = dict.fromkeys(self._FOLD_KEYS)
             use_pa = f["pa"] is not None and not fold_ego
             use_pb = not z_path
-            do1_pl = ops.split_planes(do1) if use_pa else None
+            do1_pl = ops.split_planes(do1, rec=do_rec) if use_pa else None
             t1_pl = ops.split_planes(t1) if use_pb else None
             if use_pa or use_pb:
                 xk_pl = h0_planes if k == 0 else ops.split_planes(x_k)
@@ -958,15 +966,16 @@ class LiteralKG(nn.Module):
                 ops.linear(segs, torch.cat(ws, dim=1).contiguous(), None, acc, out=dx)
             if has_o2:
                 wbuf, xs = torch.empty((n, dk), **f32), torch.empty((n, dk), **f32)
-                ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True, xs_out=xs)
+                ops.bi_bwd_rows(do2, f["p2"], x_k, sv["side"], wbuf, dx, accumulate=True, xs_out=xs, xs_amax=xs_rec)
                 spmm_t(wbuf, dx)
-                g["p2"] = ops.xt_y_planes(ops.split_planes(xs), ops.split_planes(do2))   # (x * side)^T do2
+                g["p2"] = ops.xt_y_planes(ops.split_planes(xs, rec=ops.scale_finish(xs_rec)),
+                                          ops.split_planes(do2, rec=do_rec))               # (x * side)^T do2
                 del wbuf, xs
             layer_grads[k] = (g, dgb[:c], dgb[c:])
             dy_in = dx
         g_wq = g_cq = None
         if residual:
-            dmat_pl = ops.split_planes(dmat)
+            dmat_pl = ops.split_planes(dmat, rec=ops.scale_finish(dmat_rec))
             g_wq = ops.xt_y_planes(dmat_pl, h0_planes)                          # [cols, embed_dim]
             g_cq = colsum(dmat)
             ops.linear([dmat_pl], wq.t().contiguous(), None, _lib.ACT_ACCUMULATE, out=dh0)
@@ -980,8 +989,8 @@ class LiteralKG(nn.Module):
             w_pair = pre["packed"][0]
             d_pre = torch.empty((n, 2 * d), **f32)
             g_ent = torch.empty((n, d), **f32)
-            ops.gate_bwd(dh0, keep["gz"], ent, d_pre, g_ent)
-            d_pre_pl = ops.split_planes(d_pre)
+            ops.gate_bwd(dh0, keep["gz"], ent, d_pre, g_ent, pre_amax=pre_rec)
+            d_pre_pl = ops.split_planes(d_pre, rec=ops.scale_finish(pre_rec))
             ops.linear([d_pre_pl], w_pair[:, :d].t().contiguous(), None, _lib.ACT_ACCUMULATE, out=g_ent)
             g_wpair = torch.zeros_like(w_pair)                  # [2 dim, dim + literals] = d_pre^T [ent | literals]
             ent_planes, lit_planes = keep["gate_operands"]

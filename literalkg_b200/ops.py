@@ -127,6 +127,27 @@ def scale_from_data(src: torch.Tensor, rows: Optional[torch.Tensor] = None, floo
     return rec
 
 
+def raw_record(device) -> torch.Tensor:
+    """A zeroed scale record for the kernels that raise its absmax while they PRODUCE the data (``amax`` arguments of
+    leaky_bwd / layer_bwd_rows / bi_bwd_rows / gate_bwd, or ``absmax_accumulate``); ``scale_finish`` completes it."""
+    return torch.zeros(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=device)
+
+
+def absmax_accumulate(src: torch.Tensor, rec: torch.Tensor) -> torch.Tensor:
+    """Raises the raw absmax of ``rec`` to cover ``src`` ([m, k] fp32, unit inner stride)."""
+    _rowmajor(src)
+    with _dev_guard(src, "scale_from_data"):
+        _lib.check(_lib.load().lkg_absmax_accumulate(src.data_ptr(), src.stride(0), None, src.shape[0], src.shape[1],
+                                                     rec.data_ptr(), _lib.stream()))
+    return rec
+
+
+def scale_finish(rec: torch.Tensor, floor: float = 0.0) -> torch.Tensor:
+    with _dev_guard(rec, "scale_finish"):
+        _lib.check(_lib.load().lkg_scale_finish(float(floor), rec.data_ptr(), _lib.stream()))
+    return rec
+
+
 def scale_from_bound(bound: float, device, other: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Scale record of max(bound, other.absmax) -- for planes whose magnitude is known a priori."""
     rec = torch.empty(_lib.LKG_SCALE_FLOATS, dtype=torch.float32, device=device)
@@ -486,7 +507,9 @@ def spmm_coo(coo, a_values: torch.Tensor, x: torch.Tensor, out: torch.Tensor) ->
 
 def layer_bwd_rows(y: torch.Tensor, o: torch.Tensor, has_o2: bool, mask: Optional[torch.Tensor],
                    dy_in: Optional[torch.Tensor], dyn: Optional[torch.Tensor], ln_weight: torch.Tensor,
-                   d_o: torch.Tensor, dgb: torch.Tensor) -> torch.Tensor:
+                   d_o: torch.Tensor, dgb: torch.Tensor, amax: Optional[torch.Tensor] = None,
+                   amax2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``amax`` / ``amax2``: raw records (``raw_record``) raised to max|d_o|."""
     n, c = y.shape
     for t in (y, o, d_o):
         _rowmajor(t)
@@ -495,12 +518,14 @@ def layer_bwd_rows(y: torch.Tensor, o: torch.Tensor, has_o2: bool, mask: Optiona
             n, c, int(has_o2), y.data_ptr(), y.stride(0), o.data_ptr(), o.stride(0), _lib.ptr(mask),
             _lib.ptr(dy_in), 0 if dy_in is None else _rowmajor(dy_in).stride(0),
             _lib.ptr(dyn), 0 if dyn is None else _rowmajor(dyn).stride(0),
-            _lib.f32c(ln_weight).data_ptr(), d_o.data_ptr(), d_o.stride(0), dgb.data_ptr(), _lib.stream()))
+            _lib.f32c(ln_weight).data_ptr(), d_o.data_ptr(), d_o.stride(0), dgb.data_ptr(), _lib.ptr(amax),
+            _lib.ptr(amax2), _lib.stream()))
     return d_o
 
 
 def bi_bwd_rows(d_o2: torch.Tensor, p2: torch.Tensor, x: torch.Tensor, side: torch.Tensor, w_out: torch.Tensor,
-                dx: torch.Tensor, accumulate: bool, xs_out: Optional[torch.Tensor] = None) -> None:
+                dx: torch.Tensor, accumulate: bool, xs_out: Optional[torch.Tensor] = None,
+                xs_amax: Optional[torch.Tensor] = None) -> None:
     n, d = x.shape
     c = d_o2.shape[1]
     for t in (d_o2, x, side, w_out, dx):
@@ -512,7 +537,7 @@ def bi_bwd_rows(d_o2: torch.Tensor, p2: torch.Tensor, x: torch.Tensor, side: tor
                                                x.stride(0), side.data_ptr(), side.stride(0), w_out.data_ptr(),
                                                w_out.stride(0), dx.data_ptr(), dx.stride(0), int(accumulate),
                                                _lib.ptr(xs_out), 0 if xs_out is None else _rowmajor(xs_out).stride(0),
-                                               _lib.stream()))
+                                               _lib.ptr(xs_amax), _lib.stream()))
 
 
 def xt_y(x: Optional[torch.Tensor], y: torch.Tensor, x2: Optional[torch.Tensor] = None,
@@ -552,24 +577,26 @@ def colsum(y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
-def gate_bwd(dh: torch.Tensor, gz: torch.Tensor, ent: torch.Tensor, d_pre: torch.Tensor, d_ent: torch.Tensor) -> None:
+def gate_bwd(dh: torch.Tensor, gz: torch.Tensor, ent: torch.Tensor, d_pre: torch.Tensor, d_ent: torch.Tensor,
+             pre_amax: Optional[torch.Tensor] = None) -> None:
     n, dim = dh.shape
     for t in (dh, gz, ent, d_pre, d_ent):
         _rowmajor(t)
     with _dev_guard(dh, "gate_bwd"):
         _lib.check(_lib.load().lkg_gate_bwd(dh.data_ptr(), dh.stride(0), gz.data_ptr(), gz.stride(0), ent.data_ptr(),
                                             ent.stride(0), n, dim, d_pre.data_ptr(), d_pre.stride(0), d_ent.data_ptr(),
-                                            d_ent.stride(0), _lib.stream()))
+                                            d_ent.stride(0), _lib.ptr(pre_amax), _lib.stream()))
 
 
-def leaky_bwd(grad: torch.Tensor, out: torch.Tensor, d_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+def leaky_bwd(grad: torch.Tensor, out: torch.Tensor, d_pre: Optional[torch.Tensor] = None,
+              amax: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, c = out.shape
     grad = grad if (grad.dtype == torch.float32 and grad.stride(1) == 1) else _lib.f32c(grad)
     if d_pre is None:
         d_pre = torch.empty((n, c), dtype=torch.float32, device=out.device)
     with _dev_guard(out, "leaky_bwd"):
         _lib.check(_lib.load().lkg_leaky_bwd(grad.data_ptr(), grad.stride(0), out.data_ptr(), out.stride(0), n, c,
-                                             d_pre.data_ptr(), d_pre.stride(0), _lib.stream()))
+                                             d_pre.data_ptr(), d_pre.stride(0), _lib.ptr(amax), _lib.stream()))
     return d_pre
 
 

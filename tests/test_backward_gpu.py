@@ -196,6 +196,49 @@ def test_gate_and_leaky_bwd():
     assert torch.equal(ops.leaky_bwd(gr, out), gr * torch.where(out > 0, 1.0, 0.01).float())
 
 
+def test_producer_scale_records():
+    """The kernels that write gradient matrices raise the scale record themselves (no absmax pass re-reads the data):
+    the finished record equals the one lkg_scale_from_data measures from the output."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, generator=g, device="cuda")
+
+    def same(rec, data):
+        ops.scale_finish(rec)
+        ref = ops.scale_from_data(data)
+        assert float(rec[0]) == float(data.abs().max()) and torch.equal(rec[:3], ref[:3])
+
+    n = 3001
+    out, gr = rnd(n, 256), rnd(n, 256) * 3e-4
+    rec = ops.raw_record("cuda")
+    same(rec, ops.leaky_bwd(gr, out, amax=rec))
+
+    dh, gz, ent = rnd(n, 300) * 1e-3, torch.rand(n, 600, generator=g, device="cuda"), rnd(n, 300)
+    d_pre, d_ent = torch.empty(n, 600, device="cuda"), torch.empty(n, 300, device="cuda")
+    rec = ops.raw_record("cuda")
+    ops.gate_bwd(dh, gz, ent, d_pre, d_ent, pre_amax=rec)
+    same(rec, d_pre)
+
+    for d, c in ((300, 32), (32, 32)):
+        do2, p2, x, side = rnd(n, c), rnd(d, c), rnd(n, d), rnd(n, d)
+        w, dx, xs = torch.empty(n, d, device="cuda"), torch.zeros(n, d, device="cuda"), torch.empty(n, d, device="cuda")
+        rec = ops.raw_record("cuda")
+        ops.bi_bwd_rows(do2, p2, x, side, w, dx, accumulate=True, xs_out=xs, xs_amax=rec)
+        same(rec, xs)
+
+    for c, has_o2 in ((32, True), (48, False)):
+        nt = 2 if has_o2 else 1
+        o, y, dyn = rnd(n, nt * c), rnd(n, c), rnd(n, c) * 1e-2
+        big = torch.zeros(n, nt * c + 40, device="cuda")
+        d_o = big[:, 8:8 + nt * c]
+        dgb = torch.zeros(2 * c, device="cuda")
+        rec, rec2 = ops.raw_record("cuda"), ops.raw_record("cuda")
+        rec2[0] = 1e-30                                        # a record that already covers something smaller
+        ops.layer_bwd_rows(y, o, has_o2, None, None, dyn, torch.ones(c, device="cuda"), d_o, dgb, amax=rec, amax2=rec2)
+        same(rec, d_o)
+        same(rec2, d_o)
+
+
 def test_loss_heads_vs_torch():
     """lkg_bpr_loss / lkg_transr_loss (value + every gradient) against the reference formulas in float64
     (model.py:316-348, 364-428); batch indices repeat, so the gradient scatter must accumulate."""

@@ -177,3 +177,39 @@ def test_cta_pair_gate_and_score(cta_group):
         sc.append((ops.score(emb, heads, tails, mm), mm.clone()))
     assert rel(sc[1][0], emb[heads].double() @ emb[tails].double().t()) < TOL
     assert torch.equal(sc[0][0], sc[1][0]) and torch.equal(sc[0][1], sc[1][1])
+
+
+@pytest.mark.parametrize("m,k", [(1000, 32), (513, 30), (77, 12), (2049, 300), (300, 302), (5, 4), (1, 1), (4097, 64)])
+@pytest.mark.parametrize("layout", ["contiguous", "view", "gather", "odd_view"])
+def test_split_planes_layouts(m, k, layout):
+    """The flat-indexed absmax / split kernels on narrow, ragged, strided and gathered operands: record == the data's
+    absmax and its power-of-two scale, hi + lo reproduces the value to 2^-22 of the absmax, pad columns are zero."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m * 31 + k)
+    rows = None
+    if layout == "contiguous":
+        src = torch.randn(m, k, generator=g, device="cuda")
+    elif layout == "view":
+        src = torch.randn(m, k + 24, generator=g, device="cuda")[:, 8:8 + k]          # 16-byte aligned window
+    elif layout == "odd_view":
+        src = torch.randn(m, k + 7, generator=g, device="cuda")[:, 3:3 + k]           # unaligned: scalar path
+    else:
+        src = torch.randn(3 * m + 1, k, generator=g, device="cuda")
+        rows = torch.randint(0, 3 * m + 1, (m,), generator=g, device="cuda")
+    src[m // 2, k // 2] = -7.5                                                        # the absmax, negative
+    ref = src if rows is None else src[rows]
+    pl = ops.split_planes(src, rows)
+    amax = ref.abs().max()
+    assert pl.rec[0] == amax
+    scaled = float(amax * pl.rec[1])
+    assert 2048.0 <= scaled < 4096.0 and float(pl.rec[1] * pl.rec[2]) == 1.0
+    assert (pl.dequant() - ref).abs().max() <= float(amax) * 2.0 ** -22
+    assert (pl.t[:, :m, k:] == 0).all()
+    # record built in two halves by the accumulate entry point == the one-pass record
+    rec = ops.raw_record("cuda")
+    if rows is None and m > 1:
+        ops.absmax_accumulate(src[: m // 2], rec)
+        ops.absmax_accumulate(src[m // 2:], rec)
+        ops.scale_finish(rec)
+        assert torch.equal(rec[:3], pl.rec[:3])
+        assert torch.equal(ops.split_planes(src, rec=rec).t, pl.t)
