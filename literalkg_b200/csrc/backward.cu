@@ -285,6 +285,132 @@ __global__ void __launch_bounds__(256) layer_bwd_rows_kernel(LayerBwdParams p) {
     }
 }
 
+// Narrow rows as 16-byte vectors: LPR lanes per row (one float4 of channels each), 32 / LPR rows per warp -- the
+// warp-per-row kernel above moves 128 bytes per warp and array, this one a full 512.  Needs c % 4 == 0, c <= 4 LPR
+// and 16-byte aligned rows everywhere.
+__device__ __forceinline__ float4 ld4_or(const float* p, bool ok, float fill) {
+    return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(fill, fill, fill, fill);
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) layer_bwd_rows_vec_kernel(LayerBwdParams p) {
+    constexpr int RPW = 32 / LPR, CW = 4 * LPR;
+    __shared__ float red[8][2][CW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / LPR, gl = lane % LPR;
+    const int C = p.c, ch = 4 * gl;
+    const bool okc = ch < C;
+    const float inv_c = 1.f / (float)C;
+    float lw[4], dgam[4], dbet[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        lw[q] = okc ? __ldg(p.ln_w + ch + q) : 0.f;
+        dgam[q] = dbet[q] = 0.f;
+    }
+    float amax = 0.f;
+    const int64_t units = (p.n + RPW - 1) / RPW;
+    for (int64_t unit = (int64_t)blockIdx.x * 8 + warp; unit < units; unit += (int64_t)gridDim.x * 8) {
+        const int64_t row = unit * RPW + grp;
+        const bool live = okc && row < p.n;
+        const float4 o1v = ld4_or(p.o + row * p.ld_o + ch, live, 0.f);
+        const float4 o2v = ld4_or(p.o + row * p.ld_o + C + ch, live && p.has_o2, 0.f);
+        const float4 yv = ld4_or(p.y + row * p.ld_y + ch, live, 0.f);
+        const float4 gv = ld4_or(p.dyn + row * p.ld_dyn + ch, live && p.dyn, 0.f);
+        const float4 dyv = ld4_or(p.dy_in + row * p.ld_dy + ch, live && p.dy_in, 0.f);
+        const float4 mkv = ld4_or(p.mask + row * C + ch, live && p.mask, 1.f);
+        const float o1[4] = {o1v.x, o1v.y, o1v.z, o1v.w}, o2[4] = {o2v.x, o2v.y, o2v.z, o2v.w};
+        const float y[4] = {yv.x, yv.y, yv.z, yv.w}, g[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float dyi[4] = {dyv.x, dyv.y, dyv.z, dyv.w}, mk[4] = {mkv.x, mkv.y, mkv.z, mkv.w};
+        float e[4];
+        float s1 = 0.f, sq = 0.f, dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            e[q] = live ? leaky(o1[q]) + (p.has_o2 ? leaky(o2[q]) : 0.f) : 0.f;
+            s1 += e[q];
+            sq = fmaf(y[q], y[q], sq);
+            dot = fmaf(g[q], y[q], dot);
+        }
+        const float mean = group_sum<LPR>(s1) * inv_c;
+        float s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float dlt = live ? e[q] - mean : 0.f;
+            s2 = fmaf(dlt, dlt, s2);
+        }
+        const float rstd = rsqrtf(group_sum<LPR>(s2) * inv_c + 1e-5f);
+        sq = group_sum<LPR>(sq);
+        dot = group_sum<LPR>(dot);
+        const float nrm = sqrtf(sq);
+        const float den = fmaxf(nrm, 1e-12f);
+        const float k1 = 1.f / den;
+        const float k2 = nrm > 1e-12f ? dot / (den * den * den) : 0.f;    // clamp_min passes no gradient below eps
+        float dhat[4], ehat[4];
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float dy = g[q] * k1 - y[q] * k2 + dyi[q];
+            dy *= mk[q];
+            if (!live) dy = 0.f;
+            ehat[q] = live ? (e[q] - mean) * rstd : 0.f;
+            dgam[q] = fmaf(dy, ehat[q], dgam[q]);
+            dbet[q] += dy;
+            dhat[q] = dy * lw[q];
+            m1 += dhat[q];
+            m2 = fmaf(dhat[q], ehat[q], m2);
+        }
+        m1 = group_sum<LPR>(m1) * inv_c;
+        m2 = group_sum<LPR>(m2) * inv_c;
+        if (live) {
+            float d1[4], d2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float de = (dhat[q] - m1 - ehat[q] * m2) * rstd;
+                d1[q] = de * (o1[q] > 0.f ? 1.f : 0.01f);
+                d2[q] = de * (o2[q] > 0.f ? 1.f : 0.01f);
+                amax = fmaxf(amax, fabsf(d1[q]));
+                if (p.has_o2) amax = fmaxf(amax, fabsf(d2[q]));
+            }
+            *reinterpret_cast<float4*>(p.d_o + row * p.ld_do + ch) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+            if (p.has_o2)
+                *reinterpret_cast<float4*>(p.d_o + row * p.ld_do + C + ch) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+        }
+    }
+    if (p.amax || p.amax2) {
+        amax = warp_max(amax);
+        if (lane == 0 && amax > 0.f) {
+            if (p.amax) atomicMax(reinterpret_cast<uint32_t*>(p.amax), __float_as_uint(amax));
+            if (p.amax2) atomicMax(reinterpret_cast<uint32_t*>(p.amax2), __float_as_uint(amax));
+        }
+    }
+    // LayerNorm weight / bias gradients: groups of the warp, then the 8 warps, then one atomic per channel and CTA
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            dgam[q] += __shfl_xor_sync(kFull, dgam[q], o);
+            dbet[q] += __shfl_xor_sync(kFull, dbet[q], o);
+        }
+        if (grp == 0) {
+            red[warp][0][ch + q] = dgam[q];
+            red[warp][1][ch + q] = dbet[q];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * CW; i += blockDim.x) {
+        const int half = i / CW, c = i % CW;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][half][c];
+        if (c < C) atomicAdd(p.dgb + half * C + c, s);
+    }
+}
+
 // ---- product path of the bi-interaction layer: V = do2 @ P2^T; W = V * x; dx (+)= V * side; xs = x * side ---------
 struct BiBwdParams {
     int64_t n;
@@ -362,6 +488,60 @@ __global__ void __launch_bounds__(256) bi_bwd_rows_kernel(BiBwdParams p) {
                     p.dx[row * p.ld_dx + i] = fmaf(v, sv[u], dv[u]);
                 }
             }
+        }
+    }
+    if (p.xs_amax) raise_absmax(p.xs_amax, amax);
+}
+
+// Narrow rows (d <= 64): LPR = d / 4 lanes per row hold one float4 of x / side / dx each and the row's do2 chunk by
+// chunk; do2[c] arrives by shuffle, P2^T is read from shared memory as [c][4 LPR] (the groups of a warp read the same
+// 16-byte words: broadcast).  Needs d % 4 == 0, c % 4 == 0, c <= 4 LPR and 16-byte aligned rows.
+template <int LPR>
+__global__ void __launch_bounds__(256) bi_bwd_rows_vec_kernel(BiBwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int RPW = 32 / LPR, DW = 4 * LPR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / LPR, gl = lane % LPR;
+    for (int i = threadIdx.x; i < p.c * DW; i += blockDim.x) {
+        const int cc = i / DW, di = i - cc * DW;
+        smem[i] = di < p.d ? p.p2[di * p.c + cc] : 0.f;
+    }
+    __syncthreads();
+    const int i0 = 4 * gl;
+    const bool oki = i0 < p.d;
+    const int chunks = p.c >> 2;
+    float amax = 0.f;
+    const int64_t units = (p.n + RPW - 1) / RPW;
+    for (int64_t unit = (int64_t)blockIdx.x * 8 + warp; unit < units; unit += (int64_t)gridDim.x * 8) {
+        const int64_t row = unit * RPW + grp;
+        const bool live = row < p.n;
+        const float4 dq = ld4_or(p.d_o2 + row * p.ld_do + 4 * gl, live && gl < chunks, 0.f);
+        const float4 xv = ld4_or(p.x + row * p.ld_x + i0, live && oki, 0.f);
+        const float4 sv = ld4_or(p.side + row * p.ld_side + i0, live && oki, 0.f);
+        float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && oki && p.accumulate) dv = *reinterpret_cast<const float4*>(p.dx + row * p.ld_dx + i0);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sl = 0; sl < chunks; ++sl) {
+            const float a[4] = {__shfl_sync(kFull, dq.x, sl, LPR), __shfl_sync(kFull, dq.y, sl, LPR),
+                                __shfl_sync(kFull, dq.z, sl, LPR), __shfl_sync(kFull, dq.w, sl, LPR)};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(smem + (4 * sl + q) * DW + i0);
+                v.x = fmaf(a[q], w.x, v.x);
+                v.y = fmaf(a[q], w.y, v.y);
+                v.z = fmaf(a[q], w.z, v.z);
+                v.w = fmaf(a[q], w.w, v.w);
+            }
+        }
+        if (live && oki) {
+            *reinterpret_cast<float4*>(p.w_out + row * p.ld_w + i0) = make_float4(v.x * xv.x, v.y * xv.y, v.z * xv.z, v.w * xv.w);
+            if (p.xs_out) {
+                const float4 xs = make_float4(xv.x * sv.x, xv.y * sv.y, xv.z * sv.z, xv.w * sv.w);
+                *reinterpret_cast<float4*>(p.xs_out + row * p.ld_xs + i0) = xs;
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(xs.x), fabsf(xs.y))), fmaxf(fabsf(xs.z), fabsf(xs.w)));
+            }
+            *reinterpret_cast<float4*>(p.dx + row * p.ld_dx + i0) =
+                make_float4(fmaf(v.x, sv.x, dv.x), fmaf(v.y, sv.y, dv.y), fmaf(v.z, sv.z, dv.z), fmaf(v.w, sv.w, dv.w));
         }
     }
     if (p.xs_amax) raise_absmax(p.xs_amax, amax);
@@ -479,6 +659,78 @@ __global__ void leaky_bwd_kernel(const float* __restrict__ g, int64_t ld_g, cons
     if (d_amax) raise_absmax(d_amax, amax);
 }
 
+// The same two kernels over 16-byte units ([n, dim / 4] walked flat, 32-bit index arithmetic while it fits, two units
+// in flight per thread); the scalar kernels above stay for unaligned operands.
+template <typename I>
+__global__ void __launch_bounds__(256) gate_bwd_vec_kernel(const float* __restrict__ dh, int64_t ld_dh,
+                                                           const float* __restrict__ gz, int64_t ld_gz,
+                                                           const float* __restrict__ ent, int64_t ld_ent, int64_t n, int dim,
+                                                           float* __restrict__ d_pre, int64_t ld_pre,
+                                                           float* __restrict__ d_ent, int64_t ld_de,
+                                                           float* __restrict__ pre_amax) {
+    const I qv = (I)(dim >> 2), total = (I)n * qv, stride = (I)gridDim.x * blockDim.x;
+    float amax = 0.f;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const I row = i / qv;
+        const int j = 4 * (int)(i - row * qv);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(gz + (int64_t)row * ld_gz + 2 * j));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(gz + (int64_t)row * ld_gz + 2 * j) + 1);
+        const float4 dv = __ldg(reinterpret_cast<const float4*>(dh + (int64_t)row * ld_dh + j));
+        const float4 ev = __ldg(reinterpret_cast<const float4*>(ent + (int64_t)row * ld_ent + j));
+        const float g[4] = {a0.x, a0.z, a1.x, a1.z}, z[4] = {a0.y, a0.w, a1.y, a1.w};
+        const float d[4] = {dv.x, dv.y, dv.z, dv.w}, e[4] = {ev.x, ev.y, ev.z, ev.w};
+        float pg[4], pz[4], de[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pg[q] = d[q] * z[q] * (1.f - g[q] * g[q]);
+            pz[q] = d[q] * (g[q] - e[q]) * z[q] * (1.f - z[q]);
+            de[q] = d[q] * (1.f - z[q]);
+            amax = fmaxf(amax, fmaxf(fabsf(pg[q]), fabsf(pz[q])));
+        }
+        float4* dst = reinterpret_cast<float4*>(d_pre + (int64_t)row * ld_pre + 2 * j);
+        dst[0] = make_float4(pg[0], pz[0], pg[1], pz[1]);
+        dst[1] = make_float4(pg[2], pz[2], pg[3], pz[3]);
+        *reinterpret_cast<float4*>(d_ent + (int64_t)row * ld_de + j) = make_float4(de[0], de[1], de[2], de[3]);
+    }
+    if (pre_amax) raise_absmax(pre_amax, amax);
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256) leaky_bwd_vec_kernel(const float* __restrict__ g, int64_t ld_g,
+                                                            const float* __restrict__ out, int64_t ld_out, int64_t n, int c,
+                                                            float* __restrict__ d, int64_t ld_d, float* __restrict__ d_amax) {
+    constexpr int U = 2;
+    const I cv = (I)(c >> 2), total = (I)n * cv, stride = (I)gridDim.x * blockDim.x;
+    float amax = 0.f;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+        float4 gv[U], ov[U];
+        I row[U];
+        int col[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const I j = i + (I)u * stride;
+            const bool ok = j < total;
+            row[u] = ok ? j / cv : 0;
+            col[u] = ok ? 4 * (int)(j - row[u] * cv) : -1;
+            if (ok) {
+                gv[u] = __ldg(reinterpret_cast<const float4*>(g + (int64_t)row[u] * ld_g + col[u]));
+                ov[u] = __ldg(reinterpret_cast<const float4*>(out + (int64_t)row[u] * ld_out + col[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (col[u] < 0) continue;
+            const float4 v = make_float4(gv[u].x * (ov[u].x > 0.f ? 1.f : 0.01f), gv[u].y * (ov[u].y > 0.f ? 1.f : 0.01f),
+                                         gv[u].z * (ov[u].z > 0.f ? 1.f : 0.01f), gv[u].w * (ov[u].w > 0.f ? 1.f : 0.01f));
+            *reinterpret_cast<float4*>(d + (int64_t)row[u] * ld_d + col[u]) = v;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+    }
+    if (d_amax) raise_absmax(d_amax, amax);
+}
+
+inline bool rows16(const void* ptr, int64_t ld) { return ptr == nullptr || (aligned16(ptr) && ld % 4 == 0); }
+
 }  // namespace
 }  // namespace lkg
 
@@ -548,6 +800,16 @@ extern "C" int lkg_layer_bwd_rows(int64_t n, int32_t c, int32_t has_o2, const fl
     if (c > 64) LKG_FAIL(LKG_ERR_UNSUPPORTED, "layer backward: d_out %d > 64", c);
     LayerBwdParams p{n, c, has_o2, y, ld_y, o, ld_o, mask, dy_in, ld_dy, dyn, ld_dyn, ln_weight, d_o, ld_do, dgamma_dbeta,
                      amax, amax2};
+    if (c % 4 == 0 && rows16(y, ld_y) && rows16(o, ld_o) && rows16(mask, c) && rows16(dy_in, ld_dy) && rows16(dyn, ld_dyn) &&
+        rows16(d_o, ld_do)) {
+        const int lpr = c <= 32 ? 8 : 16;
+        const int64_t units = (n + 32 / lpr - 1) / (32 / lpr);
+        const int grid = (int)std::min<int64_t>((units + 7) / 8, (int64_t)sm_count() * 8);
+        if (lpr == 8) layer_bwd_rows_vec_kernel<8><<<grid, 256, 0, stream>>>(p);
+        else layer_bwd_rows_vec_kernel<16><<<grid, 256, 0, stream>>>(p);
+        LKG_LAUNCH_CHECK("layer_bwd_rows_vec_kernel");
+        return LKG_OK;
+    }
     const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8);
     if (c <= 32) layer_bwd_rows_kernel<1><<<grid, 256, 0, stream>>>(p);
     else layer_bwd_rows_kernel<2><<<grid, 256, 0, stream>>>(p);
@@ -563,6 +825,19 @@ extern "C" int lkg_bi_bwd_rows(int64_t n, int32_t d, int32_t c, const float* d_o
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(d_o2 && p2 && x && side && w_out && dx && d > 0 && c > 0, "null argument");
     if (c > 64) LKG_FAIL(LKG_ERR_UNSUPPORTED, "bi backward: d_out %d > 64", c);
+    if (d <= 64 && d % 4 == 0 && c % 4 == 0 && c <= (d <= 32 ? 32 : 64) && rows16(d_o2, ld_do) && rows16(x, ld_x) &&
+        rows16(side, ld_side) && rows16(w_out, ld_w) && rows16(dx, ld_dx) && rows16(xs_out, ld_xs)) {
+        const int lpr = d <= 32 ? 8 : 16;
+        BiBwdParams p{n, d, c, d_o2, ld_do, p2, x, ld_x, side, ld_side, w_out, ld_w, dx, ld_dx, xs_out, ld_xs, accumulate, 0,
+                      xs_out ? xs_amax : nullptr};
+        const size_t smem = (size_t)c * 4 * lpr * sizeof(float);
+        const int64_t units = (n + 32 / lpr - 1) / (32 / lpr);
+        const int grid = (int)std::min<int64_t>((units + 7) / 8, (int64_t)sm_count() * 8);
+        if (lpr == 8) bi_bwd_rows_vec_kernel<8><<<grid, 256, smem, stream>>>(p);
+        else bi_bwd_rows_vec_kernel<16><<<grid, 256, smem, stream>>>(p);
+        LKG_LAUNCH_CHECK("bi_bwd_rows_vec_kernel");
+        return LKG_OK;
+    }
     const int cq = (c + 3) / 4;
     int ps = 4 * cq;
     if ((ps / 4) % 2 == 0) ps += 4;                           // 4 * odd
@@ -611,6 +886,19 @@ extern "C" int lkg_gate_bwd(const float* dh, int64_t ld_dh, const float* gz, int
     LKG_REQUIRE(dh && gz && ent && d_pre && d_ent && dim > 0, "null argument");
     LKG_REQUIRE(ld_gz % 2 == 0 && ld_pre % 2 == 0 && (reinterpret_cast<uintptr_t>(gz) & 7u) == 0 &&
                     (reinterpret_cast<uintptr_t>(d_pre) & 7u) == 0, "gate backward: (g, z) pairs must be 8-byte aligned");
+    if (dim % 4 == 0 && rows16(dh, ld_dh) && rows16(gz, ld_gz) && rows16(ent, ld_ent) && rows16(d_pre, ld_pre) &&
+        rows16(d_ent, ld_de)) {
+        const int64_t units = n * (dim / 4);
+        const int grid = (int)std::min<int64_t>((units + 255) / 256, (int64_t)sm_count() * 8);
+        if (units < ((int64_t)1 << 30))
+            gate_bwd_vec_kernel<uint32_t><<<grid, 256, 0, stream>>>(dh, ld_dh, gz, ld_gz, ent, ld_ent, n, dim, d_pre, ld_pre,
+                                                                    d_ent, ld_de, pre_amax);
+        else
+            gate_bwd_vec_kernel<uint64_t><<<grid, 256, 0, stream>>>(dh, ld_dh, gz, ld_gz, ent, ld_ent, n, dim, d_pre, ld_pre,
+                                                                    d_ent, ld_de, pre_amax);
+        LKG_LAUNCH_CHECK("gate_bwd_vec_kernel");
+        return LKG_OK;
+    }
     gate_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(dh, ld_dh, gz, ld_gz, ent, ld_ent, n, dim, d_pre, ld_pre, d_ent, ld_de,
                                                             pre_amax);
     LKG_LAUNCH_CHECK("gate_bwd_kernel");
@@ -622,6 +910,16 @@ extern "C" int lkg_leaky_bwd(const float* grad, int64_t ld_g, const float* out, 
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return LKG_OK;
     LKG_REQUIRE(grad && out && d_pre && c > 0, "null argument");
+    if (c % 4 == 0 && rows16(grad, ld_g) && rows16(out, ld_out) && rows16(d_pre, ld_d)) {
+        const int64_t units = n * (c / 4);
+        const int grid = (int)std::min<int64_t>((units + 511) / 512, (int64_t)sm_count() * 8);
+        if (units < ((int64_t)1 << 30))
+            leaky_bwd_vec_kernel<uint32_t><<<std::max(grid, 1), 256, 0, stream>>>(grad, ld_g, out, ld_out, n, c, d_pre, ld_d, amax);
+        else
+            leaky_bwd_vec_kernel<uint64_t><<<std::max(grid, 1), 256, 0, stream>>>(grad, ld_g, out, ld_out, n, c, d_pre, ld_d, amax);
+        LKG_LAUNCH_CHECK("leaky_bwd_vec_kernel");
+        return LKG_OK;
+    }
     leaky_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(grad, ld_g, out, ld_out, n, c, d_pre, ld_d, amax);
     LKG_LAUNCH_CHECK("leaky_bwd_kernel");
     return LKG_OK;

@@ -495,11 +495,12 @@ def spmm_t(plan: GraphPlan, a_values: torch.Tensor, x: torch.Tensor, out: torch.
 
 
 def spmm_coo(coo, a_values: torch.Tensor, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """out[seg] += a_values[perm] * x[src] over a COO list (seg, src, perm) sorted by seg (``GraphPlan.transposed``)."""
+    """out[seg] += a_values[perm] * x[src] over a COO list (seg, src, perm) sorted by seg (``GraphPlan.transposed``);
+    perm None: ``a_values`` is already in list order."""
     t_tail, t_head, t_perm = coo
     _rowmajor(x); _rowmajor(out)
     with _dev_guard(x, f"spmm_t_d{x.shape[1]}"):
-        _lib.check(_lib.load().lkg_spmm_coo(t_tail.data_ptr(), t_head.data_ptr(), t_perm.data_ptr(), a_values.data_ptr(),
+        _lib.check(_lib.load().lkg_spmm_coo(t_tail.data_ptr(), t_head.data_ptr(), _lib.ptr(t_perm), a_values.data_ptr(),
                                             t_tail.numel(), x.data_ptr(), x.stride(0), x.shape[1], out.data_ptr(),
                                             out.stride(0), _lib.stream()))
     return out

@@ -124,7 +124,8 @@ def test_xt_y_tensor_core(dx, cy, n):
 
 @pytest.mark.parametrize("c,has_o2,use_mask,use_dy,use_dyn", [(32, True, True, True, True), (32, False, False, False, True),
                                                              (64, True, False, True, True), (16, False, True, True, False),
-                                                             (48, True, True, True, True)])
+                                                             (48, True, True, True, True), (10, True, True, True, True),
+                                                             (4, False, False, True, True)])
 def test_layer_bwd_rows(c, has_o2, use_mask, use_dy, use_dyn):
     from literalkg_b200 import ops
     n = 1234
@@ -178,9 +179,10 @@ def test_bi_bwd_rows(d, c):
             assert torch.equal(xs, x * side)
 
 
-def test_gate_and_leaky_bwd():
+@pytest.mark.parametrize("n,dim,c", [(501, 300, 256), (77, 6, 10), (1030, 8, 4)])
+def test_gate_and_leaky_bwd(n, dim, c):
+    """16-byte vector kernels (dim % 4 == 0) and the scalar ones behind them."""
     from literalkg_b200 import ops
-    n, dim = 501, 300
     g = torch.Generator(device="cuda").manual_seed(1)
     dh = torch.randn(n, dim, generator=g, device="cuda")
     gz = torch.rand(n, 2 * dim, generator=g, device="cuda")
@@ -191,9 +193,11 @@ def test_gate_and_leaky_bwd():
     assert rel_err(d_pre[:, 0::2], dh.double() * zz * (1 - gg * gg)) < 1e-5
     assert rel_err(d_pre[:, 1::2], dh.double() * (gg - ent.double()) * zz * (1 - zz)) < 1e-5
     assert rel_err(d_ent, dh.double() * (1 - zz)) < 1e-5
-    out = torch.randn(n, 256, generator=g, device="cuda")
-    gr = torch.randn(n, 256, generator=g, device="cuda")
+    out = torch.randn(n, c, generator=g, device="cuda")
+    gr = torch.randn(n, c, generator=g, device="cuda")
     assert torch.equal(ops.leaky_bwd(gr, out), gr * torch.where(out > 0, 1.0, 0.01).float())
+    wide = torch.randn(n, c + 9, generator=g, device="cuda")
+    assert torch.equal(ops.leaky_bwd(wide[:, 5:5 + c], out), wide[:, 5:5 + c] * torch.where(out > 0, 1.0, 0.01).float())
 
 
 def test_producer_scale_records():
@@ -226,7 +230,7 @@ def test_producer_scale_records():
         ops.bi_bwd_rows(do2, p2, x, side, w, dx, accumulate=True, xs_out=xs, xs_amax=rec)
         same(rec, xs)
 
-    for c, has_o2 in ((32, True), (48, False)):
+    for c, has_o2 in ((32, True), (48, False), (10, True)):
         nt = 2 if has_o2 else 1
         o, y, dyn = rnd(n, nt * c), rnd(n, c), rnd(n, c) * 1e-2
         big = torch.zeros(n, nt * c + 40, device="cuda")
