@@ -4,6 +4,9 @@
 (main.py:80-317) written against the drop-in classes, with the minibatches assembled on the device.
 
     python examples/pretrain_finetune.py [--entities 770554 --edges 1050000 --relations 15 --layers 8 --steps 20]
+    python examples/pretrain_finetune.py --preset small     # BASELINE.json configs[0]: data/Small shape, ONE
+                                                            # pre-training epoch (triples / batch steps) + evaluation
+    python examples/pretrain_finetune.py --data-dir /root/reference/data/Test   # a reference data directory, where present
 
 The Pet_v2 train-split KG blob and the Drive-hosted literal pickles are not available offline, so the graph and the
 literal tables are generated with the shapes of SURVEY.md 8(d) cfg 2 (power-law heads capped at out-degree 50).
@@ -42,13 +45,33 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--diseases", type=int, default=118, help="candidate tails of the fine-tuning task")
     ap.add_argument("--seed", type=int, default=2022)
+    ap.add_argument("--ft-steps", type=int, default=None, help="fine-tuning steps (default: --steps)")
+    ap.add_argument("--preset", choices=["pet_v2", "small"], default="pet_v2",
+                    help="small: the shape of the reference's bundled data/Small split (770 563 entity ids, 251 895 triples, "
+                         "15 relations, out-degree <= 49, 118 disease tails) and main.py's epoch length")
+    ap.add_argument("--data-dir", default=None, help="read a reference data directory (dataloader.py:24-32 layout) "
+                                                     "instead of generating the KG; literals missing there are synthetic")
+    ap.add_argument("--kg-file", default="pre_training_train.txt")
     a = ap.parse_args()
+    if a.preset == "small":
+        a.entities, a.edges, a.relations = 770_563, 251_895, 15
+        a.steps = a.edges // a.batch + 1                   # main.py:107: n_kg_batch = n_kg_train // batch_size + 1
+        a.ft_steps = 0 if a.ft_steps is None else a.ft_steps
+    a.ft_steps = a.steps if a.ft_steps is None else a.ft_steps
     dev = torch.device("cuda:0")
     torch.manual_seed(a.seed)
+    if a.data_dir:
+        trip, num_table, text_table = L.dataloader.read_data_dir(a.data_dir, a.kg_file)
+        kg = argparse.Namespace(h=trip[:, 0], r=trip[:, 1], t=trip[:, 2])
+        a.entities, a.relations = int(max(kg.h.max(), kg.t.max())) + 1, int(kg.r.max()) + 1
+        a.entities = max([a.entities] + [tab.shape[0] for tab in (num_table, text_table) if tab is not None])
+    else:
+        kg = L.synthetic.make_kg(a.entities, a.edges, a.relations, seed=a.seed, max_out_degree=50)
     n = a.entities
-    kg = L.synthetic.make_kg(n, a.edges, a.relations, seed=a.seed, max_out_degree=50)
     num, txt = L.synthetic.make_literals(n, seed=a.seed, device=dev)
     data = L.KGTensors(kg.h, kg.t, kg.r, n_entities=n, device=dev)
+    if a.data_dir and num_table is not None:
+        num = data._table(num_table)                       # the bundled numeric literal dictionaries, min-max scaled
     args = reference_args(a)
     model = L.LiteralKG(args, n, a.relations, data.A_in, num, txt).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
@@ -66,15 +89,17 @@ def main():
     def sync():
         torch.cuda.synchronize(dev)
 
-    def phase(name, step_fn):
+    def phase(name, step_fn, steps):
+        if steps <= 0:
+            return []
         model.train()
         losses = []
         step_fn(); sync()                                  # warm-up (plan / cache construction)
         t0 = time.perf_counter()
-        for _ in range(a.steps):
+        for _ in range(steps):
             losses.append(step_fn())
         sync()
-        dt = (time.perf_counter() - t0) / a.steps
+        dt = (time.perf_counter() - t0) / steps
         losses = [float(x) for x in losses]
         print(f"{name}: {dt * 1e3:.1f} ms / step (sampling + forward + backward + Adam), "
               f"loss {losses[0]:.4f} -> {losses[-1]:.4f}")
@@ -101,8 +126,8 @@ def main():
         model(data.h_list, data.t_list, data.r_list, data.relations, device=dev, mode="update_att")
     sync()
     print(f"update_att: {(time.perf_counter() - t0) * 1e3:.1f} ms (includes the plan build)")
-    pre = phase("pre_training", pre_step)
-    ft = phase("fine_tuning", ft_step)
+    pre = phase("pre_training", pre_step, a.steps)
+    ft = phase("fine_tuning", ft_step, a.ft_steps)
 
     # evaluation (utils/model_utils.py:41-78): every head batch calls mode='predict'; the embedding pass behind it is
     # computed once and reused while the parameters do not change

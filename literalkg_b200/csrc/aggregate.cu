@@ -312,18 +312,36 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
     // of them is a unit of its own -- the whole warp walks its neighbour list -- instead of four of them queueing
     // behind each other in one warp (a 4 096-neighbour row is ~128 dependent round trips); after them, RPW rows each.
     const int n_solo = RPW > 1 ? min(p.n_solo, n) : 0;
-    for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(p.counter, 1);
-        unit = __shfl_sync(kFull, unit, 0);
-        const bool solo = unit < n_solo;
-        const int base = solo ? unit : n_solo + (unit - n_solo) * RPW;
-        if (base >= n) break;
-        const bool live = solo ? grp == 0 : base + grp < n;
-        const int row = live ? (p.g.row_order ? __ldg(p.g.row_order + base + grp) : row0 + base + grp) : 0;
+    // The header of a unit is a chain of dependent round trips (counter -> row_order -> rowptr) in front of the index
+    // and gather round trips; with ~20 neighbours per row that chain was most of a unit's time (ncu r02: long
+    // scoreboard on top, DRAM at 37 %).  It is software pipelined: the unit after next is claimed, the next unit's
+    // row ids are loaded while this unit gathers and its extents while this unit runs the combine.
+    auto claim = [&]() {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(p.counter, 1);
+        return u;                                            // lane 0's value, broadcast where it is used
+    };
+    auto unit_base = [&](int unit, bool& is_solo) {
+        is_solo = unit < n_solo;
+        return is_solo ? unit : n_solo + (unit - n_solo) * RPW;
+    };
+    auto unit_row = [&](int base_, bool live_) {
+        return live_ ? (p.g.row_order ? __ldg(p.g.row_order + base_ + grp) : row0 + base_ + grp) : 0;
+    };
+    bool solo;
+    int base = unit_base(__shfl_sync(kFull, claim(), 0), solo);
+    int claimed = claim();
+    bool live = base < n && (solo ? grp == 0 : base + grp < n);
+    int row = unit_row(base, live);
+    int u0 = live ? __ldg(p.g.rowptr + row) : 0;
+    int u1 = live ? __ldg(p.g.rowptr + row + 1) : 0;
+    while (base < n) {
+        bool solo_n;
+        const int base_n = unit_base(__shfl_sync(kFull, claimed, 0), solo_n);
+        const bool live_n = base_n < n && (solo_n ? grp == 0 : base_n + grp < n);
+        const int row_n = unit_row(base_n, live_n);
+        claimed = claim();
         const int64_t lrow = row - p.local_row_base;
-        const int u0 = live ? __ldg(p.g.rowptr + row) : 0;
-        const int u1 = live ? __ldg(p.g.rowptr + row + 1) : 0;
         int max_deg = u1 - u0;
 #pragma unroll
         for (int o = LPR; o < 32; o <<= 1) max_deg = max(max_deg, __shfl_xor_sync(kFull, max_deg, o));
@@ -383,6 +401,10 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
                 side = acc;
             }
         }
+
+        // the next unit's extents: in flight during the combine
+        const int u0_n = live_n ? __ldg(p.g.rowptr + row_n) : 0;
+        const int u1_n = live_n ? __ldg(p.g.rowptr + row_n + 1) : 0;
 
         // ---- phase 2: folded combine in registers ------------------------------------------------------
         float4 eg = make_float4(0, 0, 0, 0);
@@ -519,6 +541,12 @@ __global__ void __launch_bounds__(256) aggregate_narrow_kernel(AggParams p) {
                 }
             }
         }
+        base = base_n;
+        solo = solo_n;
+        live = live_n;
+        row = row_n;
+        u0 = u0_n;
+        u1 = u1_n;
     }
 }
 
