@@ -285,7 +285,7 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # 128 MB all-gathers at 8 ranks: 0.30 ms with NCCL's default channel count, 0.21 ms with 32 (scratch/nccl_probe.py)
+        # 128 MB all-gathers at 8 ranks: 0.30 ms with NCCL's default channel count, 0.21 ms with 32 (round-1 probe)
         os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
