@@ -216,6 +216,14 @@ int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t 
                    const float* bias /*nullable [n]*/, int32_t activation, float* out, int64_t ldo,
                    uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
                    void* stream);
+/* The same GEMM with two destinations: columns [0, split_col) go to out, columns [split_col, n) to
+ * out2[row * ld2 + col - split_col] (split_col a multiple of 4).  The stacked h0 @ Q GEMM writes layer 1's pre-projected
+ * sum term z straight into the [h0 | z] table the aggregation gathers from (no copy between the two layouts). */
+int lkg_linear_fwd_split(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n,
+                         const float* bias /*nullable [n]*/, int32_t activation, float* out, int64_t ldo,
+                         float* out2 /*nullable*/, int64_t ld2, int32_t split_col,
+                         uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride, const float* out_rec,
+                         void* stream);
 /* Tuning / test knob of the GEMM engine (host call, process wide): 0 = automatic (a CTA pair issuing
  * tcgen05.mma.cta_group::2 over 256-row tiles whenever there is a tile for every SM pair, else one CTA per 128-row
  * tile), 1 / 2 = force the CTA-group size.  Results are bit-identical either way (same products, same order). */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "lkg_gemm_set_cta_group": (C.c_int, [i32]),
     "lkg_linear_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64,
                                  i64, vp, vp]),
+    "lkg_linear_fwd_split": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), i32, vp, i32, vp, i64, vp, i64, i32,
+                                       vp, i64, i64, vp, vp]),
     "lkg_gate_fwd": (C.c_int, [C.POINTER(LkgPlanes), i64, C.POINTER(LkgPlanes), vp, i32, vp, i64, vp, i64, vp, i64,
                                i64, vp, vp, i64, vp]),
     "lkg_aggregate_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),

@@ -69,6 +69,9 @@ struct TcParams {
     int act;
     float* out;
     int64_t ldo;
+    float* out2;                        // linear, optional: the columns from split_col (a multiple of 4) on are written
+    int64_t ld2;                        //   to out2[row * ld2 + col - split_col] instead (two consumers, two layouts)
+    int split_col;
     __half* out_planes;                 // optional hi/lo copy of the output (feeds the next GEMM)
     int64_t ld_planes, plane_stride;
     const float* x_ent;                 // gate mix input
@@ -145,7 +148,8 @@ struct EpiAlign {
 };
 __device__ __forceinline__ EpiAlign epi_align(const TcParams& p) {
     EpiAlign a;
-    a.out4 = ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && (p.ldo % 4 == 0);
+    a.out4 = ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && (p.ldo % 4 == 0) &&
+             (!p.out2 || (((reinterpret_cast<uintptr_t>(p.out2) & 15u) == 0) && (p.ld2 % 4 == 0)));
     a.ent4 = p.x_ent && ((reinterpret_cast<uintptr_t>(p.x_ent) & 15u) == 0) && (p.ld_ent % 4 == 0);
     a.gz4 = p.gz_out && ((reinterpret_cast<uintptr_t>(p.gz_out) & 15u) == 0) && (p.ld_gz % 4 == 0);
     a.planes4 = p.out_planes && ((reinterpret_cast<uintptr_t>(p.out_planes) & 7u) == 0) && (p.ld_planes % 4 == 0) &&
@@ -164,12 +168,18 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, const EpiAlign
     const int valid = col_end - col;             // columns of this lane inside the tile and the matrix (<= 0: none)
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EPI == kEpiLinear && p.bias && valid > 0) b = ld4_guard(p.bias + col, valid, al.bias4);
+    float* obase = p.out + col;
+    int64_t ostride = p.ldo;
+    if (EPI == kEpiLinear && p.out2 && col >= p.split_col) {
+        obase = p.out2 + (col - p.split_col);
+        ostride = p.ld2;
+    }
     float4 old[8];
     if (EPI == kEpiLinear && p.accumulate) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int64_t row = row0 + it * 4 + rsub;
-            old[it] = (row < p.m && valid > 0) ? ld4_guard(p.out + row * p.ldo + col, valid, al.out4)
+            old[it] = (row < p.m && valid > 0) ? ld4_guard(obase + row * ostride, valid, al.out4)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
@@ -200,7 +210,7 @@ __device__ __forceinline__ void epilogue_block(const TcParams& p, const EpiAlign
                     hi = fmaxf(hi, vv[j]);
                 }
         }
-        st4_guard(p.out + row * p.ldo + col, v, valid, al.out4);
+        st4_guard(obase + row * ostride, v, valid, al.out4);
         if (EPI == kEpiLinear && p.out_planes) {
             const float4 sv = make_float4(v.x * out_scale, v.y * out_scale, v.z * out_scale, v.w * out_scale);
             st_planes4(p.out_planes + row * p.ld_planes + col, p.plane_stride, sv, valid, al.planes4);
@@ -993,10 +1003,13 @@ extern "C" int lkg_gemm_set_cta_group(int32_t cta_group) {
     return LKG_OK;
 }
 
-extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n, const float* bias,
-                              int32_t activation, float* out, int64_t ldo, uint16_t* out_planes, int64_t ld_planes,
-                              int64_t plane_stride, const float* out_rec, void* stream_) {
-    LKG_REQUIRE(out && ldo >= n, "bad linear output");
+extern "C" int lkg_linear_fwd_split(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n, const float* bias,
+                                    int32_t activation, float* out, int64_t ldo, float* out2, int64_t ld2,
+                                    int32_t split_col, uint16_t* out_planes, int64_t ld_planes, int64_t plane_stride,
+                                    const float* out_rec, void* stream_) {
+    LKG_REQUIRE(out && ldo >= (out2 ? split_col : n), "bad linear output");
+    LKG_REQUIRE(!out2 || (split_col > 0 && split_col < n && split_col % 4 == 0 && ld2 >= n - split_col),
+                "bad split output (split_col %d of %d columns must be a positive multiple of 4)", split_col, n);
     LKG_REQUIRE(!out_planes || out_rec, "out_planes needs a scale record");
     if (m == 0) return LKG_OK;
     TcParams p{};
@@ -1005,11 +1018,21 @@ extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* 
     p.accumulate = (activation & LKG_ACT_ACCUMULATE) != 0;
     p.out = out;
     p.ldo = ldo;
+    p.out2 = out2;
+    p.ld2 = ld2;
+    p.split_col = split_col;
     p.out_planes = (__half*)out_planes;
     p.ld_planes = ld_planes;
     p.plane_stride = plane_stride;
     p.out_rec = out_rec;
     return launch_tc<kEpiLinear>(p, a, m, b, n, (cudaStream_t)stream_);
+}
+
+extern "C" int lkg_linear_fwd(const lkg_planes* a, int64_t m, const lkg_planes* b, int32_t n, const float* bias,
+                              int32_t activation, float* out, int64_t ldo, uint16_t* out_planes, int64_t ld_planes,
+                              int64_t plane_stride, const float* out_rec, void* stream_) {
+    return lkg_linear_fwd_split(a, m, b, n, bias, activation, out, ldo, nullptr, 0, 0, out_planes, ld_planes, plane_stride,
+                                out_rec, stream_);
 }
 
 extern "C" int lkg_gate_fwd(const lkg_planes* x, int64_t m, const lkg_planes* w_pair, const float* bias_pair,

@@ -651,13 +651,19 @@ class LiteralKG(nn.Module):
                 and self.use_residual and self.aggregation_type == 'bi-interaction' and d >= 128 and d % 4 == 0
                 and self.aggregator_layers[0].out_dim % 4 == 0)
 
-    def _residual_gemm(self, h0_planes, folds):
-        """h0 @ Q for all layers (+ layer 1's ego @ Pa and the z columns) as one GEMM -> (h0q, offsets, zoff)."""
+    def _residual_gemm(self, h0_planes, folds, z_out=None):
+        """h0 @ Q for all layers (+ layer 1's ego @ Pa and the z columns) as one GEMM -> (h0q, offsets, zoff).
+        ``z_out``: [rows, C] view that receives the z columns instead of h0q (the [h0 | z] table)."""
         qkey = tuple(id(f) for f in folds)                 # the fold dicts are cached per parameter version
         if self._h0q_cache is None or self._h0q_cache[0] != qkey:
             self._h0q_cache = (qkey, *self._stack_q(folds), folds)
         _, wq, cq, offsets, zoff, _ = self._h0q_cache
-        return ops.linear([h0_planes], wq, cq), offsets, zoff
+        if z_out is not None and zoff > 0 and zoff % 4 == 0:
+            return ops.linear([h0_planes], wq, cq, out2=z_out, split_col=zoff), offsets, zoff
+        h0q = ops.linear([h0_planes], wq, cq)
+        if z_out is not None:
+            z_out.copy_(h0q[:, zoff:zoff + z_out.shape[1]])
+        return h0q, offsets, zoff
 
     def _gate_stage(self, part, keep=None, pre=None) -> dict:
         """First stage of the embedding pass: buffers, the literal gate on this rank's rows and -- row partitioned,
@@ -712,9 +718,8 @@ class LiteralKG(nn.Module):
         extra = {}
         if combined:                                      # z = h0 @ Pb next to h0 (the residual GEMM only needs parameters)
             folds = [layer.folded(self.lamda, self.alpha, k + 1) for k, layer in enumerate(self.aggregator_layers)]
-            h0q, offsets, zoff = self._residual_gemm(h0_planes, folds)
-            c0 = self.aggregator_layers[0].out_dim
-            h0_tab[rb:re, d:].copy_(h0q[:, zoff:zoff + c0])
+            # the z columns of the stacked GEMM land in the table directly (no copy between the two layouts)
+            h0q, offsets, zoff = self._residual_gemm(h0_planes, folds, z_out=h0_tab[rb:re, d:])
             extra = dict(combined=True, folds=folds, h0q=h0q, offsets=offsets, zoff=zoff)
         work = None
         if gather_h0:

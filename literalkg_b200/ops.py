@@ -205,10 +205,12 @@ def _planes_out(out_planes):
 
 
 def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor], activation: int = _lib.ACT_NONE,
-           out: Optional[torch.Tensor] = None, out_planes=None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, out_planes=None, out2: Optional[torch.Tensor] = None,
+           split_col: int = 0) -> torch.Tensor:
     """out = act([seg0 | seg1 | ...] @ weight^T + bias) on the tensor cores.  ``segments``: Planes / PlanesView
     of the A operand; ``weight``: fp32 [out_features, sum(k)] (nn.Linear layout), packed per call.
-    ``out_planes``: Planes whose scale record already bounds the result."""
+    ``out_planes``: Planes whose scale record already bounds the result.  ``out2`` / ``split_col``: the result columns
+    from ``split_col`` on are written to ``out2`` ([m, n - split_col] view) instead of ``out``."""
     wp = pack_weight(weight, segments)
     m, n = segments[0].rows, weight.shape[0]
     if out is None:
@@ -216,10 +218,14 @@ def linear(segments: Sequence, weight: torch.Tensor, bias: Optional[torch.Tensor
     a, b = _lib.planes_operand(segments), _lib.planes_operand([wp])
     if activation & _lib.ACT_ACCUMULATE:
         assert out is not None
+    if out2 is not None:
+        assert out2.dtype == torch.float32 and out2.stride(1) == 1 and tuple(out2.shape) == (m, n - split_col)
     with _dev_guard(weight, f"linear_k{weight.shape[1]}_n{n}"):
-        _lib.check(_lib.load().lkg_linear_fwd(C.byref(a), m, C.byref(b), n,
-                                              _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
-                                              out.data_ptr(), out.stride(0), *_planes_out(out_planes), _lib.stream()))
+        _lib.check(_lib.load().lkg_linear_fwd_split(C.byref(a), m, C.byref(b), n,
+                                                    _lib.ptr(None if bias is None else _lib.f32c(bias)), activation,
+                                                    out.data_ptr(), out.stride(0), _lib.ptr(out2),
+                                                    0 if out2 is None else out2.stride(0), int(split_col),
+                                                    *_planes_out(out_planes), _lib.stream()))
     return out
 
 

@@ -213,3 +213,23 @@ def test_split_planes_layouts(m, k, layout):
         ops.scale_finish(rec)
         assert torch.equal(rec[:3], pl.rec[:3])
         assert torch.equal(ops.split_planes(src, rec=rec).t, pl.t)
+
+
+@pytest.mark.parametrize("m,n,k,split", [(1000, 224, 300, 192), (257, 96, 64, 4), (4096, 272, 300, 256), (300, 40, 12, 36)])
+def test_linear_split_output(m, n, k, split):
+    """lkg_linear_fwd_split: the result columns from ``split`` on go to a second buffer with its own row stride (the
+    [h0 | z] table), bit-identical to the one-destination GEMM."""
+    from literalkg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    x = torch.randn(m, k, generator=g, device="cuda")
+    w = torch.randn(n, k, generator=g, device="cuda") / k ** 0.5
+    b = torch.randn(n, generator=g, device="cuda")
+    xp = ops.split_planes(x)
+    ref = ops.linear([xp], w, b, 0)
+    big = torch.full((m, n - split + 24), -7.0, device="cuda")
+    out = torch.full((m, n), -7.0, device="cuda")
+    ops.linear([xp], w, b, 0, out=out, out2=big[:, 8:8 + n - split], split_col=split)
+    assert torch.equal(out[:, :split], ref[:, :split]) and (out[:, split:] == -7.0).all()
+    assert torch.equal(big[:, 8:8 + n - split], ref[:, split:])
+    assert (big[:, :8] == -7.0).all() and (big[:, 8 + n - split:] == -7.0).all()
+    assert rel(ref, x.double() @ w.double().t() + b.double()) < TOL
